@@ -1,0 +1,407 @@
+/*  mcall_abi.cu -- the C-ABI of include/mcall_b200.h: context, host-built tables, the device entry
+ *  point (kernels enqueued on the caller's stream) and the host entry point (slabs double-buffered
+ *  H2D -> kernels -> D2H over two CUDA streams).
+ *
+ *  There is NO CPU fallback: without a CUDA device mcb_init fails with MCB_ENODEV.
+ */
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include <algorithm>
+#include "mcall_b200.h"
+#include "mcall_kernels.cuh"
+
+using namespace mcb;
+
+#define NCLASS 6                /* allele-count classes 1..5 + class 0 = everything else */
+#define MAX_STAGE 16
+
+struct HostSlab                 /* one half of the host-path double buffer */
+{
+    cudaStream_t stream = nullptr;
+    cudaEvent_t  done = nullptr;
+    void  *dev = nullptr;  size_t dev_bytes = 0;    /* one arena, carved per slab */
+    int32_t *lists = nullptr, *counts = nullptr;  int list_cap = 0;
+};
+
+struct mcb_ctx
+{
+    mcb_params p;
+    int device = 0, nsm = 0;
+    double theta_log = 0;
+    double pl2p[256];
+    DevTables *d_tab = nullptr;
+    uint8_t  *d_ploidy = nullptr;  int nploidy = 0, ploidy_cap = 0;  bool any_nondiploid = false;
+    std::vector<uint8_t> h_ploidy;
+    uint32_t *d_grp_off = nullptr, *d_grp_smpl = nullptr;
+    /* device-path scratch */
+    int32_t *d_lists = nullptr, *d_counts = nullptr;  int list_cap = 0;
+    HostSlab slab[2];
+    /* options */
+    int64_t opt_tile_bytes = 8192, opt_ring_bytes = 65536, opt_blocks_per_sm = 0, opt_slab_bytes = 256ll<<20;
+    /* stats */
+    int64_t stats[4] = {0,0,0,0};
+    std::string cuda_err;
+};
+
+static int cuda_fail(mcb_ctx *ctx, cudaError_t e, const char *what)
+{
+    if ( ctx )
+    {
+        char buf[512];
+        snprintf(buf, sizeof buf, "%s: %s", what, cudaGetErrorString(e));
+        ctx->cuda_err = buf;
+    }
+    return MCB_ECUDA;
+}
+#define CK(call) do { cudaError_t e_ = (call); if ( e_!=cudaSuccess ) return cuda_fail(ctx, e_, #call); } while (0)
+
+/* ---- host-built tables --------------------------------------------------------------------------- */
+static inline double gq_of(double x) { return -4.34294*log(x); }       /* mcall.c:877, host libm */
+static void build_tables(DevTables *t)
+{
+    for (int i=0; i<256; i++) t->pl2p[i] = pow(10., -i/10.);            /* mcall.c:56-61 */
+    for (int i=0; i<MCB_PL2P_BIG; i++) t->pl2p_big[i] = pow(10., -i/10.);  /* mcall.c:472 */
+    /*  gq_thr[k] = the largest double x in (0,1] with gq_of(x) >= k, found by bisection over the
+     *  (ordered) bit patterns of positive doubles.  GQ = max{k : x <= gq_thr[k]}, capped at 127.   */
+    t->gq_thr[0] = HUGE_VAL;
+    for (int k=1; k<128; k++)
+    {
+        uint64_t lo = 1, hi;                    /* lo: smallest denormal, gq ~ 3232 >= k */
+        double one = 1.0; memcpy(&hi, &one, 8); /* gq_of(1.0) = -0 < k */
+        while ( hi - lo > 1 )
+        {
+            uint64_t mid = lo + (hi-lo)/2;
+            double x; memcpy(&x, &mid, 8);
+            if ( gq_of(x) >= (double)k ) lo = mid; else hi = mid;
+        }
+        memcpy(&t->gq_thr[k], &lo, 8);
+    }
+}
+static double init_theta(double theta, const uint8_t *init_ploidy, int nsmpl)      /* mcall.c:397-416 */
+{
+    if ( !(theta>0) ) return theta;
+    int n = 0;
+    if ( !init_ploidy ) n = 2*nsmpl;
+    else for (int i=0; i<nsmpl; i++) n += init_ploidy[i];
+    double aM = 1;
+    for (int i=2; i<n; i++) aM += 1./i;
+    theta *= aM;
+    if ( theta >= 1 )
+    {
+        fprintf(stderr,"The prior is too big (theta*aM=%.2f), going with 0.99\n", theta);
+        theta = 0.99;
+    }
+    return log(theta);
+}
+
+/* ---- lifecycle ------------------------------------------------------------------------------------ */
+extern "C" int mcb_version(void) { return 100; }
+
+extern "C" const char *mcb_strerror(int code)
+{
+    switch ( code )
+    {
+        case MCB_OK:     return "ok";
+        case MCB_EINVAL: return "invalid argument";
+        case MCB_ENOMEM: return "out of memory";
+        case MCB_ECUDA:  return "CUDA error";
+        case MCB_ENODEV: return "no CUDA device (this library has no CPU fallback)";
+        case MCB_EPL:    return "Wrong number of PL fields";
+        case MCB_EQS:    return "The QS annotation not present / FORMAT/AD required with -G";
+        case MCB_EPRIOR: return "Incorrect prior AN,AC values";
+    }
+    return "unknown error";
+}
+extern "C" const char *mcb_last_cuda_error(const mcb_ctx *ctx) { return ctx ? ctx->cuda_err.c_str() : ""; }
+extern "C" double mcb_get_theta(const mcb_ctx *ctx) { return ctx->theta_log; }
+extern "C" int mcb_get_pl2p(const mcb_ctx *ctx, double *out) { memcpy(out, ctx->pl2p, sizeof(double)*256); return 0; }
+extern "C" int mcb_get_stats(const mcb_ctx *ctx, int64_t stats[4]) { memcpy(stats, ctx->stats, sizeof(int64_t)*4); return 0; }
+
+extern "C" int mcb_set_option(mcb_ctx *ctx, const char *key, int64_t value)
+{
+    if ( !ctx || !key ) return MCB_EINVAL;
+    if ( !strcmp(key,"tile_bytes") )         ctx->opt_tile_bytes = value;
+    else if ( !strcmp(key,"ring_bytes") )    ctx->opt_ring_bytes = value;
+    else if ( !strcmp(key,"blocks_per_sm") ) ctx->opt_blocks_per_sm = value;
+    else if ( !strcmp(key,"slab_bytes") )    ctx->opt_slab_bytes = value;
+    else return MCB_EINVAL;
+    return MCB_OK;
+}
+
+static int upload_ploidy(mcb_ctx *ctx)
+{
+    int S = ctx->p.nsmpl;
+    if ( ctx->nploidy > ctx->ploidy_cap )
+    {
+        if ( ctx->d_ploidy ) cudaFree(ctx->d_ploidy);
+        ctx->ploidy_cap = std::max(4, 2*ctx->nploidy);
+        CK(cudaMalloc(&ctx->d_ploidy, (size_t)ctx->ploidy_cap*S));
+    }
+    CK(cudaMemcpy(ctx->d_ploidy, ctx->h_ploidy.data(), (size_t)ctx->nploidy*S, cudaMemcpyHostToDevice));
+    ctx->any_nondiploid = false;
+    for (size_t i=0; i<ctx->h_ploidy.size(); i++) if ( ctx->h_ploidy[i]!=2 ) { ctx->any_nondiploid = true; break; }
+    return MCB_OK;
+}
+
+extern "C" int mcb_init(mcb_ctx **out, const mcb_params *params)
+{
+    if ( !out || !params || params->nsmpl<=0 || params->max_nals<1 || params->max_nals>MCB_MAX_NALS ) return MCB_EINVAL;
+    if ( params->output_tags & MCB_CALL_FMT_GP ) return MCB_EINVAL;     /* FORMAT/GP output: not in this build yet */
+    if ( params->ngroups > 1 ) return MCB_EINVAL;                       /* -G groups: not in this build yet */
+    int ndev = 0;
+    if ( cudaGetDeviceCount(&ndev)!=cudaSuccess || ndev<=0 ) return MCB_ENODEV;
+    if ( params->device<0 || params->device>=ndev ) return MCB_EINVAL;
+    mcb_ctx *ctx = new mcb_ctx();
+    ctx->p = *params;
+    ctx->p.init_ploidy = nullptr; ctx->p.grp_off = nullptr; ctx->p.grp_smpl = nullptr;
+    if ( !(ctx->p.tie_eps > 0) ) ctx->p.tie_eps = 1e-6;
+    ctx->device = params->device;
+    *out = ctx;
+    CK(cudaSetDevice(ctx->device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, ctx->device));
+    ctx->nsm = prop.multiProcessorCount;
+    ctx->theta_log = init_theta(params->theta, params->init_ploidy, params->nsmpl);
+
+    DevTables *t = new DevTables();
+    build_tables(t);
+    memcpy(ctx->pl2p, t->pl2p, sizeof ctx->pl2p);
+    cudaError_t e = cudaMalloc(&ctx->d_tab, sizeof(DevTables));
+    if ( e==cudaSuccess ) e = cudaMemcpy(ctx->d_tab, t, sizeof(DevTables), cudaMemcpyHostToDevice);
+    delete t;
+    if ( e!=cudaSuccess ) return cuda_fail(ctx, e, "tables");
+
+    ctx->h_ploidy.assign(params->nsmpl, 2);     /* id 0: all diploid */
+    ctx->nploidy = 1;
+    int rc = upload_ploidy(ctx);
+    if ( rc ) return rc;
+    CK(cudaMalloc(&ctx->d_counts, sizeof(int32_t)*NCLASS));
+    for (int i=0; i<2; i++)
+    {
+        CK(cudaStreamCreateWithFlags(&ctx->slab[i].stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&ctx->slab[i].done, cudaEventDisableTiming));
+        CK(cudaMalloc(&ctx->slab[i].counts, sizeof(int32_t)*NCLASS));
+    }
+    return MCB_OK;
+}
+
+extern "C" void mcb_destroy(mcb_ctx *ctx)
+{
+    if ( !ctx ) return;
+    cudaSetDevice(ctx->device);
+    cudaFree(ctx->d_tab); cudaFree(ctx->d_ploidy); cudaFree(ctx->d_grp_off); cudaFree(ctx->d_grp_smpl);
+    cudaFree(ctx->d_lists); cudaFree(ctx->d_counts);
+    for (int i=0; i<2; i++)
+    {
+        if ( ctx->slab[i].stream ) cudaStreamDestroy(ctx->slab[i].stream);
+        if ( ctx->slab[i].done ) cudaEventDestroy(ctx->slab[i].done);
+        cudaFree(ctx->slab[i].dev); cudaFree(ctx->slab[i].lists); cudaFree(ctx->slab[i].counts);
+    }
+    delete ctx;
+}
+
+extern "C" int mcb_set_ploidy(mcb_ctx *ctx, int id, const uint8_t *ploidy)
+{
+    if ( !ctx || id<0 || id>65535 || !ploidy ) return MCB_EINVAL;
+    int S = ctx->p.nsmpl;
+    for (int i=0; i<S; i++) if ( ploidy[i]>2 ) return MCB_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    if ( id >= ctx->nploidy )
+    {
+        ctx->h_ploidy.resize((size_t)(id+1)*S, 2);
+        ctx->nploidy = id+1;
+    }
+    memcpy(ctx->h_ploidy.data() + (size_t)id*S, ploidy, S);
+    CK(cudaDeviceSynchronize());
+    return upload_ploidy(ctx);
+}
+
+extern "C" void *mcb_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if ( cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault)!=cudaSuccess ) return nullptr;
+    return p;
+}
+extern "C" void mcb_host_free(void *ptr) { if ( ptr ) cudaFreeHost(ptr); }
+
+/* ---- launch geometry -------------------------------------------------------------------------------- */
+static void tile_geometry(const mcb_ctx *ctx, int nals, int *tile_smpl, int *nstage, size_t *ring_bytes)
+{
+    int G = nals*(nals+1)/2, S = ctx->p.nsmpl;
+    int ts = (int)(ctx->opt_tile_bytes/(4*G));
+    ts = std::max(256, ts/256*256);
+    int ntiles = (S + ts - 1)/ts;
+    size_t tile_bytes = (size_t)ts*G*4;
+    int cap = (int)std::max<int64_t>(2, ctx->opt_ring_bytes/(int64_t)tile_bytes);
+    int ns = std::min(MAX_STAGE, std::min(ntiles, cap));
+    if ( ns<1 ) ns = 1;
+    *tile_smpl = ts; *nstage = ns; *ring_bytes = tile_bytes*ns;
+}
+
+static int enqueue(mcb_ctx *ctx, const mcb_batch *b, const mcb_result *r, int32_t *lists, int32_t *counts, int list_stride, cudaStream_t st)
+{
+    CK(cudaMemsetAsync(counts, 0, sizeof(int32_t)*NCLASS, st));
+    CK(launch_classify(b->nals, b->nsites, lists, counts, list_stride, st));
+    int launches = 1;
+    KArgs a;
+    memset(&a, 0, sizeof a);
+    a.pl = b->pl; a.pl_off = b->pl_off; a.nals = b->nals; a.unseen = b->unseen; a.ploidy_id = b->ploidy_id;
+    a.qs = b->qs; a.nqs = b->nqs; a.ad = b->ad; a.ad_off = b->ad_off; a.nad = b->nad;
+    a.prior_an = b->prior_an; a.prior_ac = b->prior_ac;
+    a.ret = r->ret; a.als_new = r->als_new; a.als_map = r->als_map; a.qual = r->qual; a.ac = r->ac; a.an = r->an;
+    a.site_flags = r->site_flags; a.diag = r->diag; a.gt = r->gt; a.gq = r->gq; a.gp = r->gp; a.out_pl = r->pl;
+    a.tab = ctx->d_tab; a.ploidy_tab = ctx->d_ploidy; a.nploidy = ctx->nploidy;
+    a.nsmpl = ctx->p.nsmpl; a.max_nals = ctx->p.max_nals; a.flag = ctx->p.flag; a.output_tags = ctx->p.output_tags;
+    a.theta = ctx->theta_log; a.tie_eps = ctx->p.tie_eps; a.use_prior = ctx->p.use_prior;
+    const bool ploidy = ctx->any_nondiploid;
+    for (int nals=1; nals<=5; nals++)
+    {
+        size_t ring; tile_geometry(ctx, nals, &a.tile_smpl, &a.nstage, &ring);
+        a.site_list = lists + (size_t)nals*list_stride; a.site_count = counts + nals;
+        int nb = 1;
+        CK(site_kernel_occupancy(nals, ploidy, ring, &nb));
+        if ( nb<1 ) return cuda_fail(ctx, cudaErrorLaunchOutOfResources, "site kernel does not fit on an SM");
+        if ( ctx->opt_blocks_per_sm>0 ) nb = std::min<int>(nb, (int)ctx->opt_blocks_per_sm);
+        int grid = (int)std::min<int64_t>((int64_t)b->nsites, (int64_t)ctx->nsm*nb);
+        CK(launch_site_kernel(nals, ploidy, a, grid, ring, st));
+        launches++;
+    }
+    CK(launch_unsupported(lists, counts, r->ret, r->site_flags, b->nals, st));
+    launches++;
+    ctx->stats[0] += launches;
+    ctx->stats[1] += b->nsites;
+    return MCB_OK;
+}
+
+extern "C" int mcb_call_device(mcb_ctx *ctx, const mcb_batch *b, const mcb_result *r, void *cuda_stream)
+{
+    if ( !ctx || !b || !r || !r->ret || b->nsites<0 || !b->pl || !b->pl_off || !b->nals ) return MCB_EINVAL;
+    if ( b->nsites==0 ) return MCB_OK;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t) cuda_stream;
+    if ( b->nsites > ctx->list_cap )
+    {
+        CK(cudaStreamSynchronize(st));
+        if ( ctx->d_lists ) CK(cudaFree(ctx->d_lists));
+        ctx->list_cap = b->nsites;
+        CK(cudaMalloc(&ctx->d_lists, sizeof(int32_t)*(size_t)NCLASS*ctx->list_cap));
+    }
+    ctx->stats[0] = ctx->stats[1] = 0;
+    return enqueue(ctx, b, r, ctx->d_lists, ctx->d_counts, ctx->list_cap, st);
+}
+
+/* ---- host path: slabs double-buffered over two streams ---------------------------------------------- */
+static inline size_t pad256(size_t n) { return (n + 255) & ~(size_t)255; }
+
+extern "C" int mcb_call_host(mcb_ctx *ctx, const mcb_batch *b, const mcb_result *r)
+{
+    if ( !ctx || !b || !r || !r->ret || b->nsites<0 || !b->pl || !b->pl_off || !b->nals ) return MCB_EINVAL;
+    if ( b->nsites==0 ) return MCB_OK;
+    CK(cudaSetDevice(ctx->device));
+    const int S = ctx->p.nsmpl, M = ctx->p.max_nals, R = b->nsites;
+    ctx->stats[0] = ctx->stats[1] = 0;
+
+    /* per-site PL extents (host knows nals) and a monotonicity check: slabs copy one contiguous PL range */
+    std::vector<int64_t> ext(R);
+    for (int i=0; i<R; i++)
+    {
+        int n = b->nals[i];
+        ext[i] = (( (int64_t)S*n*(n+1)/2 ) + 3) & ~(int64_t)3;
+        if ( (b->pl_off[i] & 3) || (i && b->pl_off[i] < b->pl_off[i-1] + ext[i-1]) ) return MCB_EINVAL;
+    }
+    const bool want_pl = r->pl != nullptr, want_gt = r->gt != nullptr;
+    const bool want_gq = r->gq && (ctx->p.output_tags & (MCB_CALL_FMT_GQ|MCB_CALL_FMT_GP));
+
+    int beg = 0, islab = 0;
+    while ( beg < R )
+    {
+        /* slab = as many sites as fit opt_slab_bytes of PL */
+        int end = beg; int64_t pl_ints = 0;
+        while ( end < R && (end==beg || (pl_ints + ext[end])*4 <= ctx->opt_slab_bytes) ) { pl_ints = b->pl_off[end] + ext[end] - b->pl_off[beg]; end++; }
+        const int n = end - beg;
+        HostSlab &sl = ctx->slab[islab & 1];
+        CK(cudaEventSynchronize(sl.done));      /* previous use of this half finished (event starts signalled) */
+
+        /* carve the arena */
+        size_t off = 0;
+        auto carve = [&](size_t bytes) { size_t o = off; off += pad256(bytes); return o; };
+        size_t o_pl = carve((size_t)pl_ints*4), o_plout = want_pl ? carve((size_t)pl_ints*4) : 0;
+        size_t o_ploff = carve(sizeof(int64_t)*n), o_nals = carve(n), o_unseen = carve(n), o_pid = carve(2*(size_t)n);
+        size_t o_qs = carve(sizeof(float)*(size_t)n*M), o_nqs = carve(n);
+        size_t o_pan = carve(sizeof(int32_t)*n), o_pac = carve(sizeof(int32_t)*(size_t)n*M);
+        size_t o_ret = carve(4*(size_t)n), o_als = carve(4*(size_t)n), o_map = carve((size_t)n*M), o_qual = carve(4*(size_t)n);
+        size_t o_ac = carve(4*(size_t)n*M), o_an = carve(4*(size_t)n), o_fl = carve(4*(size_t)n), o_diag = carve(32*(size_t)n);
+        size_t o_gt = want_gt ? carve(8*(size_t)n*S) : 0, o_gq = want_gq ? carve(4*(size_t)n*S) : 0;
+        if ( off > sl.dev_bytes )
+        {
+            if ( sl.dev ) CK(cudaFree(sl.dev));
+            sl.dev_bytes = off + off/8;
+            CK(cudaMalloc(&sl.dev, sl.dev_bytes));
+        }
+        if ( n > sl.list_cap )
+        {
+            if ( sl.lists ) CK(cudaFree(sl.lists));
+            sl.list_cap = n + n/8;
+            CK(cudaMalloc(&sl.lists, sizeof(int32_t)*(size_t)NCLASS*sl.list_cap));
+        }
+        char *base = (char*) sl.dev;
+        cudaStream_t st = sl.stream;
+        const int64_t pl0 = b->pl_off[beg];
+#define H2D(dst,src,bytes) CK(cudaMemcpyAsync(base+(dst), (src), (bytes), cudaMemcpyHostToDevice, st))
+        H2D(o_pl, b->pl + pl0, (size_t)pl_ints*4);
+        H2D(o_ploff, b->pl_off + beg, sizeof(int64_t)*n);
+        H2D(o_nals, b->nals + beg, n);
+        if ( b->unseen ) H2D(o_unseen, b->unseen + beg, n);
+        if ( b->ploidy_id ) H2D(o_pid, b->ploidy_id + beg, 2*(size_t)n);
+        if ( b->qs ) H2D(o_qs, b->qs + (size_t)beg*M, sizeof(float)*(size_t)n*M);
+        if ( b->nqs ) H2D(o_nqs, b->nqs + beg, n);
+        if ( b->prior_an ) H2D(o_pan, b->prior_an + beg, sizeof(int32_t)*n);
+        if ( b->prior_ac ) H2D(o_pac, b->prior_ac + (size_t)beg*M, sizeof(int32_t)*(size_t)n*M);
+#undef H2D
+        /* device views: pl pointers are biased by -pl0 so that the absolute pl_off[] stay valid */
+        mcb_batch db; memset(&db, 0, sizeof db);
+        db.nsites = n;
+        db.pl = (const int32_t*)(base+o_pl) - pl0; db.pl_off = (const int64_t*)(base+o_ploff);
+        db.nals = (const uint8_t*)(base+o_nals);
+        db.unseen = b->unseen ? (const uint8_t*)(base+o_unseen) : nullptr;
+        db.ploidy_id = b->ploidy_id ? (const uint16_t*)(base+o_pid) : nullptr;
+        db.qs = b->qs ? (const float*)(base+o_qs) : nullptr;
+        db.nqs = b->nqs ? (const uint8_t*)(base+o_nqs) : nullptr;
+        db.prior_an = b->prior_an ? (const int32_t*)(base+o_pan) : nullptr;
+        db.prior_ac = b->prior_ac ? (const int32_t*)(base+o_pac) : nullptr;
+        mcb_result dr; memset(&dr, 0, sizeof dr);
+        dr.ret = (int32_t*)(base+o_ret); dr.als_new = (uint32_t*)(base+o_als); dr.als_map = (int8_t*)(base+o_map);
+        dr.qual = (float*)(base+o_qual); dr.ac = (int32_t*)(base+o_ac); dr.an = (int32_t*)(base+o_an);
+        dr.site_flags = (uint32_t*)(base+o_fl); dr.diag = (double*)(base+o_diag);
+        dr.gt = want_gt ? (int32_t*)(base+o_gt) : nullptr;
+        dr.gq = want_gq ? (int32_t*)(base+o_gq) : nullptr;
+        dr.pl = want_pl ? (int32_t*)(base+o_plout) - pl0 : nullptr;
+
+        int rc = enqueue(ctx, &db, &dr, sl.lists, sl.counts, sl.list_cap, st);
+        if ( rc ) return rc;
+
+#define D2H(dst,src,bytes) CK(cudaMemcpyAsync((dst), base+(src), (bytes), cudaMemcpyDeviceToHost, st))
+        D2H(r->ret + beg, o_ret, 4*(size_t)n);
+        if ( r->als_new ) D2H(r->als_new + beg, o_als, 4*(size_t)n);
+        if ( r->als_map ) D2H(r->als_map + (size_t)beg*M, o_map, (size_t)n*M);
+        if ( r->qual ) D2H(r->qual + beg, o_qual, 4*(size_t)n);
+        if ( r->ac ) D2H(r->ac + (size_t)beg*M, o_ac, 4*(size_t)n*M);
+        if ( r->an ) D2H(r->an + beg, o_an, 4*(size_t)n);
+        if ( r->site_flags ) D2H(r->site_flags + beg, o_fl, 4*(size_t)n);
+        if ( r->diag ) D2H(r->diag + (size_t)beg*4, o_diag, 32*(size_t)n);
+        if ( want_gt ) D2H(r->gt + (size_t)beg*S*2, o_gt, 8*(size_t)n*S);
+        if ( want_gq ) D2H(r->gq + (size_t)beg*S, o_gq, 4*(size_t)n*S);
+        if ( want_pl ) D2H(r->pl + pl0, o_plout, (size_t)pl_ints*4);
+#undef D2H
+        CK(cudaEventRecord(sl.done, st));
+        beg = end; islab++;
+    }
+    CK(cudaStreamSynchronize(ctx->slab[0].stream));
+    CK(cudaStreamSynchronize(ctx->slab[1].stream));
+    return MCB_OK;
+}

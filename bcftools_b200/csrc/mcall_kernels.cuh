@@ -1,0 +1,87 @@
+/*  mcall_kernels.cuh -- sm_100a kernels of the B200-native `call -m` hot path.
+ *
+ *  One CTA owns one site (record).  A site's FORMAT/PL block ([nsmpl][G] int32, contiguous) is moved
+ *  into shared memory by the bulk-copy engine (cp.async.bulk + mbarrier, "TMA 1-D") in tiles of
+ *  TILE samples through an NSTAGE ring, and is consumed twice by the same CTA:
+ *
+ *    phase 1  "site reduction"   = set_pdg (mcall.c:451-544) + mcall_find_best_alleles (mcall.c:591-710)
+ *                                   + QUAL candidates (mcall.c:1546-1561) + trimming maps (mcall.c:547-570)
+ *    phase 2  "per-sample genotype" = mcall_call_genotypes incl. GQ (mcall.c:745-886),
+ *                                   mcall_set_ref_genotypes (mcall.c:713-743), mcall_trim_and_update_PLs
+ *                                   (mcall.c:1158-1194), AC/AN and the final QUAL (mcall.c:1631-1650)
+ *
+ *  When the whole site fits in the ring the second pass re-reads shared memory; otherwise the tiles are
+ *  fetched again and hit L2 (the CTA read them microseconds earlier), so HBM sees each PL byte once.
+ *
+ *  Numerics (DESIGN.md "numerics"):
+ *    phase 2 is a literal FP64 transcription (IEEE divide, no FMA contraction, float32 round trip of
+ *    every GP, float32 qsum) => GT / AC / AN / trimmed PL / GQ are bit-exact versus the reference.
+ *    GQ's -4.34294*log(1-max/sum) is evaluated with a 127-entry threshold table built on the HOST
+ *    with the host libm, so it reproduces glibc's log() rounding instead of CUDA's.
+ *    phase 1 replaces "one log() per sample per allele set" by exponent-tracked running products
+ *    (one log per allele set per site) and folds the per-sample normaliser 1/sum out of the loop;
+ *    the single-allele sets are exact integer PL sums.  Likelihood totals agree with the reference
+ *    to ~1e-11 absolute (the reference's own rounding noise is ~1e-10); QUAL within 1e-6 relative;
+ *    allele-set near-ties (gap < tie_eps) are flagged per site (MCB_SITE_NEAR_TIE).
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "mcall_b200.h"
+
+namespace mcb {
+
+#define MCB_PL2P_BIG 3300           /* host-built pow(10,-i/10) for i<3300; beyond that glibc's pow() underflows to 0 */
+
+struct DevTables
+{
+    double pl2p[256];               /* call->pl2p, built on the host with glibc pow (mcall.c:56-61) */
+    double gq_thr[128];             /* gq_thr[k] = largest x with (int)(-4.34294*log(x)) >= k, host libm (mcall.c:877) */
+    double pl2p_big[MCB_PL2P_BIG];  /* same function for PL >= 256 (mcall.c:472), rare path, read from global */
+};
+
+struct KArgs
+{
+    /* batch (device pointers) */
+    const int32_t  *pl;  const int64_t *pl_off;  const uint8_t *nals;  const uint8_t *unseen;
+    const uint16_t *ploidy_id;  const float *qs;  const uint8_t *nqs;
+    const int32_t  *ad;  const int64_t *ad_off;  const uint8_t *nad;
+    const int32_t  *prior_an;  const int32_t *prior_ac;
+    /* result (device pointers, may be NULL) */
+    int32_t *ret;  uint32_t *als_new;  int8_t *als_map;  float *qual;  int32_t *ac;  int32_t *an;
+    uint32_t *site_flags;  double *diag;  int32_t *gt;  int32_t *gq;  float *gp;  int32_t *out_pl;
+    /* context */
+    const DevTables *tab;
+    const uint8_t *ploidy_tab;  int nploidy;
+    const uint32_t *grp_off;  const uint32_t *grp_smpl;  int ngroups;
+    const int32_t *site_list;  const int32_t *site_count;      /* the sites of this allele-count class */
+    int nsmpl, max_nals;
+    uint32_t flag, output_tags;
+    double theta, tie_eps;
+    int use_prior;
+    int tile_smpl, nstage;
+};
+
+/*  Per-site decision record shared between the two phases (shared memory).  */
+struct SiteState
+{
+    double   q[MCB_MAX_NALS];       /* group qsum widened to double: (double)(float) */
+    double   max_qual, lk_sum, ref_lk, gap;
+    uint32_t grp_als;               /* the group's own best allele set (mcall.c:706) */
+    uint32_t als_new;               /* union | REF | -A (mcall.c:1552-1574) */
+    int      grp_nals, nals_new, is_variant, ret_early;
+    uint32_t flags;
+    int8_t   als_map[MCB_MAX_NALS];
+    int16_t  pl_map[MCB_MAX_NALS*(MCB_MAX_NALS+1)/2 > 64 ? 64 : MCB_MAX_NALS*(MCB_MAX_NALS+1)/2];
+    int      ac[MCB_MAX_NALS];
+};
+
+}   // namespace mcb
+
+namespace mcb {
+/*  launchers implemented in mcall_kernels.cu  */
+cudaError_t launch_site_kernel(int nals, bool ploidy, const KArgs &a, int grid, size_t ring_bytes, cudaStream_t st);
+cudaError_t launch_classify(const uint8_t *nals, int nsites, int32_t *lists, int32_t *counts, int list_stride, cudaStream_t st);
+cudaError_t launch_unsupported(const int32_t *list, const int32_t *count, int32_t *ret, uint32_t *site_flags, const uint8_t *nals, cudaStream_t st);
+cudaError_t site_kernel_occupancy(int nals, bool ploidy, size_t ring_bytes, int *blocks_per_sm);
+}

@@ -1,0 +1,140 @@
+"""Thin ctypes wrapper over the C-ABI (include/mcall_b200.h) -- used by tests and bench.py.
+
+It mirrors the reference's hook trio (call.h:131-147): `MCaller(params)` = mcall_init,
+`MCaller.call_host / call_device` = mcall over a batch of records, `MCaller.close` = mcall_destroy.
+No computation happens in Python and there is no fallback: a missing library or a missing GPU raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libmcall_b200.so")
+_lib = None
+
+EXPORTS = ["mcb_init", "mcb_destroy", "mcb_set_ploidy", "mcb_call_device", "mcb_call_host", "mcb_host_alloc",
+           "mcb_host_free", "mcb_strerror", "mcb_last_cuda_error", "mcb_get_theta", "mcb_get_pl2p", "mcb_get_stats",
+           "mcb_set_option", "mcb_version"]
+
+
+class McallError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load libmcall_b200.so (building it in-tree if the sources are newer).  Raises if unavailable."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            from . import build
+            build.build()
+        L = C.CDLL(_LIB_PATH)
+        L.mcb_init.restype = C.c_int
+        L.mcb_init.argtypes = [C.POINTER(C.c_void_p), C.POINTER(abi.McbParams)]
+        L.mcb_destroy.restype = None
+        L.mcb_destroy.argtypes = [C.c_void_p]
+        L.mcb_set_ploidy.restype = C.c_int
+        L.mcb_set_ploidy.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.mcb_call_device.restype = C.c_int
+        L.mcb_call_device.argtypes = [C.c_void_p, C.POINTER(abi.McbBatch), C.POINTER(abi.McbResult), C.c_void_p]
+        L.mcb_call_host.restype = C.c_int
+        L.mcb_call_host.argtypes = [C.c_void_p, C.POINTER(abi.McbBatch), C.POINTER(abi.McbResult)]
+        L.mcb_host_alloc.restype = C.c_void_p
+        L.mcb_host_alloc.argtypes = [C.c_size_t]
+        L.mcb_host_free.restype = None
+        L.mcb_host_free.argtypes = [C.c_void_p]
+        L.mcb_strerror.restype = C.c_char_p
+        L.mcb_strerror.argtypes = [C.c_int]
+        L.mcb_last_cuda_error.restype = C.c_char_p
+        L.mcb_last_cuda_error.argtypes = [C.c_void_p]
+        L.mcb_get_theta.restype = C.c_double
+        L.mcb_get_theta.argtypes = [C.c_void_p]
+        L.mcb_get_pl2p.restype = C.c_int
+        L.mcb_get_pl2p.argtypes = [C.c_void_p, C.c_void_p]
+        L.mcb_get_stats.restype = C.c_int
+        L.mcb_get_stats.argtypes = [C.c_void_p, C.c_void_p]
+        L.mcb_set_option.restype = C.c_int
+        L.mcb_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int64]
+        L.mcb_version.restype = C.c_int
+        _lib = L
+    return _lib
+
+
+class MCaller:
+    def __init__(self, params, ploidy_tab=None, options=None):
+        self.params = params
+        self._ctx = C.c_void_p()
+        L = lib()
+        p = params.c_struct()
+        rc = L.mcb_init(C.byref(self._ctx), C.byref(p))
+        if rc != 0:
+            msg = L.mcb_strerror(rc).decode()
+            if self._ctx:
+                msg += " / " + L.mcb_last_cuda_error(self._ctx).decode()
+                L.mcb_destroy(self._ctx)
+                self._ctx = C.c_void_p()
+            raise McallError(f"mcb_init failed: {msg}")
+        if ploidy_tab is not None:
+            tab = np.ascontiguousarray(ploidy_tab, np.uint8).reshape(-1, params.nsmpl)
+            for i in range(tab.shape[0]):
+                self.set_ploidy(i, tab[i])
+        for k, v in (options or {}).items():
+            self.set_option(k, v)
+
+    def _check(self, rc, what):
+        if rc != 0:
+            L = lib()
+            raise McallError(f"{what} failed: {L.mcb_strerror(rc).decode()} / {L.mcb_last_cuda_error(self._ctx).decode()}")
+
+    def set_ploidy(self, idx, ploidy):
+        v = np.ascontiguousarray(ploidy, np.uint8)
+        assert v.size == self.params.nsmpl
+        self._check(lib().mcb_set_ploidy(self._ctx, int(idx), v.ctypes.data), "mcb_set_ploidy")
+
+    def set_option(self, key, value):
+        self._check(lib().mcb_set_option(self._ctx, key.encode(), int(value)), f"mcb_set_option({key})")
+
+    @property
+    def theta(self):
+        return lib().mcb_get_theta(self._ctx)
+
+    def pl2p(self):
+        out = np.zeros(256, np.float64)
+        lib().mcb_get_pl2p(self._ctx, out.ctypes.data)
+        return out
+
+    def stats(self):
+        out = np.zeros(4, np.int64)
+        lib().mcb_get_stats(self._ctx, out.ctypes.data)
+        return out
+
+    def call_host(self, batch, result=None, want_gp=False):
+        """mcb_call_host on numpy (host) arrays; returns an abi.HostResult."""
+        res = result if result is not None else abi.HostResult(batch, want_gp=want_gp)
+        b, r = batch.c_struct(), res.c_struct()
+        self._check(lib().mcb_call_host(self._ctx, C.byref(b), C.byref(r)), "mcb_call_host")
+        return res
+
+    def call_device(self, batch_struct, result_struct, stream=0):
+        """mcb_call_device on already-built McbBatch/McbResult structs holding DEVICE pointers."""
+        self._check(lib().mcb_call_device(self._ctx, C.byref(batch_struct), C.byref(result_struct), C.c_void_p(stream)),
+                    "mcb_call_device")
+
+    def close(self):
+        if self._ctx:
+            lib().mcb_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

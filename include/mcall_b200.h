@@ -61,6 +61,9 @@ extern "C" {
 #define MCB_SITE_UNSEEN_SEL   (1u<<2)   /* the unseen allele <*> was selected: reference behaviour undefined */
 #define MCB_SITE_TOO_MANY_ALS (1u<<3)   /* n_allele > 32: skipped (mcall.c:1539-1543) */
 #define MCB_SITE_NO_QS        (1u<<4)   /* nqs<=0: reference would error() out (mcall.c:1457) */
+#define MCB_SITE_PL_RANGE      (1u<<6)   /* a PL > 2500 was seen: likelihoods underflow, parity with the reference not guaranteed */
+#define MCB_SITE_BAD_PRIOR     (1u<<7)   /* -F: AN < sum(AC); the reference error()s out (mcall.c:1523) */
+#define MCB_SITE_UNSUPPORTED   (1u<<8)   /* site shape not covered by the device kernels (n_allele==0) */
 #define MCB_SITE_REF_GT       (1u<<5)   /* genotypes come from mcall_set_ref_genotypes (mcall.c:1582,1587): no GQ/GP written */
 
 typedef struct mcb_ctx mcb_ctx;     /* opaque; one per GPU, used from one host thread (like call_t) */

@@ -1,0 +1,20 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def oracle_built():
+    """Compile the CPU oracles once (plain-C restatement; the compiled reference only where /root/reference exists)."""
+    from oracle import pyoracle
+    pyoracle.build()
+    return pyoracle
