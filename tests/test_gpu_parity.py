@@ -64,3 +64,17 @@ def test_empty_batch():
     with mcall.MCaller(params) as mc:
         res = mc.call_host(batch)
     assert res.ret.size == 0
+
+
+from tests import golden_util  # noqa: E402
+
+
+@pytest.mark.parametrize("name", golden_util.case_names())
+def test_cuda_reproduces_reference_goldens(name):
+    """The CUDA path against the reference's own golden records (tests/golden, from test/test.pl:276-308)."""
+    from bcftools_b200 import mcall
+    params, batch, tab, case = golden_util.load_case(name)
+    want_gp = bool(params.output_tags & abi.CALL_FMT_GP)
+    with mcall.MCaller(params, ploidy_tab=tab) as mc:
+        res = mc.call_host(batch, want_gp=want_gp)
+    assert golden_util.check_against_expect(case, params, batch, res) == len(case["expect"])
