@@ -23,6 +23,18 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def build_variant(out_path, defines, verbose=False):
+    """Experimental builds with extra -D flags (scripts/ use this for register-cap sweeps)."""
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + ["-D" + d for d in defines] + ["-shared", "-o", out_path] + [os.path.join(CSRC, s) for s in SOURCES]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or r.returncode:
+        sys.stderr.write(r.stdout + r.stderr)
+    if r.returncode:
+        raise RuntimeError("nvcc failed building " + out_path)
+    return out_path
+
+
 def build(force=False, verbose=False):
     if not force and not _stale():
         return LIB

@@ -42,7 +42,7 @@ struct mcb_ctx
     int32_t *d_lists = nullptr, *d_counts = nullptr;  int list_cap = 0;
     HostSlab slab[2];
     /* options */
-    int64_t opt_tile_bytes = 8192, opt_ring_bytes = 65536, opt_blocks_per_sm = 0, opt_slab_bytes = 256ll<<20;
+    int64_t opt_tile_bytes = 8192, opt_ring_bytes = 65536, opt_blocks_per_sm = 0, opt_slab_bytes = 256ll<<20, opt_block = 256;
     /* stats */
     int64_t stats[4] = {0,0,0,0};
     std::string cuda_err;
@@ -129,6 +129,7 @@ extern "C" int mcb_set_option(mcb_ctx *ctx, const char *key, int64_t value)
     else if ( !strcmp(key,"ring_bytes") )    ctx->opt_ring_bytes = value;
     else if ( !strcmp(key,"blocks_per_sm") ) ctx->opt_blocks_per_sm = value;
     else if ( !strcmp(key,"slab_bytes") )    ctx->opt_slab_bytes = value;
+    else if ( !strcmp(key,"block") )         { if ( value!=128 && value!=256 ) return MCB_EINVAL; ctx->opt_block = value; }
     else return MCB_EINVAL;
     return MCB_OK;
 }
@@ -151,7 +152,6 @@ static int upload_ploidy(mcb_ctx *ctx)
 extern "C" int mcb_init(mcb_ctx **out, const mcb_params *params)
 {
     if ( !out || !params || params->nsmpl<=0 || params->max_nals<1 || params->max_nals>MCB_MAX_NALS ) return MCB_EINVAL;
-    if ( params->output_tags & MCB_CALL_FMT_GP ) return MCB_EINVAL;     /* FORMAT/GP output: not in this build yet */
     if ( params->ngroups > 1 ) return MCB_EINVAL;                       /* -G groups: not in this build yet */
     int ndev = 0;
     if ( cudaGetDeviceCount(&ndev)!=cudaSuccess || ndev<=0 ) return MCB_ENODEV;
@@ -229,12 +229,33 @@ extern "C" void *mcb_host_alloc(size_t bytes)
 }
 extern "C" void mcb_host_free(void *ptr) { if ( ptr ) cudaFreeHost(ptr); }
 
+/*  Self-test of the shared-reciprocal division used by phase 2 (see rcp_shared/div_shared in mcall_kernels.cu):
+ *  mode 0 = exhaustive biallelic domain (256^3 PL triples), mode 6/10/15 = n random multi-allelic vectors.
+ *  Writes the number of quotients that differ from IEEE a/b; must be 0.                                     */
+extern "C" int mcb_selftest_div(mcb_ctx *ctx, int mode, uint64_t n, uint64_t seed, uint64_t *mismatch)
+{
+    if ( !ctx || !mismatch ) return MCB_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    unsigned long long *d = nullptr;
+    CK(cudaMalloc(&d, 8));
+    CK(cudaMemset(d, 0, 8));
+    if ( mode==0 ) n = 1ull<<24;
+    CK(launch_selftest_div(ctx->d_tab, mode, n, seed, d, 0));
+    CK(cudaDeviceSynchronize());
+    unsigned long long h = 0;
+    CK(cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    *mismatch = h;
+    return MCB_OK;
+}
+
 /* ---- launch geometry -------------------------------------------------------------------------------- */
 static void tile_geometry(const mcb_ctx *ctx, int nals, int *tile_smpl, int *nstage, size_t *ring_bytes)
 {
     int G = nals*(nals+1)/2, S = ctx->p.nsmpl;
     int ts = (int)(ctx->opt_tile_bytes/(4*G));
     ts = std::max(256, ts/256*256);
+    ts = std::min(ts, 32*(int)ctx->opt_block);      /* the AC counters of phase 2 allow at most 63 samples per thread and tile */
     int ntiles = (S + ts - 1)/ts;
     size_t tile_bytes = (size_t)ts*G*4;
     int cap = (int)std::max<int64_t>(2, ctx->opt_ring_bytes/(int64_t)tile_bytes);
@@ -264,11 +285,11 @@ static int enqueue(mcb_ctx *ctx, const mcb_batch *b, const mcb_result *r, int32_
         size_t ring; tile_geometry(ctx, nals, &a.tile_smpl, &a.nstage, &ring);
         a.site_list = lists + (size_t)nals*list_stride; a.site_count = counts + nals;
         int nb = 1;
-        CK(site_kernel_occupancy(nals, ploidy, ring, &nb));
+        CK(site_kernel_occupancy(nals, ploidy, (int)ctx->opt_block, ring, &nb));
         if ( nb<1 ) return cuda_fail(ctx, cudaErrorLaunchOutOfResources, "site kernel does not fit on an SM");
         if ( ctx->opt_blocks_per_sm>0 ) nb = std::min<int>(nb, (int)ctx->opt_blocks_per_sm);
         int grid = (int)std::min<int64_t>((int64_t)b->nsites, (int64_t)ctx->nsm*nb);
-        CK(launch_site_kernel(nals, ploidy, a, grid, ring, st));
+        CK(launch_site_kernel(nals, ploidy, (int)ctx->opt_block, a, grid, ring, st));
         launches++;
     }
     CK(launch_unsupported(lists, counts, r->ret, r->site_flags, b->nals, st));
@@ -316,6 +337,7 @@ extern "C" int mcb_call_host(mcb_ctx *ctx, const mcb_batch *b, const mcb_result 
     }
     const bool want_pl = r->pl != nullptr, want_gt = r->gt != nullptr;
     const bool want_gq = r->gq && (ctx->p.output_tags & (MCB_CALL_FMT_GQ|MCB_CALL_FMT_GP));
+    const bool want_gp = r->gp && (ctx->p.output_tags & MCB_CALL_FMT_GP);
 
     int beg = 0, islab = 0;
     while ( beg < R )
@@ -331,6 +353,7 @@ extern "C" int mcb_call_host(mcb_ctx *ctx, const mcb_batch *b, const mcb_result 
         size_t off = 0;
         auto carve = [&](size_t bytes) { size_t o = off; off += pad256(bytes); return o; };
         size_t o_pl = carve((size_t)pl_ints*4), o_plout = want_pl ? carve((size_t)pl_ints*4) : 0;
+        size_t o_gp = want_gp ? carve((size_t)pl_ints*4) : 0;
         size_t o_ploff = carve(sizeof(int64_t)*n), o_nals = carve(n), o_unseen = carve(n), o_pid = carve(2*(size_t)n);
         size_t o_qs = carve(sizeof(float)*(size_t)n*M), o_nqs = carve(n);
         size_t o_pan = carve(sizeof(int32_t)*n), o_pac = carve(sizeof(int32_t)*(size_t)n*M);
@@ -381,6 +404,7 @@ extern "C" int mcb_call_host(mcb_ctx *ctx, const mcb_batch *b, const mcb_result 
         dr.gt = want_gt ? (int32_t*)(base+o_gt) : nullptr;
         dr.gq = want_gq ? (int32_t*)(base+o_gq) : nullptr;
         dr.pl = want_pl ? (int32_t*)(base+o_plout) - pl0 : nullptr;
+        dr.gp = want_gp ? (float*)(base+o_gp) - pl0 : nullptr;
 
         int rc = enqueue(ctx, &db, &dr, sl.lists, sl.counts, sl.list_cap, st);
         if ( rc ) return rc;
@@ -397,6 +421,7 @@ extern "C" int mcb_call_host(mcb_ctx *ctx, const mcb_batch *b, const mcb_result 
         if ( want_gt ) D2H(r->gt + (size_t)beg*S*2, o_gt, 8*(size_t)n*S);
         if ( want_gq ) D2H(r->gq + (size_t)beg*S, o_gq, 4*(size_t)n*S);
         if ( want_pl ) D2H(r->pl + pl0, o_plout, (size_t)pl_ints*4);
+        if ( want_gp ) D2H(r->gp + pl0, o_gp, (size_t)pl_ints*4);
 #undef D2H
         CK(cudaEventRecord(sl.done, st));
         beg = end; islab++;

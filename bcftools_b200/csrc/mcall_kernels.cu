@@ -4,32 +4,38 @@
 #include "mcall_kernels.cuh"
 #include <math_constants.h>
 
+/*  ALL shared memory of the site kernel is one dynamic array with C linkage: its 32-bit shared address is a
+ *  link-time constant that inline PTX can name (`mov.u32 r, mcb_smem`), so hot-loop accesses become
+ *  LDS [reg+imm] instead of generic-pointer arithmetic.  Layout: Shared<> state at 0, PL tile ring behind it.  */
+extern "C" { extern __shared__ __align__(128) unsigned char mcb_smem[]; }
+
 namespace mcb {
 
 #define I32_MISSING   INT32_MIN
 #define I32_VEC_END   (INT32_MIN+1)
 #define MAX_STAGE     16
-#define BLOCK         256
-#define NWARP         (BLOCK/32)
+
+__device__ __forceinline__ uint32_t smem_base() { uint32_t b; asm("mov.u32 %0, mcb_smem;" : "=r"(b)); return b; }
+__host__ __device__ constexpr size_t align128(size_t n) { return (n + 127) & ~(size_t)127; }
 
 /* ------------------------------------------------------------------------------------------------
  *  bulk-copy engine + mbarrier (PTX; SASS: UBLKCP / SYNCS)
  * ---------------------------------------------------------------------------------------------- */
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count)
 {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
 }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
 {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+                 :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
     asm volatile(
         "{\n"
@@ -39,7 +45,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         "@P1 bra DONE;\n"
         "bra LAB_WAIT;\n"
         "DONE:\n"
-        "}\n" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+        "}\n" :: "r"(bar), "r"(parity) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init()   { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -71,108 +77,177 @@ __device__ __forceinline__ double logsumexp2_dev(double a, double b)       /* mc
     return log(1 + exp(a-b)) + b;
 }
 
+/*  IEEE-754 double division with the reciprocal shared between several numerators.
+ *  This is the fast path of the compiler's own `a/b` (MUFU.RCP64H seed, two Newton steps, one
+ *  residual correction) with the divisor-only part hoisted; the quotient is the correctly rounded
+ *  a/b for a >= 2^-969 and b in the normal range, which the caller guarantees (PL <= 255 =>
+ *  a >= 10^-25.5, 10^-25.5 <= b <= 528).  tests/test_gpu_division.py checks bit-identity with `/`
+ *  over the whole 256^3 biallelic table domain and random multi-allelic sums.                   */
+__device__ __forceinline__ double rcp_shared(double b)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+    double e = fma(-b, r, 1.0);
+    e = fma(e, e, e);
+    r = fma(r, e, r);
+    e = fma(-b, r, 1.0);
+    return fma(r, e, r);
+}
+__device__ __forceinline__ double div_shared(double a, double b, double r)
+{
+    double q = __dmul_rn(a, r);
+    double rem = fma(-b, q, a);
+    return fma(r, rem, q);
+}
+
+/* ------------------------------------------------------------------------------------------------
+ *  explicit shared-space accesses with 32-bit addresses.  Going through generic pointers makes the
+ *  compiler rebuild the shared-window base (S2R SR_CgaCtaId ...) in front of every access (measured:
+ *  ~60 of 445 instructions per sample in the first version of this kernel).
+ * ---------------------------------------------------------------------------------------------- */
+__device__ __forceinline__ int lds32(uint32_t a) { int v; asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+template<int OFF> __device__ __forceinline__ int lds32o(uint32_t a) { int v; asm volatile("ld.shared.s32 %0, [%1+%2];" : "=r"(v) : "r"(a), "n"(OFF)); return v; }
+__device__ __forceinline__ double lds64(uint32_t a) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a)); return v; }
+template<int OFF> __device__ __forceinline__ double lds64o(uint32_t a) { double v; asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(v) : "r"(a), "n"(OFF)); return v; }
+__device__ __forceinline__ int4 lds128(uint32_t a)
+{
+    int4 v; asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); return v;
+}
+__device__ __forceinline__ float lg2_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
 template<int NALS> struct Shape
 {
-    static constexpr int G     = NALS*(NALS+1)/2;
-    static constexpr int NPAIR = NALS*(NALS-1)/2;
-    static constexpr int NTRI  = NALS*(NALS-1)*(NALS-2)/6;
-    static constexpr int NSUB  = NALS + NPAIR + NTRI;
-    static constexpr int NACC  = NPAIR + NTRI + 2;          /* products: pairs, triples, N_all, N_called */
+    static constexpr int G      = NALS*(NALS+1)/2;
+    static constexpr int NPAIR  = NALS*(NALS-1)/2;
+    static constexpr int NTRI   = NALS*(NALS-1)*(NALS-2)/6;
+    static constexpr int NSUB   = NALS + NPAIR + NTRI;
+    static constexpr int NACC   = NPAIR + NTRI + 2;         /* products: pairs, triples, N_all, N_called */
+    static constexpr bool SPLIT = NALS >= 5;                /* accumulate pairs and triples in separate sample loops */
+    static constexpr int MAXSEL = NALS<3 ? NALS : 3;        /* an allele set has at most 3 alleles (mcall.c:589-590) */
+    static constexpr int NSLOT  = MAXSEL*(MAXSEL+1)/2;      /* genotypes spanned by the selected alleles */
 };
 
-template<int NALS> struct Shared
+/*  per-site constants of phase 2: the group's selected alleles s0<s1<s2 span at most 6 genotypes ("slots"),
+ *  kept in the output (igt) order  k: 0=(s0,s0) 1=(s1,s0) 2=(s1,s1) 3=(s2,s0) 4=(s2,s1) 5=(s2,s2)        */
+struct Phase2Consts
+{
+    int4   slot_out[6];     /* diploid call of slot k: {gt0, gt1, AC increment lo, hi} (12-bit counters per new allele) */
+    int4   hap_out[3];      /* haploid call of allele s_x: {gt0, vector_end, AC increment lo, hi} */
+    double q[3];            /* (double)qsum[s_x], mcall.c:797, 820 */
+    int    nsel;            /* number of selected alleles, 1..3 */
+    int    jgt4[6];         /* byte offset of the slot's genotype in the ORIGINAL PL vector */
+    int    igt[6];          /* genotype index in the trimmed vector (GP) */
+    int    hap_new[3];      /* new allele index of s_x */
+    uint32_t inc_dip;       /* bit k: slot k lies below nmax=ngt_new (mcall.c:852) */
+    uint32_t inc_hap;       /* bit x: als_map[s_x] < grp->nals (mcall.c:853) */
+};
+
+template<int NALS, int BLOCK> struct Shared
 {
     using S = Shape<NALS>;
+    static constexpr int NW = BLOCK/32;
     double   pl2p[256];
-    double   gq_thr[128];
+    double   gq_thr[130];                            /* [128],[129] = -1: never reached */
     uint64_t bars[MAX_STAGE];
     /* per-site coefficients of the allele sets (mcall.c:629-633, 671-677) */
     double   cf_pair[(S::NPAIR ? S::NPAIR : 1)*5];   /* fa2 fb2 fab | fa fb */
     double   cf_tri[(S::NTRI ? S::NTRI : 1)*9];      /* fa2 fb2 fc2 fab fac fbc | fa fb fc */
     uint32_t live;                                   /* bit k: pair k evaluated; bit NPAIR+k: triple k evaluated */
     /* cross-warp reduction scratch */
-    double   red_M[NWARP][S::NACC];
-    int      red_E[NWARP][S::NACC];
-    long long red_pls[NWARP][NALS];
-    int      red_cnt[NWARP][2];
+    double   red_M[NW][S::NACC];
+    int      red_E[NW][S::NACC];
+    long long red_pls[NW][NALS];
+    int      red_cnt[NW][2];
     /* site decision record */
     float    qf[NALS];
-    double   q[NALS];
     double   max_qual, lk_sum, ref_lk, gap;
     uint32_t grp_als, als_new, flags;
     int      grp_nals, nals_new, is_variant, ret_early, pl_dropped, ref_gt;
     int      als_map[NALS];
     int      pl_map[S::G];
     int      ac[8];
-    unsigned long long ac_packed[2];
+    Phase2Consts p2;
 };
 
 /* ------------------------------------------------------------------------------------------------
- *  set_pdg for one sample (mcall.c:460-543).  `row` is the sample's PL vector in shared memory;
- *  the missing-value fill of mcall.c:495-527 is written back to it because the filled values are
- *  what gets trimmed and output later.  Returns true when the sample carries data.
+ *  set_pdg for one sample (mcall.c:460-543), the rare part: missing / vector_end values present.
+ *  `row` indexes the sample's PL vector inside the ring; the fill of mcall.c:495-527 is written back
+ *  because the filled values are what gets trimmed and output later.  Returns 0 when the sample has
+ *  no data (all missing).
  * ---------------------------------------------------------------------------------------------- */
-template<int NALS>
-__device__ __noinline__ int fix_missing(int32_t *row, int unseen)
+__device__ __noinline__ int fix_missing(uint32_t row_s, int nals, int unseen)
 {
-    constexpr int G = Shape<NALS>::G;
-    /* first scan: a vector_end anywhere before the first missing, or a missing first value => all missing */
+    const int G = nals*(nals+1)/2;
+    auto PL = [&](int j) -> int { int v; asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(row_s + 4u*(uint32_t)j)); return v; };
     int j;
     for (j=0; j<G; j++)
     {
-        if ( row[j]==I32_VEC_END ) return 0;
-        if ( row[j]==I32_MISSING ) break;
+        const int v = PL(j);
+        if ( v==I32_VEC_END ) return 0;         /* not diploid-shaped: all missing, mcall.c:465-470 */
+        if ( v==I32_MISSING ) break;
     }
-    if ( j==0 ) return 0;
-    if ( j==G ) return 1;       /* nothing missing after all (negative garbage): leave as is */
+    if ( j==0 ) return 0;                       /* first value missing: all missing, mcall.c:476-481 */
+    if ( j==G ) return 0;                       /* negative garbage that is no sentinel: undefined in the reference */
     j = 0;
-    for (int ia=0; ia<NALS; ia++)
+    for (int ia=0; ia<nals; ia++)
         for (int ib=0; ib<=ia; ib++)
         {
-            if ( row[j]==I32_MISSING )
+            const int v = PL(j);
+            if ( v==I32_MISSING )
             {
                 int k = gt_idx(ia,unseen);
-                if ( row[k]==I32_MISSING ) k = gt_idx(ib,unseen);
-                if ( row[k]==I32_MISSING ) k = gt_idx(unseen,unseen);
-                row[j] = row[k]==I32_MISSING ? 255 : row[k];
+                if ( PL(k)==I32_MISSING ) k = gt_idx(ib,unseen);
+                if ( PL(k)==I32_MISSING ) k = gt_idx(unseen,unseen);
+                const int w = PL(k)==I32_MISSING ? 255 : PL(k);
+                asm volatile("st.shared.s32 [%0], %1;" :: "r"(row_s + 4u*(uint32_t)j), "r"(w) : "memory");
             }
-            else if ( row[j] < 0 ) return 0;    /* vector_end behind a missing value: undefined in the reference */
+            else if ( v < 0 ) return 0;         /* vector_end behind a missing value: undefined in the reference */
             j++;
         }
     return 1;
 }
 
+/*  PL >= 256 (mcall.c:472): host-built table in global memory, 0 beyond the double range  */
+__device__ __noinline__ double big_pl_to_p(const DevTables *tab, int v, uint32_t *flags)
+{
+    if ( v > 2500 ) *flags |= MCB_SITE_PL_RANGE;
+    return (unsigned)v < (unsigned)MCB_PL2P_BIG ? tab->pl2p_big[v] : 0.0;
+}
+
+/*  One sample's PLs, likelihoods p[j] = pl2p[PL[j]] and their sum in index order (mcall.c:462-474).
+ *  row_s = shared address of the PL vector.  Returns false for "no data" samples.                 */
 template<int NALS>
-__device__ __forceinline__ bool load_sample(int32_t *row, int unseen, const double *s_pl2p, const DevTables *tab,
-                                            int (&pl)[Shape<NALS>::G], double (&p)[Shape<NALS>::G], double &sum, uint32_t &flags)
+__device__ __forceinline__ bool load_sample(uint32_t row_s, uint32_t pl2p_s, int unseen, const DevTables *tab,
+                                            int (&pl)[Shape<NALS>::G], double (&p)[Shape<NALS>::G], double &sum, int &orv, uint32_t &flags)
 {
     constexpr int G = Shape<NALS>::G;
-    int orv = 0;
-    #pragma unroll
-    for (int j=0; j<G; j++) { pl[j] = row[j]; orv |= pl[j]; }
-    if ( orv < 0 )
+    auto load_pl = [&]()
     {
-        if ( !fix_missing<NALS>(row, unseen) ) return false;
         orv = 0;
         #pragma unroll
-        for (int j=0; j<G; j++) { pl[j] = row[j]; orv |= pl[j]; }
+        for (int j=0; j<G; j++)
+        {
+            const int v = lds32(row_s + 4u*(uint32_t)j);
+            pl[j] = v; orv |= v;
+        }
+    };
+    load_pl();
+    if ( orv < 0 )
+    {
+        if ( !fix_missing(row_s, NALS, unseen) ) return false;
+        load_pl();
+        if ( orv < 0 ) return false;
     }
     if ( orv==0 ) return false;         /* PL=0,..,0: sum==n_gt, no data (mcall.c:529-537) */
     if ( orv & ~255 )
     {
-        /* PL >= 256 (mcall.c:472): host-built table in global memory, 0 beyond the double range */
         #pragma unroll
-        for (int j=0; j<G; j++)
-        {
-            int v = pl[j];
-            p[j] = (unsigned)v < 256u ? s_pl2p[v] : ((unsigned)v < (unsigned)MCB_PL2P_BIG ? tab->pl2p_big[v] : 0.0);
-            if ( v > 2500 ) flags |= MCB_SITE_PL_RANGE;
-        }
+        for (int j=0; j<G; j++) p[j] = pl[j] < 256 ? lds64(pl2p_s + 8u*(uint32_t)pl[j]) : big_pl_to_p(tab, pl[j], &flags);
     }
     else
     {
         #pragma unroll
-        for (int j=0; j<G; j++) p[j] = s_pl2p[pl[j]];
+        for (int j=0; j<G; j++) p[j] = lds64(pl2p_s + 8u*(uint32_t)pl[j]);
     }
     sum = p[0];
     #pragma unroll
@@ -183,16 +258,25 @@ __device__ __forceinline__ bool load_sample(int32_t *row, int unseen, const doub
 /* ------------------------------------------------------------------------------------------------
  *  the fused kernel
  * ---------------------------------------------------------------------------------------------- */
-template<int NALS, bool PLOIDY>
-__global__ void __launch_bounds__(BLOCK) mcall_site_kernel(const KArgs a)
+template<int NALS, int BLOCK> struct MinBlocks
+{
+#ifndef MCB_MINB2
+#define MCB_MINB2 4         /* CTAs of 256 threads per SM the 1-2 allele kernels are compiled for (register cap 65536/(256*n)) */
+#endif
+    static constexpr int per256 = NALS<=2 ? MCB_MINB2 : (NALS==3 ? 2 : 1);
+    static constexpr int value  = BLOCK==256 ? per256 : (NALS<=2 ? 2*MCB_MINB2 : (NALS==3 ? 4 : (NALS==4 ? 3 : 2)));
+};
+
+template<int NALS, bool PLOIDY, int BLOCK>
+__global__ void __launch_bounds__(BLOCK, (MinBlocks<NALS,BLOCK>::value)) mcall_site_kernel(const KArgs a)
 {
     using S = Shape<NALS>;
     constexpr int G = S::G, NPAIR = S::NPAIR, NTRI = S::NTRI, NSUB = S::NSUB, NACC = S::NACC;
+    constexpr int MAXSEL = S::MAXSEL, NSLOT = S::NSLOT, NW = BLOCK/32;
     constexpr double LN2 = 0.693147180559945309417232121458, LN10_10 = 0.2302585092994045684017991454684;
 
-    __shared__ Shared<NALS> sh;
-    extern __shared__ __align__(128) unsigned char ring_raw[];
-    int32_t *ring = reinterpret_cast<int32_t*>(ring_raw);
+    using SH = Shared<NALS,BLOCK>;
+    SH &sh = *reinterpret_cast<SH*>(mcb_smem);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nsmpl = a.nsmpl, TS = a.tile_smpl, nstage = a.nstage;
@@ -200,12 +284,17 @@ __global__ void __launch_bounds__(BLOCK) mcall_site_kernel(const KArgs a)
     const int ntiles = (nsmpl + TS - 1)/TS;
     const bool resident = ntiles <= nstage;
     const int total_visits = resident ? ntiles : 2*ntiles;
+    const uint32_t sbase = smem_base();
+    const uint32_t ring_s = sbase + (uint32_t)align128(sizeof(SH)), bars_s = sbase + (uint32_t)offsetof(SH, bars);
+    const uint32_t pl2p_s = sbase + (uint32_t)offsetof(SH, pl2p), thr_s = sbase + (uint32_t)offsetof(SH, gq_thr);
+    const uint32_t slot_s = sbase + (uint32_t)(offsetof(SH, p2) + offsetof(Phase2Consts, slot_out));
+    const uint32_t hap_s  = sbase + (uint32_t)(offsetof(SH, p2) + offsetof(Phase2Consts, hap_out));
 
     for (int i=tid; i<256; i+=BLOCK) sh.pl2p[i] = a.tab->pl2p[i];
-    for (int i=tid; i<128; i+=BLOCK) sh.gq_thr[i] = a.tab->gq_thr[i];
+    for (int i=tid; i<130; i+=BLOCK) sh.gq_thr[i] = i<128 ? a.tab->gq_thr[i] : -1.0;
     if ( tid==0 )
     {
-        for (int i=0; i<nstage; i++) mbar_init(&sh.bars[i], 1);
+        for (int i=0; i<nstage; i++) mbar_init(bars_s + 8*i, 1);
         fence_mbar_init();
     }
     __syncthreads();
@@ -216,7 +305,8 @@ __global__ void __launch_bounds__(BLOCK) mcall_site_kernel(const KArgs a)
     for (int isite = blockIdx.x; isite < nsites; isite += gridDim.x)
     {
         const int site = a.site_list[isite];
-        const int32_t *site_pl = a.pl + a.pl_off[site];
+        const int64_t site_off = a.pl_off[site];
+        const int32_t *site_pl = a.pl + site_off;
         const int unseen = a.unseen ? a.unseen[site] : 0;
         const uint8_t *ploidy = nullptr;
         if ( PLOIDY )
@@ -231,8 +321,8 @@ __global__ void __launch_bounds__(BLOCK) mcall_site_kernel(const KArgs a)
             int t = v % ntiles, stage = v % nstage;
             int n = min(TS, nsmpl - t*TS);
             uint32_t bytes = ((uint32_t)(n*G*4) + 15u) & ~15u;
-            mbar_expect_tx(&sh.bars[stage], bytes);
-            bulk_g2s(ring + (size_t)stage*tile_ints, site_pl + (size_t)t*tile_ints, bytes, &sh.bars[stage]);
+            mbar_expect_tx(bars_s + 8*stage, bytes);
+            bulk_g2s(ring_s + 4u*(uint32_t)(stage*tile_ints), site_pl + (size_t)t*tile_ints, bytes, bars_s + 8*stage);
         };
         if ( tid==0 )
             for (int v=0; v<nstage && v<total_visits; v++) issue(v);
@@ -274,9 +364,8 @@ __global__ void __launch_bounds__(BLOCK) mcall_site_kernel(const KArgs a)
                 for (int j=0; j<NALS; j++) q[j] = __fdiv_rn(q[j], qsum);
             }
             #pragma unroll
-            for (int j=0; j<NALS; j++) { sh.qf[j] = q[j]; sh.q[j] = (double)q[j]; }
+            for (int j=0; j<NALS; j++) sh.qf[j] = q[j];
             sh.flags = flags;
-            sh.ac_packed[0] = sh.ac_packed[1] = 0;
             for (int j=0; j<8; j++) sh.ac[j] = 0;
         }
         __syncthreads();
@@ -289,15 +378,16 @@ __global__ void __launch_bounds__(BLOCK) mcall_site_kernel(const KArgs a)
                 int aa = 1; while ( aa*(aa+1)/2 <= lane ) aa++;     /* pair_idx(aa,bb)==lane */
                 int bb = lane - aa*(aa-1)/2;
                 float qa = sh.qf[aa], qb = sh.qf[bb];
+                double *cf = sh.cf_pair + lane*5;
                 if ( qa!=0 && qb!=0 )
                 {
                     float den = __fadd_rn(qa,qb);
                     double fa = (double)__fdiv_rn(qa,den), fb = (double)__fdiv_rn(qb,den);
-                    double *cf = sh.cf_pair + lane*5;
                     cf[0] = __dmul_rn(fa,fa); cf[1] = __dmul_rn(fb,fb); cf[2] = __dmul_rn(__dmul_rn(2.0,fa),fb);
                     cf[3] = fa; cf[4] = fb;
                     live = 1u<<lane;
                 }
+                else { cf[0] = cf[1] = cf[2] = cf[3] = cf[4] = 0; }
             }
             else if ( lane-NPAIR < NTRI )
             {
@@ -307,16 +397,17 @@ __global__ void __launch_bounds__(BLOCK) mcall_site_kernel(const KArgs a)
                 int bb = 1; while ( bb*(bb+1)/2 <= r ) bb++;
                 int cc = r - bb*(bb-1)/2;
                 float qa = sh.qf[aa], qb = sh.qf[bb], qc = sh.qf[cc];
+                double *cf = sh.cf_tri + k*9;
                 if ( qa!=0 && qb!=0 && qc!=0 )
                 {
                     float den = __fadd_rn(__fadd_rn(qa,qb),qc);
                     double fa = (double)__fdiv_rn(qa,den), fb = (double)__fdiv_rn(qb,den), fc = (double)__fdiv_rn(qc,den);
-                    double *cf = sh.cf_tri + k*9;
                     cf[0] = __dmul_rn(fa,fa); cf[1] = __dmul_rn(fb,fb); cf[2] = __dmul_rn(fc,fc);
                     cf[3] = __dmul_rn(__dmul_rn(2.0,fa),fb); cf[4] = __dmul_rn(__dmul_rn(2.0,fa),fc); cf[5] = __dmul_rn(__dmul_rn(2.0,fb),fc);
                     cf[6] = fa; cf[7] = fb; cf[8] = fc;
                     live = 1u<<lane;
                 }
+                else { for (int j=0; j<9; j++) cf[j] = 0; }
             }
             #pragma unroll
             for (int off=16; off; off>>=1) live |= __shfl_xor_sync(0xffffffffu, live, off);
@@ -327,103 +418,145 @@ __global__ void __launch_bounds__(BLOCK) mcall_site_kernel(const KArgs a)
 
         /* =========================== phase 1: site reduction ==================================== */
         double accM[NACC]; int accE[NACC];
-        long long plsum[NALS];
+        int plsum32[NALS]; long long plsum[NALS];
         int cnt_all = 0, cnt_called = 0, since_renorm = 0;
         uint32_t tflags = 0;
         #pragma unroll
         for (int k=0; k<NACC; k++) { accM[k] = 1.0; accE[k] = 0; }
         #pragma unroll
-        for (int k=0; k<NALS; k++) plsum[k] = 0;
+        for (int k=0; k<NALS; k++) { plsum[k] = 0; plsum32[k] = 0; }
+        /* coefficients of the small shapes live in registers; larger shapes read them from shared memory */
+        constexpr bool CF_REG = NALS<=3;
+        double cfp[CF_REG ? (NPAIR ? NPAIR : 1)*5 : 1], cft[CF_REG ? (NTRI ? NTRI : 1)*9 : 1];
+        if ( CF_REG )
+        {
+            #pragma unroll
+            for (int k=0; k<NPAIR*5; k++) cfp[k] = sh.cf_pair[k];
+            #pragma unroll
+            for (int k=0; k<NTRI*9; k++) cft[k] = sh.cf_tri[k];
+        }
+        const uint32_t cfp_s = sbase + (uint32_t)offsetof(SH, cf_pair), cft_s = sbase + (uint32_t)offsetof(SH, cf_tri);
+        auto CP = [&](int k, int c) -> double { return CF_REG ? cfp[CF_REG ? k*5+c : 0] : lds64(cfp_s + 8u*(uint32_t)(k*5+c)); };
+        auto CT = [&](int k, int c) -> double { return CF_REG ? cft[CF_REG ? k*9+c : 0] : lds64(cft_s + 8u*(uint32_t)(k*9+c)); };
 
         for (int t=0; t<ntiles; t++)
         {
             const int stage = t % nstage;
-            mbar_wait(&sh.bars[stage], (phase_bits>>stage)&1u);
+            mbar_wait(bars_s + 8*stage, (phase_bits>>stage)&1u);
             phase_bits ^= 1u<<stage;
-            int32_t *tile = ring + (size_t)stage*tile_ints;
+            const uint32_t tile_s = ring_s + 4u*(uint32_t)(stage*tile_ints);
             const int s0 = t*TS, n = min(TS, nsmpl - s0);
-            for (int s=tid; s<n; s+=BLOCK)
+            /* pass 0: normalisers, single-allele sums, pairs (+ triples unless SPLIT); pass 1 (SPLIT): triples */
+            #pragma unroll 1
+            for (int pass=0; pass<(S::SPLIT ? 2 : 1); pass++)
             {
-                int pl[G]; double p[G]; double sum;
-                if ( !load_sample<NALS>(tile + s*G, unseen, sh.pl2p, a.tab, pl, p, sum, tflags) ) continue;
-                /* single-allele sets: log(pdg[aa]) = -PL*ln10/10 - log(sum), every sample incl. ploidy 0 (mcall.c:607-611) */
+                const bool do_pairs = pass==0, do_tri = S::SPLIT ? pass==1 : true;
+                #pragma unroll 1
+                for (int s=tid; s<n; s+=BLOCK)
+                {
+                    int pl[G]; double p[G]; double sum; int orv;
+                    if ( !load_sample<NALS>(tile_s + (uint32_t)(s*G*4), pl2p_s, unseen, a.tab, pl, p, sum, orv, tflags) ) continue;
+                    int pld = 2;
+                    if ( PLOIDY ) pld = __ldg(ploidy + s0 + s);
+                    if ( pass==0 )
+                    {
+                        /* single-allele sets: log(pdg[aa]) = -PL*ln10/10 - log(sum), every sample incl. ploidy 0 (mcall.c:607-611) */
+                        if ( orv & ~255 )
+                        {
+                            #pragma unroll
+                            for (int k=0; k<NALS; k++) plsum[k] += pl[hom_idx(k)];
+                        }
+                        else
+                        {
+                            #pragma unroll
+                            for (int k=0; k<NALS; k++) plsum32[k] += pl[hom_idx(k)];
+                        }
+                        cnt_all++;
+                        acc_mul(accM[NACC-2], accE[NACC-2], sum);
+                        if ( PLOIDY && pld!=0 ) { cnt_called++; acc_mul(accM[NACC-1], accE[NACC-1], sum); }
+                    }
+                    if ( PLOIDY && pld==0 ) continue;       /* ploidy 0: val stays 0 (mcall.c:639-644) */
+                    if ( !PLOIDY || pld==2 )
+                    {
+                        if ( do_pairs )
+                        {
+                            #pragma unroll
+                            for (int x=1; x<NALS; x++)
+                                #pragma unroll
+                                for (int y=0; y<x; y++)
+                                {
+                                    const int k = pair_idx(x,y);
+                                    if ( live & (1u<<k) )
+                                    {
+                                        double val = fma(CP(k,2), p[gt_idx(x,y)], fma(CP(k,1), p[hom_idx(y)], CP(k,0)*p[hom_idx(x)]));
+                                        acc_mul(accM[k], accE[k], val);
+                                    }
+                                }
+                        }
+                        if ( do_tri )
+                        {
+                            #pragma unroll
+                            for (int x=2; x<NALS; x++)
+                                #pragma unroll
+                                for (int y=1; y<x; y++)
+                                    #pragma unroll
+                                    for (int z=0; z<y; z++)
+                                    {
+                                        const int k = tri_idx(x,y,z);
+                                        if ( live & (1u<<(NPAIR+k)) )
+                                        {
+                                            double val = fma(CT(k,5), p[gt_idx(y,z)], fma(CT(k,4), p[gt_idx(x,z)], fma(CT(k,3), p[gt_idx(x,y)],
+                                                         fma(CT(k,2), p[hom_idx(z)], fma(CT(k,1), p[hom_idx(y)], CT(k,0)*p[hom_idx(x)])))));
+                                            acc_mul(accM[NPAIR+k], accE[NPAIR+k], val);
+                                        }
+                                    }
+                        }
+                    }
+                    else    /* haploid (mcall.c:642-643, 687-688) */
+                    {
+                        if ( do_pairs )
+                        {
+                            #pragma unroll
+                            for (int x=1; x<NALS; x++)
+                                #pragma unroll
+                                for (int y=0; y<x; y++)
+                                {
+                                    const int k = pair_idx(x,y);
+                                    if ( live & (1u<<k) )
+                                    {
+                                        double val = fma(CP(k,4), p[hom_idx(y)], CP(k,3)*p[hom_idx(x)]);
+                                        acc_mul(accM[k], accE[k], val);
+                                    }
+                                }
+                        }
+                        if ( do_tri )
+                        {
+                            #pragma unroll
+                            for (int x=2; x<NALS; x++)
+                                #pragma unroll
+                                for (int y=1; y<x; y++)
+                                    #pragma unroll
+                                    for (int z=0; z<y; z++)
+                                    {
+                                        const int k = tri_idx(x,y,z);
+                                        if ( live & (1u<<(NPAIR+k)) )
+                                        {
+                                            double val = fma(CT(k,8), p[hom_idx(z)], fma(CT(k,7), p[hom_idx(y)], CT(k,6)*p[hom_idx(x)]));
+                                            acc_mul(accM[NPAIR+k], accE[NPAIR+k], val);
+                                        }
+                                    }
+                        }
+                    }
+                }
+            }
+            #pragma unroll
+            for (int k=0; k<NALS; k++) { plsum[k] += plsum32[k]; plsum32[k] = 0; }
+            since_renorm += (TS + BLOCK - 1)/BLOCK;
+            if ( since_renorm >= 256 )
+            {
                 #pragma unroll
-                for (int k=0; k<NALS; k++) plsum[k] += pl[hom_idx(k)];
-                cnt_all++;
-                acc_mul(accM[NACC-2], accE[NACC-2], sum);
-                int pld = 2;
-                if ( PLOIDY ) { pld = ploidy[s0+s]; if ( pld==0 ) continue; }      /* ploidy 0: val stays 0 (mcall.c:639-644) */
-                cnt_called++;
-                if ( PLOIDY ) acc_mul(accM[NACC-1], accE[NACC-1], sum);
-                if ( !PLOIDY || pld==2 )
-                {
-                    #pragma unroll
-                    for (int x=1; x<NALS; x++)
-                        #pragma unroll
-                        for (int y=0; y<x; y++)
-                        {
-                            const int k = pair_idx(x,y);
-                            if ( live & (1u<<k) )
-                            {
-                                const double *cf = sh.cf_pair + k*5;
-                                double val = fma(cf[2], p[gt_idx(x,y)], fma(cf[1], p[hom_idx(y)], cf[0]*p[hom_idx(x)]));
-                                acc_mul(accM[k], accE[k], val);
-                            }
-                        }
-                    #pragma unroll
-                    for (int x=2; x<NALS; x++)
-                        #pragma unroll
-                        for (int y=1; y<x; y++)
-                            #pragma unroll
-                            for (int z=0; z<y; z++)
-                            {
-                                const int k = tri_idx(x,y,z);
-                                if ( live & (1u<<(NPAIR+k)) )
-                                {
-                                    const double *cf = sh.cf_tri + k*9;
-                                    double val = fma(cf[5], p[gt_idx(y,z)], fma(cf[4], p[gt_idx(x,z)], fma(cf[3], p[gt_idx(x,y)],
-                                                 fma(cf[2], p[hom_idx(z)], fma(cf[1], p[hom_idx(y)], cf[0]*p[hom_idx(x)])))));
-                                    acc_mul(accM[NPAIR+k], accE[NPAIR+k], val);
-                                }
-                            }
-                }
-                else    /* haploid (mcall.c:642-643, 687-688) */
-                {
-                    #pragma unroll
-                    for (int x=1; x<NALS; x++)
-                        #pragma unroll
-                        for (int y=0; y<x; y++)
-                        {
-                            const int k = pair_idx(x,y);
-                            if ( live & (1u<<k) )
-                            {
-                                const double *cf = sh.cf_pair + k*5;
-                                double val = fma(cf[4], p[hom_idx(y)], cf[3]*p[hom_idx(x)]);
-                                acc_mul(accM[k], accE[k], val);
-                            }
-                        }
-                    #pragma unroll
-                    for (int x=2; x<NALS; x++)
-                        #pragma unroll
-                        for (int y=1; y<x; y++)
-                            #pragma unroll
-                            for (int z=0; z<y; z++)
-                            {
-                                const int k = tri_idx(x,y,z);
-                                if ( live & (1u<<(NPAIR+k)) )
-                                {
-                                    const double *cf = sh.cf_tri + k*9;
-                                    double val = fma(cf[8], p[hom_idx(z)], fma(cf[7], p[hom_idx(y)], cf[6]*p[hom_idx(x)]));
-                                    acc_mul(accM[NPAIR+k], accE[NPAIR+k], val);
-                                }
-                            }
-                }
-                if ( ++since_renorm >= 256 )
-                {
-                    #pragma unroll
-                    for (int k=0; k<NACC; k++) acc_renorm(accM[k], accE[k]);
-                    since_renorm = 0;
-                }
+                for (int k=0; k<NACC; k++) acc_renorm(accM[k], accE[k]);
+                since_renorm = 0;
             }
             if ( !resident )
             {
@@ -432,11 +565,13 @@ __global__ void __launch_bounds__(BLOCK) mcall_site_kernel(const KArgs a)
                 if ( tid==0 && t+nstage < total_visits ) issue(t+nstage);
             }
         }
+        if ( !PLOIDY ) cnt_called = cnt_all;
 
         /* ---- block reduction of the products (mantissa multiply, exponent add) and the integer sums */
         #pragma unroll
         for (int k=0; k<NACC; k++)
         {
+            if ( !PLOIDY && k==NACC-1 ) continue;
             acc_renorm(accM[k], accE[k]);
             #pragma unroll
             for (int off=16; off; off>>=1)
@@ -473,14 +608,12 @@ __global__ void __launch_bounds__(BLOCK) mcall_site_kernel(const KArgs a)
         {
             int n_all = 0, n_called = 0;
             #pragma unroll
-            for (int w=0; w<NWARP; w++) { n_all += sh.red_cnt[w][0]; n_called += sh.red_cnt[w][1]; }
-            if ( !PLOIDY ) n_called = n_all;
+            for (int w=0; w<NW; w++) { n_all += sh.red_cnt[w][0]; n_called += sh.red_cnt[w][1]; }
             auto total_log = [&](int k, int n) -> double
             {
                 double M = 1.0; int E = 0;
                 #pragma unroll
-                for (int w=0; w<NWARP; w++) { M = __dmul_rn(M, sh.red_M[w][k]); E += sh.red_E[w][k]; }
-                /* |E| < 2^31: at most 2^20 samples x 2047 */
+                for (int w=0; w<NW; w++) { M = __dmul_rn(M, sh.red_M[w][k]); E += sh.red_E[w][k]; }
                 return log(M) + (double)(E - 1023*n)*LN2;
             };
             const double lnN_all    = n_all ? total_log(NACC-2, n_all) : 0.0;
@@ -491,7 +624,7 @@ __global__ void __launch_bounds__(BLOCK) mcall_site_kernel(const KArgs a)
             {
                 long long ps = 0;
                 #pragma unroll
-                for (int w=0; w<NWARP; w++) ps += sh.red_pls[w][lane];
+                for (int w=0; w<NW; w++) ps += sh.red_pls[w][lane];
                 bool set = n_all > 0;
                 lk = set ? -LN10_10*(double)ps - lnN_all : 0.0;
                 if ( lane>0 ) lk += a.theta;
@@ -570,12 +703,13 @@ __global__ void __launch_bounds__(BLOCK) mcall_site_kernel(const KArgs a)
                     if ( als_new & (1u<<j) ) nals_new++;
                 }
                 int nout = 0, kk = 0, l = 0;                /* mcall.c:547-570 */
+                int amap[NALS];
                 #pragma unroll
-                for (int x=0; x<NALS; x++) sh.als_map[x] = (als_new & (1u<<x)) ? nout++ : -1;
+                for (int x=0; x<NALS; x++) { amap[x] = (als_new & (1u<<x)) ? nout++ : -1; sh.als_map[x] = amap[x]; }
                 #pragma unroll
                 for (int x=0; x<NALS; x++)
                     #pragma unroll
-                    for (int y=0; y<=x; y++) { if ( (als_new & (1u<<x)) && (als_new & (1u<<y)) ) sh.pl_map[kk++] = l; l++; }
+                    for (int y=0; y<=x; y++) { if ( (als_new & (1u<<x)) && (als_new & (1u<<y)) ) { if ( kk<G ) sh.pl_map[kk] = l; kk++; } l++; }
                 for (; kk<G; kk++) sh.pl_map[kk] = 0;
                 if ( unseen && (als_new & (1u<<unseen)) ) flags |= MCB_SITE_UNSEEN_SEL;
                 sh.pl_dropped = als_new==1;
@@ -588,6 +722,37 @@ __global__ void __launch_bounds__(BLOCK) mcall_site_kernel(const KArgs a)
                 sh.grp_als = gals; sh.grp_nals = gn; sh.als_new = als_new; sh.nals_new = nals_new;
                 sh.is_variant = is_variant; sh.ret_early = ret_early; sh.flags = flags;
                 sh.max_qual = max_qual; sh.lk_sum = lk_sum; sh.ref_lk = ref_lk; sh.gap = gap;
+                /* phase-2 constants: selected alleles in ascending order and the <=6 genotypes they span */
+                {
+                    Phase2Consts &c = sh.p2;
+                    const int ngt_new = nals_new*(nals_new+1)/2;
+                    int sel[3] = {0,0,0}, ns = 0;
+                    #pragma unroll
+                    for (int j=0; j<NALS; j++) if ( (gals>>j)&1u ) { if ( ns<3 ) sel[ns] = j; ns++; }
+                    if ( ns>3 ) ns = 3;
+                    c.nsel = ns; c.inc_dip = 0; c.inc_hap = 0;
+                    for (int x=0; x<3; x++)
+                    {
+                        c.q[x] = x<ns ? (double)sh.qf[sel[x]] : 0.0;
+                        int nx = x<ns ? amap[sel[x]] : 0;
+                        c.hap_new[x] = nx;
+                        if ( x<ns && nx < gn ) c.inc_hap |= 1u<<x;
+                        unsigned long long hinc = 1ull << (12*min(nx,4));
+                        c.hap_out[x] = make_int4(MCB_GT_UNPHASED(nx), I32_VEC_END, (int)(uint32_t)hinc, (int)(uint32_t)(hinc>>32));
+                        for (int y=0; y<=x; y++)
+                        {
+                            int k = x*(x+1)/2 + y;
+                            int ny = y<ns ? amap[sel[y]] : 0;
+                            c.jgt4[k] = (x<ns) ? 4*gt_idx(sel[x], sel[y]) : 0;
+                            int ig = gt_idx(nx, ny);
+                            c.igt[k] = ig;
+                            if ( x<ns && ig < ngt_new ) c.inc_dip |= 1u<<k;
+                            /* gts[0] = smaller new allele, gts[1] = larger (mcall.c:830-831); AC: one count per allele */
+                            unsigned long long inc = (1ull << (12*min(ny,4))) + (1ull << (12*min(nx,4)));
+                            c.slot_out[k] = make_int4(MCB_GT_UNPHASED(ny), MCB_GT_UNPHASED(nx), (int)(uint32_t)inc, (int)(uint32_t)(inc>>32));
+                        }
+                    }
+                }
             }
         }
         __syncthreads();
@@ -605,161 +770,241 @@ __global__ void __launch_bounds__(BLOCK) mcall_site_kernel(const KArgs a)
                 for (int v=ntiles; v<ntiles+nstage && v<total_visits; v++)
                 {
                     const int stage = v % nstage;
-                    mbar_wait(&sh.bars[stage], (phase_bits>>stage)&1u);
+                    mbar_wait(bars_s + 8*stage, (phase_bits>>stage)&1u);
                     phase_bits ^= 1u<<stage;
                 }
             __syncthreads();
             continue;
         }
         {
-            const uint32_t gals = sh.grp_als;
             const int nals_new = sh.nals_new, ngt_new = nals_new*(nals_new+1)/2, grp_nals = sh.grp_nals;
             const bool ref_gt = sh.ref_gt, pl_dropped = sh.pl_dropped;
             const bool want_gq = a.gq && (a.output_tags & (MCB_CALL_FMT_GQ|MCB_CALL_FMT_GP));
-            int32_t *out_pl = (a.out_pl && !pl_dropped) ? a.out_pl + a.pl_off[site] : nullptr;
+            const bool want_gp = a.gp && (a.output_tags & MCB_CALL_FMT_GP) && !ref_gt;
+            const bool want_gqm = want_gq || want_gp;       /* the max/sum arithmetic is shared by GQ and GP */
+            int32_t *out_pl = (a.out_pl && !pl_dropped) ? a.out_pl + site_off : nullptr;
+            float   *out_gp = want_gp ? a.gp + site_off : nullptr;
             int2 *out_gt = a.gt ? reinterpret_cast<int2*>(a.gt) + (size_t)site*nsmpl : nullptr;
             int32_t *out_gq = want_gq ? a.gq + (size_t)site*nsmpl : nullptr;
-            unsigned long long ac_lo = 0, ac_hi = 0;
+            /* per-site constants into registers */
+            const int nsel = sh.p2.nsel;
+            const double q0 = sh.p2.q[0], q1 = sh.p2.q[1], q2 = sh.p2.q[2];
+            int jgt4[NSLOT];
+            #pragma unroll
+            for (int k=0; k<NSLOT; k++) jgt4[k] = sh.p2.jgt4[k];
+            const uint32_t inc_dip = sh.p2.inc_dip, inc_hap = sh.p2.inc_hap;
+            const uint32_t full_dip = nsel>=3 ? 0x3fu : (nsel==2 ? 0x7u : 0x1u), full_hap = (1u<<nsel) - 1u;
+            const bool inc_full = (inc_dip & full_dip)==full_dip && (inc_hap & full_hap)==full_hap;
+            constexpr int NPLM = G<6 ? G : 6;
+            int plm4[NPLM];
+            #pragma unroll
+            for (int k=0; k<NPLM; k++) plm4[k] = 4*sh.pl_map[k];
+            unsigned long long acc = 0;     /* AC: 12-bit counters, new allele j at bits [12j,12j+12) */
+            int acc_n = 0;
             uint32_t tflags2 = 0;
+            auto flush_ac = [&]()           /* called by all threads of the block together */
+            {
+                unsigned long long v = acc;     /* <= 2*60 per lane and field: no carry between the 12-bit fields within a warp */
+                #pragma unroll
+                for (int off=16; off; off>>=1) v += __shfl_xor_sync(0xffffffffu, v, off);
+                if ( lane==0 )
+                {
+                    #pragma unroll
+                    for (int j=0; j<5; j++)
+                    {
+                        int c = (int)((v >> (12*j)) & 0xfff);
+                        if ( c ) atomicAdd(&sh.ac[j], c);
+                    }
+                }
+                acc = 0; acc_n = 0;
+            };
 
             for (int t=0; t<ntiles; t++)
             {
                 const int v = resident ? t : ntiles + t, stage = v % nstage;
                 if ( !resident )
                 {
-                    mbar_wait(&sh.bars[stage], (phase_bits>>stage)&1u);
+                    mbar_wait(bars_s + 8*stage, (phase_bits>>stage)&1u);
                     phase_bits ^= 1u<<stage;
                 }
-                int32_t *tile = ring + (size_t)stage*tile_ints;
+                const uint32_t tile_s = ring_s + 4u*(uint32_t)(stage*tile_ints);
                 const int s0 = t*TS, n = min(TS, nsmpl - s0);
+                if ( acc_n + (TS + BLOCK - 1)/BLOCK > 63 ) flush_ac();     /* uniform across the block: safe to shuffle */
+                acc_n += (TS + BLOCK - 1)/BLOCK;
+                #pragma unroll 1
                 for (int s=tid; s<n; s+=BLOCK)
                 {
-                    int pl[G]; double p[G]; double sum = 1;
-                    int32_t *row = tile + s*G;
-                    const bool has = load_sample<NALS>(row, unseen, sh.pl2p, a.tab, pl, p, sum, tflags2);
-                    const int pld = PLOIDY ? ploidy[s0+s] : 2;
-                    int gt0, gt1, gq = 0;
-                    if ( !pld ) { gt0 = MCB_GT_MISSING; gt1 = I32_VEC_END; }
-                    else if ( !has ) { gt0 = MCB_GT_MISSING; gt1 = pld==2 ? MCB_GT_MISSING : I32_VEC_END; }
+                    int pl[G]; double p[G]; double sum = 1; int orv;
+                    const uint32_t row_s = tile_s + (uint32_t)(s*G*4);
+                    const bool has = load_sample<NALS>(row_s, pl2p_s, unseen, a.tab, pl, p, sum, orv, tflags2);
+                    const int pld = PLOIDY ? __ldg(ploidy + s0 + s) : 2;
+                    int4 outc = make_int4(MCB_GT_MISSING, pld==2 ? MCB_GT_MISSING : I32_VEC_END, 0, 0);
+                    int gq = 0;
+                    bool called = false;
+                    double gsum = 0;
+                    double gv[NSLOT];
+                    if ( !pld || !has ) { }
                     else if ( ref_gt )          /* mcall.c:713-743 */
                     {
-                        gt0 = MCB_GT_UNPHASED(0); gt1 = pld==2 ? MCB_GT_UNPHASED(0) : I32_VEC_END;
-                        ac_lo += (unsigned long long)pld;
+                        outc = make_int4(MCB_GT_UNPHASED(0), pld==2 ? MCB_GT_UNPHASED(0) : I32_VEC_END, pld, 0);
                     }
-                    else                        /* mcall.c:787-840, literal */
+                    else                        /* mcall.c:787-840, literal arithmetic */
                     {
-                        double best = 0; int g0 = 0, g1 = 0;
-                        double ghom[NALS], ghet[NPAIR ? NPAIR : 1];
-                        #pragma unroll
-                        for (int x=0; x<NALS; x++)
+                        called = true;
+                        const bool fast = !(orv & ~255);
+                        const double r = fast ? rcp_shared(sum) : 0.0;
+                        auto pdg_of = [&](int k) -> double
                         {
-                            ghom[x] = 0;
-                            if ( gals & (1u<<x) )
+                            double pk;
+                            if ( NALS==1 ) pk = p[0];
+                            else if ( NALS==2 ) pk = k==1 ? p[1] : (k==2 ? p[2] : (jgt4[0] ? p[2] : p[0]));
+                            else
                             {
-                                const double pdg = __ddiv_rn(p[hom_idx(x)], sum);
-                                const double lk = pld==2 ? __dmul_rn(__dmul_rn(pdg, sh.q[x]), sh.q[x]) : __dmul_rn(pdg, sh.q[x]);
-                                ghom[x] = (double)__double2float_rn(lk);
-                                if ( best < lk ) { best = lk; g0 = sh.als_map[x]; }
+                                const int v = lds32(row_s + (uint32_t)jgt4[k<NSLOT?k:0]);
+                                pk = (fast || v<256) ? lds64(pl2p_s + 8u*(uint32_t)(v & 255)) : big_pl_to_p(a.tab, v, &tflags2);
                             }
+                            return fast ? div_shared(pk, sum, r) : __ddiv_rn(pk, sum);
+                        };
+                        double best = 0; int bk = 0;        /* default 0/0 when every lk is 0 (mcall.c:787-789) */
+                        bool any_best = false;
+                        #pragma unroll
+                        for (int k=0; k<NSLOT; k++) gv[k] = 0;
+                        /* homozygous / haploid, a ascending (mcall.c:793-808) */
+                        {
+                            const double pdg = pdg_of(0);
+                            const double lk = pld==2 ? __dmul_rn(__dmul_rn(pdg,q0),q0) : __dmul_rn(pdg,q0);
+                            gv[0] = lk;
+                            if ( best < lk ) { best = lk; bk = 0; any_best = true; }
+                        }
+                        if constexpr ( MAXSEL>1 ) if ( nsel>1 )
+                        {
+                            const double pdg = pdg_of(2);
+                            const double lk = pld==2 ? __dmul_rn(__dmul_rn(pdg,q1),q1) : __dmul_rn(pdg,q1);
+                            gv[2] = lk;
+                            if ( best < lk ) { best = lk; bk = 2; any_best = true; }
+                        }
+                        if constexpr ( MAXSEL>2 ) if ( nsel>2 )
+                        {
+                            const double pdg = pdg_of(5);
+                            const double lk = pld==2 ? __dmul_rn(__dmul_rn(pdg,q2),q2) : __dmul_rn(pdg,q2);
+                            gv[5] = lk;
+                            if ( best < lk ) { best = lk; bk = 5; any_best = true; }
                         }
                         if ( pld==2 )
                         {
-                            g1 = g0;
-                            #pragma unroll
-                            for (int x=1; x<NALS; x++)
-                                #pragma unroll
-                                for (int y=0; y<x; y++)
-                                {
-                                    ghet[pair_idx(x,y)] = 0;
-                                    if ( (gals & (1u<<x)) && (gals & (1u<<y)) )
-                                    {
-                                        const double pdg = __ddiv_rn(p[gt_idx(x,y)], sum);
-                                        const double lk = __dmul_rn(__dmul_rn(__dmul_rn(2.0,pdg), sh.q[x]), sh.q[y]);
-                                        ghet[pair_idx(x,y)] = (double)__double2float_rn(lk);
-                                        if ( best < lk ) { best = lk; g0 = sh.als_map[y]; g1 = sh.als_map[x]; }
-                                    }
-                                }
-                            gt0 = MCB_GT_UNPHASED(g0); gt1 = MCB_GT_UNPHASED(g1);
-                            if ( g0<4 ) ac_lo += 1ull<<(16*g0); else ac_hi += 1ull<<(16*(g0-4));
-                            if ( g1<4 ) ac_lo += 1ull<<(16*g1); else ac_hi += 1ull<<(16*(g1-4));
+                            /* heterozygous: (s1,s0), (s2,s0), (s2,s1)  (mcall.c:812-834) */
+                            if constexpr ( MAXSEL>1 ) if ( nsel>1 )
+                            {
+                                const double lk = __dmul_rn(__dmul_rn(__dmul_rn(2.0,pdg_of(1)),q1),q0);
+                                gv[1] = lk;
+                                if ( best < lk ) { best = lk; bk = 1; any_best = true; }
+                            }
+                            if constexpr ( MAXSEL>2 ) if ( nsel>2 )
+                            {
+                                const double lk = __dmul_rn(__dmul_rn(__dmul_rn(2.0,pdg_of(3)),q2),q0);
+                                gv[3] = lk;
+                                if ( best < lk ) { best = lk; bk = 3; any_best = true; }
+                                const double lk2 = __dmul_rn(__dmul_rn(__dmul_rn(2.0,pdg_of(4)),q2),q1);
+                                gv[4] = lk2;
+                                if ( best < lk2 ) { best = lk2; bk = 4; any_best = true; }
+                            }
+                            /* nothing beat 0: the reference keeps its 0/0 default, i.e. NEW allele 0 (mcall.c:788) */
+                            outc = any_best ? lds128(slot_s + 16u*(uint32_t)bk) : make_int4(MCB_GT_UNPHASED(0), MCB_GT_UNPHASED(0), 2, 0);
                         }
                         else
                         {
-                            gt0 = MCB_GT_UNPHASED(g0); gt1 = I32_VEC_END;
-                            if ( g0<4 ) ac_lo += 1ull<<(16*g0); else ac_hi += 1ull<<(16*(g0-4));
+                            const int bx = bk==0 ? 0 : (bk==2 ? 1 : 2);
+                            outc = any_best ? lds128(hap_s + 16u*(uint32_t)bx) : make_int4(MCB_GT_UNPHASED(0), I32_VEC_END, 1, 0);
                         }
-                        if ( want_gq )          /* mcall.c:843-878: max and sum over gps[0..nmax) in index order */
+                        if ( want_gqm )         /* mcall.c:843-878: max and sum over the float32 gps[0..nmax) in index order */
                         {
-                            double gmax = 0, gsum = 0;
-                            if ( pld==2 )
+                            double gmax;
+                            #pragma unroll
+                            for (int k=0; k<NSLOT; k++) gv[k] = (double)__double2float_rn(gv[k]);
+                            if ( inc_full )
                             {
+                                /* float rounding is monotone: max of the rounded values = rounded max */
+                                gmax = (double)__double2float_rn(best);
+                                gsum = gv[0];
                                 #pragma unroll
-                                for (int x=0; x<NALS; x++)
-                                {
-                                    if ( !(gals & (1u<<x)) ) continue;
-                                    #pragma unroll
-                                    for (int y=0; y<x; y++)
-                                    {
-                                        if ( !(gals & (1u<<y)) ) continue;
-                                        if ( gt_idx(sh.als_map[x], sh.als_map[y]) < ngt_new )
-                                        {
-                                            const double g = ghet[pair_idx(x,y)];
-                                            if ( gmax < g ) gmax = g;
-                                            gsum = __dadd_rn(gsum, g);
-                                        }
-                                    }
-                                    if ( hom_idx(sh.als_map[x]) < ngt_new )
-                                    {
-                                        const double g = ghom[x];
-                                        if ( gmax < g ) gmax = g;
-                                        gsum = __dadd_rn(gsum, g);
-                                    }
-                                }
+                                for (int k=1; k<NSLOT; k++) gsum = __dadd_rn(gsum, gv[k]);     /* absent slots hold +0 */
                             }
                             else
                             {
+                                gmax = 0;
+                                const uint32_t inc = pld==2 ? inc_dip : ((inc_hap&1u) | ((inc_hap&2u)<<1) | ((inc_hap&4u)<<3));
                                 #pragma unroll
-                                for (int x=0; x<NALS; x++)
-                                    if ( (gals & (1u<<x)) && sh.als_map[x] < grp_nals )
+                                for (int k=0; k<NSLOT; k++)
+                                    if ( inc & (1u<<k) )
                                     {
-                                        const double g = ghom[x];
-                                        if ( gmax < g ) gmax = g;
-                                        gsum = __dadd_rn(gsum, g);
+                                        if ( gmax < gv[k] ) gmax = gv[k];
+                                        gsum = __dadd_rn(gsum, gv[k]);
                                     }
                             }
                             const double xx = __dadd_rn(1.0, -__ddiv_rn(gmax, gsum));
                             if ( !(xx==xx) ) gq = 127;      /* NaN (0/0): `max<=INT8_MAX` is false => INT8_MAX */
                             else
                             {
-                                /* (int)(-4.34294*log(x)) from host-libm thresholds; float estimate, then exact fix-up */
-                                int k = xx > 0 ? (int)(-3.0102999f*__log2f((float)xx)) : 127;
+                                /* (int)(-4.34294*log(x)) from host-libm thresholds: float estimate, exact fix-up */
+                                int k = __float2int_rz(-3.0102999f*lg2_approx((float)xx));
                                 k = max(0, min(127, k));
-                                while ( k<127 && xx <= sh.gq_thr[k+1] ) k++;
-                                while ( k>0 && xx > sh.gq_thr[k] ) k--;
+                                if ( xx <= lds64(thr_s + 8u*(uint32_t)(k+1)) ) { k++; while ( xx <= lds64(thr_s + 8u*(uint32_t)(k+1)) ) k++; }
+                                else while ( xx > lds64(thr_s + 8u*(uint32_t)k) ) k--;
                                 gq = k;
                             }
                         }
                     }
-                    if ( out_gt ) out_gt[s0+s] = make_int2(gt0, gt1);
-                    if ( out_gq ) out_gq[s0+s] = gq;
-                    if ( out_pl )               /* mcall.c:1158-1194; `row` holds the filled PLs */
+                    acc += (unsigned long long)(uint32_t)outc.z | ((unsigned long long)(uint32_t)outc.w << 32);
+                    const int sg = s0 + s;
+                    if ( out_gt ) out_gt[sg] = make_int2(outc.x, outc.y);
+                    if ( out_gq ) out_gq[sg] = gq;
+                    if ( out_pl )               /* mcall.c:1158-1194; the ring row holds the filled PLs */
                     {
-                        int32_t *dst = out_pl + (size_t)(s0+s)*ngt_new;
+                        int32_t *dst = out_pl + (size_t)sg*ngt_new;
                         if ( pld==2 )
                         {
                             #pragma unroll
-                            for (int k=0; k<G; k++) if ( k<ngt_new ) dst[k] = row[sh.pl_map[k]];
+                            for (int k=0; k<G; k++)
+                                if ( k<ngt_new ) dst[k] = lds32(row_s + (uint32_t)(k<NPLM ? plm4[k<NPLM?k:0] : 4*sh.pl_map[k]));
                         }
                         else if ( pld==1 )
                         {
                             #pragma unroll
                             for (int k=0; k<G; k++)
-                                if ( k<ngt_new ) dst[k] = k<nals_new ? row[sh.pl_map[hom_idx(k)]] : I32_VEC_END;
+                                if ( k<ngt_new ) dst[k] = k<nals_new ? lds32(row_s + 4u*(uint32_t)sh.pl_map[hom_idx(k)]) : I32_VEC_END;
                         }
                         else
                         {
                             #pragma unroll
                             for (int k=0; k<G; k++) if ( k<ngt_new ) dst[k] = k==0 ? I32_MISSING : I32_VEC_END;
+                        }
+                    }
+                    if ( out_gp )               /* FORMAT/GP, mcall.c:859-884 (gv[] holds the float32-rounded values) */
+                    {
+                        float *dst = out_gp + (size_t)sg*ngt_new;
+                        const int nmax = pld==2 ? ngt_new : (pld==1 ? grp_nals : 0);
+                        if ( !called )
+                        {
+                            for (int k=0; k<ngt_new; k++) dst[k] = 0.f;
+                            if ( nmax==0 ) { dst[0] = __uint_as_float(MCB_FLOAT_MISSING_BITS); if ( 1<ngt_new ) dst[1] = __uint_as_float(MCB_FLOAT_VECTOR_END_BITS); }
+                            else if ( nmax<ngt_new ) dst[nmax] = __uint_as_float(MCB_FLOAT_VECTOR_END_BITS);
+                        }
+                        else
+                        {
+                            const float zero = (float)__ddiv_rn(0.0, gsum);
+                            for (int k=0; k<ngt_new; k++) dst[k] = k<nmax ? zero : __uint_as_float(MCB_FLOAT_VECTOR_END_BITS);
+                            if ( pld==2 )
+                            {
+                                #pragma unroll
+                                for (int k=0; k<NSLOT; k++)
+                                    if ( inc_dip & (1u<<k) ) dst[sh.p2.igt[k]] = (float)__ddiv_rn(gv[k], gsum);
+                            }
+                            else
+                            {
+                                #pragma unroll
+                                for (int x=0; x<MAXSEL; x++)
+                                    if ( inc_hap & (1u<<x) ) dst[sh.p2.hap_new[x]] = (float)__ddiv_rn(gv[x*(x+3)/2], gsum);
+                            }
                         }
                     }
                 }
@@ -770,15 +1015,7 @@ __global__ void __launch_bounds__(BLOCK) mcall_site_kernel(const KArgs a)
                     if ( tid==0 && v+nstage < total_visits ) issue(v+nstage);
                 }
             }
-            /* ---- AC: packed 16-bit counters per thread -> shared int counters (mcall.c:839-840) */
-            #pragma unroll
-            for (int j=0; j<4; j++)
-            {
-                int c0 = (int)((ac_lo >> (16*j)) & 0xffff), c1 = (int)((ac_hi >> (16*j)) & 0xffff);
-                #pragma unroll
-                for (int off=16; off; off>>=1) { c0 += __shfl_xor_sync(0xffffffffu, c0, off); c1 += __shfl_xor_sync(0xffffffffu, c1, off); }
-                if ( lane==0 ) { if ( c0 ) atomicAdd(&sh.ac[j], c0); if ( c1 ) atomicAdd(&sh.ac[4+j], c1); }
-            }
+            flush_ac();
             if ( tflags2 ) atomicOr(&sh.flags, tflags2);
         }
         __syncthreads();
@@ -809,6 +1046,50 @@ __global__ void __launch_bounds__(BLOCK) mcall_site_kernel(const KArgs a)
 }
 
 /* ------------------------------------------------------------------------------------------------
+ *  division self-test: div_shared(a, b, rcp_shared(b)) must be bit-identical to a/b on the table domain
+ * ---------------------------------------------------------------------------------------------- */
+__global__ void selftest_div_kernel(const DevTables *tab, int mode, unsigned long long n, unsigned long long seed, unsigned long long *mismatch)
+{
+    unsigned long long bad = 0;
+    const unsigned long long stride = (unsigned long long)gridDim.x*blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x*blockDim.x + threadIdx.x; i<n; i += stride)
+    {
+        double num[15]; int g;
+        if ( mode==0 )      /* exhaustive biallelic: i encodes three PLs */
+        {
+            g = 3;
+            num[0] = tab->pl2p[i & 255]; num[1] = tab->pl2p[(i>>8) & 255]; num[2] = tab->pl2p[(i>>16) & 255];
+        }
+        else                /* random G = 6, 10 or 15 */
+        {
+            unsigned long long x = (i + 1)*0x9E3779B97F4A7C15ull ^ seed;
+            g = mode;
+            for (int j=0; j<g; j++)
+            {
+                x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull; x ^= x >> 27; x *= 0x94D049BB133111EBull; x ^= x >> 31;
+                /* skew towards small PLs like real data, but cover all 256 values */
+                int v = (x & 3) ? (int)((x>>8) & 255) : (int)((x>>8) & 15);
+                num[j] = tab->pl2p[v];
+            }
+        }
+        double sum = num[0];
+        for (int j=1; j<g; j++) sum = __dadd_rn(sum, num[j]);
+        const double r = rcp_shared(sum);
+        for (int j=0; j<g; j++)
+        {
+            double q1 = div_shared(num[j], sum, r), q2 = __ddiv_rn(num[j], sum);
+            if ( __double_as_longlong(q1) != __double_as_longlong(q2) ) bad++;
+        }
+    }
+    if ( bad ) atomicAdd(mismatch, bad);
+}
+cudaError_t launch_selftest_div(const DevTables *tab, int mode, unsigned long long n, unsigned long long seed, unsigned long long *mismatch, cudaStream_t st)
+{
+    selftest_div_kernel<<<148*8, 256, 0, st>>>(tab, mode, n, seed, mismatch);
+    return cudaGetLastError();
+}
+
+/* ------------------------------------------------------------------------------------------------
  *  site classification: one list of site indices per allele count (1..5), one for everything else
  * ---------------------------------------------------------------------------------------------- */
 __global__ void classify_sites_kernel(const uint8_t *nals, int nsites, int32_t *lists, int32_t *counts, int list_stride)
@@ -833,58 +1114,54 @@ __global__ void unsupported_sites_kernel(const int32_t *list, const int32_t *cou
     }
 }
 
-template<int NALS, bool PLOIDY>
+template<int NALS, bool PLOIDY, int BLOCK>
 static cudaError_t launch_one(const KArgs &a, int grid, size_t ring_bytes, cudaStream_t st)
 {
-    auto kern = mcall_site_kernel<NALS,PLOIDY>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bytes);
+    auto kern = mcall_site_kernel<NALS,PLOIDY,BLOCK>;
+    const size_t smem = align128(sizeof(Shared<NALS,BLOCK>)) + ring_bytes;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if ( e!=cudaSuccess ) return e;
-    kern<<<grid, BLOCK, ring_bytes, st>>>(a);
+    kern<<<grid, BLOCK, smem, st>>>(a);
     return cudaGetLastError();
 }
-
-cudaError_t launch_site_kernel(int nals, bool ploidy, const KArgs &a, int grid, size_t ring_bytes, cudaStream_t st)
-{
-    switch ( nals*2 + (ploidy?1:0) )
-    {
-        case 2:  return launch_one<1,false>(a,grid,ring_bytes,st);
-        case 3:  return launch_one<1,true >(a,grid,ring_bytes,st);
-        case 4:  return launch_one<2,false>(a,grid,ring_bytes,st);
-        case 5:  return launch_one<2,true >(a,grid,ring_bytes,st);
-        case 6:  return launch_one<3,false>(a,grid,ring_bytes,st);
-        case 7:  return launch_one<3,true >(a,grid,ring_bytes,st);
-        case 8:  return launch_one<4,false>(a,grid,ring_bytes,st);
-        case 9:  return launch_one<4,true >(a,grid,ring_bytes,st);
-        case 10: return launch_one<5,false>(a,grid,ring_bytes,st);
-        case 11: return launch_one<5,true >(a,grid,ring_bytes,st);
-    }
-    return cudaErrorInvalidValue;
-}
-
-template<int NALS, bool PLOIDY>
+template<int NALS, bool PLOIDY, int BLOCK>
 static cudaError_t occ_one(size_t ring_bytes, int *nb)
 {
-    auto kern = mcall_site_kernel<NALS,PLOIDY>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bytes);
+    auto kern = mcall_site_kernel<NALS,PLOIDY,BLOCK>;
+    const size_t smem = align128(sizeof(Shared<NALS,BLOCK>)) + ring_bytes;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if ( e!=cudaSuccess ) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(nb, kern, BLOCK, ring_bytes);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(nb, kern, BLOCK, smem);
 }
-cudaError_t site_kernel_occupancy(int nals, bool ploidy, size_t ring_bytes, int *nb)
+/*  one dispatcher for launch (nb==NULL) and occupancy query (nb!=NULL)  */
+template<int NALS>
+static cudaError_t dispatch(bool ploidy, int block, const KArgs *a, int grid, size_t ring_bytes, cudaStream_t st, int *nb)
 {
-    switch ( nals*2 + (ploidy?1:0) )
+#define MCB_CASE(P,B) return nb ? occ_one<NALS,P,B>(ring_bytes, nb) : launch_one<NALS,P,B>(*a, grid, ring_bytes, st)
+    if ( block==128 ) { if ( ploidy ) MCB_CASE(true,128); MCB_CASE(false,128); }
+    if ( block==256 ) { if ( ploidy ) MCB_CASE(true,256); MCB_CASE(false,256); }
+#undef MCB_CASE
+    return cudaErrorInvalidValue;
+}
+static cudaError_t dispatch_nals(int nals, bool ploidy, int block, const KArgs *a, int grid, size_t ring_bytes, cudaStream_t st, int *nb)
+{
+    switch ( nals )
     {
-        case 2:  return occ_one<1,false>(ring_bytes,nb);
-        case 3:  return occ_one<1,true >(ring_bytes,nb);
-        case 4:  return occ_one<2,false>(ring_bytes,nb);
-        case 5:  return occ_one<2,true >(ring_bytes,nb);
-        case 6:  return occ_one<3,false>(ring_bytes,nb);
-        case 7:  return occ_one<3,true >(ring_bytes,nb);
-        case 8:  return occ_one<4,false>(ring_bytes,nb);
-        case 9:  return occ_one<4,true >(ring_bytes,nb);
-        case 10: return occ_one<5,false>(ring_bytes,nb);
-        case 11: return occ_one<5,true >(ring_bytes,nb);
+        case 1: return dispatch<1>(ploidy, block, a, grid, ring_bytes, st, nb);
+        case 2: return dispatch<2>(ploidy, block, a, grid, ring_bytes, st, nb);
+        case 3: return dispatch<3>(ploidy, block, a, grid, ring_bytes, st, nb);
+        case 4: return dispatch<4>(ploidy, block, a, grid, ring_bytes, st, nb);
+        case 5: return dispatch<5>(ploidy, block, a, grid, ring_bytes, st, nb);
     }
     return cudaErrorInvalidValue;
+}
+cudaError_t launch_site_kernel(int nals, bool ploidy, int block, const KArgs &a, int grid, size_t ring_bytes, cudaStream_t st)
+{
+    return dispatch_nals(nals, ploidy, block, &a, grid, ring_bytes, st, nullptr);
+}
+cudaError_t site_kernel_occupancy(int nals, bool ploidy, int block, size_t ring_bytes, int *nb)
+{
+    return dispatch_nals(nals, ploidy, block, nullptr, 0, ring_bytes, nullptr, nb);
 }
 
 cudaError_t launch_classify(const uint8_t *nals, int nsites, int32_t *lists, int32_t *counts, int list_stride, cudaStream_t st)

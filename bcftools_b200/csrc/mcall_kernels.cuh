@@ -62,26 +62,13 @@ struct KArgs
     int tile_smpl, nstage;
 };
 
-/*  Per-site decision record shared between the two phases (shared memory).  */
-struct SiteState
-{
-    double   q[MCB_MAX_NALS];       /* group qsum widened to double: (double)(float) */
-    double   max_qual, lk_sum, ref_lk, gap;
-    uint32_t grp_als;               /* the group's own best allele set (mcall.c:706) */
-    uint32_t als_new;               /* union | REF | -A (mcall.c:1552-1574) */
-    int      grp_nals, nals_new, is_variant, ret_early;
-    uint32_t flags;
-    int8_t   als_map[MCB_MAX_NALS];
-    int16_t  pl_map[MCB_MAX_NALS*(MCB_MAX_NALS+1)/2 > 64 ? 64 : MCB_MAX_NALS*(MCB_MAX_NALS+1)/2];
-    int      ac[MCB_MAX_NALS];
-};
-
 }   // namespace mcb
 
 namespace mcb {
 /*  launchers implemented in mcall_kernels.cu  */
-cudaError_t launch_site_kernel(int nals, bool ploidy, const KArgs &a, int grid, size_t ring_bytes, cudaStream_t st);
+cudaError_t launch_site_kernel(int nals, bool ploidy, int block, const KArgs &a, int grid, size_t ring_bytes, cudaStream_t st);
 cudaError_t launch_classify(const uint8_t *nals, int nsites, int32_t *lists, int32_t *counts, int list_stride, cudaStream_t st);
 cudaError_t launch_unsupported(const int32_t *list, const int32_t *count, int32_t *ret, uint32_t *site_flags, const uint8_t *nals, cudaStream_t st);
-cudaError_t site_kernel_occupancy(int nals, bool ploidy, size_t ring_bytes, int *blocks_per_sm);
+cudaError_t site_kernel_occupancy(int nals, bool ploidy, int block, size_t ring_bytes, int *blocks_per_sm);
+cudaError_t launch_selftest_div(const DevTables *tab, int mode, unsigned long long n, unsigned long long seed, unsigned long long *mismatch, cudaStream_t st);
 }

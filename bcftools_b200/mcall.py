@@ -11,12 +11,12 @@ import numpy as np
 
 from . import abi
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libmcall_b200.so")
+_LIB_PATH = os.environ.get("MCALL_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libmcall_b200.so")
 _lib = None
 
 EXPORTS = ["mcb_init", "mcb_destroy", "mcb_set_ploidy", "mcb_call_device", "mcb_call_host", "mcb_host_alloc",
            "mcb_host_free", "mcb_strerror", "mcb_last_cuda_error", "mcb_get_theta", "mcb_get_pl2p", "mcb_get_stats",
-           "mcb_set_option", "mcb_version"]
+           "mcb_set_option", "mcb_version", "mcb_selftest_div"]
 
 
 class McallError(RuntimeError):
@@ -58,6 +58,8 @@ def lib():
         L.mcb_set_option.restype = C.c_int
         L.mcb_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int64]
         L.mcb_version.restype = C.c_int
+        L.mcb_selftest_div.restype = C.c_int
+        L.mcb_selftest_div.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64)]
         _lib = L
     return _lib
 
@@ -121,6 +123,12 @@ class MCaller:
         """mcb_call_device on already-built McbBatch/McbResult structs holding DEVICE pointers."""
         self._check(lib().mcb_call_device(self._ctx, C.byref(batch_struct), C.byref(result_struct), C.c_void_p(stream)),
                     "mcb_call_device")
+
+    def selftest_div(self, mode, n=0, seed=1):
+        """Number of quotients of the shared-reciprocal division that differ from IEEE a/b (must be 0)."""
+        bad = C.c_uint64(0)
+        self._check(lib().mcb_selftest_div(self._ctx, int(mode), int(n), int(seed), C.byref(bad)), "mcb_selftest_div")
+        return bad.value
 
     def close(self):
         if self._ctx:

@@ -1,0 +1,17 @@
+set -x
+cd $GRAFT_REPO_ROOT
+mkdir -p gpurun_out
+timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -5 | tee gpurun_out/pytest_gpu.log
+Q="python scripts/quick_bench.py"
+for lib in "" _minb3 _minb2; do
+ export MCALL_B200_LIB=$GRAFT_REPO_ROOT/bcftools_b200/lib/libmcall_b200$lib.so
+ for b in 256 128; do for tb in 8192 32768; do
+  echo "lib=$lib" | tee -a gpurun_out/quick5.log
+  $Q --config C2 --sites 4096 --rep 8 --block $b --opt tile_bytes=$tb 2>&1 | tail -1 | tee -a gpurun_out/quick5.log
+  $Q --config C3 --sites 4096 --rep 8 --block $b --opt tile_bytes=$tb 2>&1 | tail -1 | tee -a gpurun_out/quick5.log
+ done; done
+done
+unset MCALL_B200_LIB
+$Q --config C3 --sites 2048 --rep 4 --iters 2 --opt tile_bytes=32768 > gpurun_out/plain3.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:mcall_site_kernel -s 16 -c 4 -o gpurun_out/prof_c3_v4 $Q --config C3 --sites 2048 --rep 4 --iters 2 --opt tile_bytes=32768 > gpurun_out/ncu3.log 2>&1
+tail -2 gpurun_out/ncu3.log
