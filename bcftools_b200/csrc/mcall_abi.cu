@@ -42,7 +42,10 @@ struct mcb_ctx
     int32_t *d_lists = nullptr, *d_counts = nullptr;  int list_cap = 0;
     HostSlab slab[2];
     /* options */
-    int64_t opt_tile_bytes = 8192, opt_ring_bytes = 65536, opt_blocks_per_sm = 0, opt_slab_bytes = 256ll<<20, opt_block = 256;
+    int64_t opt_tile_bytes = 32768, opt_ring_bytes = 65536, opt_blocks_per_sm = 0, opt_slab_bytes = 256ll<<20, opt_block = 128;
+    int64_t opt_time_kernels = 0;
+    cudaEvent_t kev[NCLASS+1] = {};      /* events around the per-class launches (time_kernels=1) */
+    bool kev_valid = false;
     /* stats */
     int64_t stats[4] = {0,0,0,0};
     std::string cuda_err;
@@ -129,6 +132,7 @@ extern "C" int mcb_set_option(mcb_ctx *ctx, const char *key, int64_t value)
     else if ( !strcmp(key,"ring_bytes") )    ctx->opt_ring_bytes = value;
     else if ( !strcmp(key,"blocks_per_sm") ) ctx->opt_blocks_per_sm = value;
     else if ( !strcmp(key,"slab_bytes") )    ctx->opt_slab_bytes = value;
+    else if ( !strcmp(key,"time_kernels") )  ctx->opt_time_kernels = value;
     else if ( !strcmp(key,"block") )         { if ( value!=128 && value!=256 ) return MCB_EINVAL; ctx->opt_block = value; }
     else return MCB_EINVAL;
     return MCB_OK;
@@ -200,8 +204,10 @@ extern "C" void mcb_destroy(mcb_ctx *ctx)
     {
         if ( ctx->slab[i].stream ) cudaStreamDestroy(ctx->slab[i].stream);
         if ( ctx->slab[i].done ) cudaEventDestroy(ctx->slab[i].done);
+        
         cudaFree(ctx->slab[i].dev); cudaFree(ctx->slab[i].lists); cudaFree(ctx->slab[i].counts);
     }
+    for (int i=0; i<=NCLASS; i++) if ( ctx->kev[i] ) cudaEventDestroy(ctx->kev[i]);
     delete ctx;
 }
 
@@ -228,6 +234,18 @@ extern "C" void *mcb_host_alloc(size_t bytes)
     return p;
 }
 extern "C" void mcb_host_free(void *ptr) { if ( ptr ) cudaFreeHost(ptr); }
+
+/*  Device time of the site kernel of each allele-count class in the last mcb_call_device (needs option
+ *  time_kernels=1; synchronises the events).  ms[k] for k=1..5; ms[0] = sum.                              */
+extern "C" int mcb_get_kernel_times(mcb_ctx *ctx, float ms[6])
+{
+    if ( !ctx || !ms || !ctx->kev_valid ) return MCB_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaEventSynchronize(ctx->kev[5]));
+    ms[0] = 0;
+    for (int k=1; k<=5; k++) { CK(cudaEventElapsedTime(&ms[k], ctx->kev[k-1], ctx->kev[k])); ms[0] += ms[k]; }
+    return MCB_OK;
+}
 
 /*  Self-test of the shared-reciprocal division used by phase 2 (see rcp_shared/div_shared in mcall_kernels.cu):
  *  mode 0 = exhaustive biallelic domain (256^3 PL triples), mode 6/10/15 = n random multi-allelic vectors.
@@ -280,6 +298,12 @@ static int enqueue(mcb_ctx *ctx, const mcb_batch *b, const mcb_result *r, int32_
     a.nsmpl = ctx->p.nsmpl; a.max_nals = ctx->p.max_nals; a.flag = ctx->p.flag; a.output_tags = ctx->p.output_tags;
     a.theta = ctx->theta_log; a.tie_eps = ctx->p.tie_eps; a.use_prior = ctx->p.use_prior;
     const bool ploidy = ctx->any_nondiploid;
+    const bool timing = ctx->opt_time_kernels && lists==ctx->d_lists;
+    if ( timing )
+    {
+        for (int i=0; i<=NCLASS; i++) if ( !ctx->kev[i] ) CK(cudaEventCreate(&ctx->kev[i]));
+        CK(cudaEventRecord(ctx->kev[0], st));
+    }
     for (int nals=1; nals<=5; nals++)
     {
         size_t ring; tile_geometry(ctx, nals, &a.tile_smpl, &a.nstage, &ring);
@@ -291,7 +315,9 @@ static int enqueue(mcb_ctx *ctx, const mcb_batch *b, const mcb_result *r, int32_
         int grid = (int)std::min<int64_t>((int64_t)b->nsites, (int64_t)ctx->nsm*nb);
         CK(launch_site_kernel(nals, ploidy, (int)ctx->opt_block, a, grid, ring, st));
         launches++;
+        if ( timing ) CK(cudaEventRecord(ctx->kev[nals], st));
     }
+    ctx->kev_valid = timing;
     CK(launch_unsupported(lists, counts, r->ret, r->site_flags, b->nals, st));
     launches++;
     ctx->stats[0] += launches;

@@ -16,7 +16,7 @@ _lib = None
 
 EXPORTS = ["mcb_init", "mcb_destroy", "mcb_set_ploidy", "mcb_call_device", "mcb_call_host", "mcb_host_alloc",
            "mcb_host_free", "mcb_strerror", "mcb_last_cuda_error", "mcb_get_theta", "mcb_get_pl2p", "mcb_get_stats",
-           "mcb_set_option", "mcb_version", "mcb_selftest_div"]
+           "mcb_set_option", "mcb_version", "mcb_selftest_div", "mcb_get_kernel_times"]
 
 
 class McallError(RuntimeError):
@@ -58,10 +58,50 @@ def lib():
         L.mcb_set_option.restype = C.c_int
         L.mcb_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int64]
         L.mcb_version.restype = C.c_int
+        L.mcb_get_kernel_times.restype = C.c_int
+        L.mcb_get_kernel_times.argtypes = [C.c_void_p, C.c_void_p]
         L.mcb_selftest_div.restype = C.c_int
         L.mcb_selftest_div.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64)]
         _lib = L
     return _lib
+
+
+def pinned_empty(shape, dtype):
+    """numpy array backed by pinned host memory from mcb_host_alloc (kept alive by the returned array)."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) if np.ndim(shape) else int(shape)
+    nbytes = max(1, n * dtype.itemsize)
+    ptr = lib().mcb_host_alloc(nbytes)
+    if not ptr:
+        raise McallError("mcb_host_alloc failed")
+    buf = (C.c_char * nbytes).from_address(ptr)
+    arr = np.frombuffer(buf, dtype=dtype, count=n).reshape(shape)
+    _PINNED[arr.ctypes.data] = ptr
+    return arr
+
+
+_PINNED = {}
+
+
+def pin_batch(batch):
+    """Copy every array of a HostBatch into pinned memory (in place)."""
+    for name in abi.BATCH_FIELDS:
+        a = getattr(batch, name)
+        if a is not None:
+            p = pinned_empty(a.shape, a.dtype)
+            p[...] = a
+            setattr(batch, name, p)
+    return batch
+
+
+def pin_result(res):
+    for name in abi.RESULT_FIELDS:
+        a = getattr(res, name)
+        if a is not None:
+            p = pinned_empty(a.shape, a.dtype)
+            p[...] = a
+            setattr(res, name, p)
+    return res
 
 
 class MCaller:
@@ -123,6 +163,12 @@ class MCaller:
         """mcb_call_device on already-built McbBatch/McbResult structs holding DEVICE pointers."""
         self._check(lib().mcb_call_device(self._ctx, C.byref(batch_struct), C.byref(result_struct), C.c_void_p(stream)),
                     "mcb_call_device")
+
+    def kernel_times_ms(self):
+        """Per allele-count class device time of the last call_device (option time_kernels=1): array[6], [0]=sum."""
+        out = np.zeros(6, np.float32)
+        self._check(lib().mcb_get_kernel_times(self._ctx, out.ctypes.data), "mcb_get_kernel_times")
+        return out
 
     def selftest_div(self, mode, n=0, seed=1):
         """Number of quotients of the shared-reciprocal division that differ from IEEE a/b (must be 0)."""

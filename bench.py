@@ -1,0 +1,343 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the B200-native `bcftools call -m` hot path.
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched by torchrun, one rank per GPU)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+Metric (BASELINE.json): sample-genotype calls per second (one call = one (sample, site) genotype call).
+Workload at N=1 (config.workload): BASELINE.json configs[2] "C3" -- 2,504 samples (1000G-shaped), 2-5 alleles per
+site (70/20/7/3 %), allele trimming on, FORMAT/GQ requested.  This is the config the north-star target is quoted on
+and it fits one GPU.  A STEP is one pass of the hot path over one batch of `--sites` sites (default 16,384 unique
+synthetic sites replicated x4 in HBM = 65,536 sites, 2.9 GB of PL; the 1M-site job is 15.3 such steps).
+
+  value     device-resident throughput: inputs already in HBM, CUDA events on the launching stream, max over ranks
+  e2e       the same metric through the C-ABI host entry point mcb_call_host with pinned HOST buffers:
+            H2D of the PL slab + kernels + D2H of GT/GQ/PL/site records inside the timed region
+  roofline  dominant kernel (mcall_site_kernel<2 alleles>): algorithmic bytes of its sites / its own device time
+  cpu_baseline  the CPU oracle on this box's host cores on a bounded sample of the same workload (rank 0, N=1)
+
+The reference arm times the reference's own CPU implementation of the path (oracle/_ref = the unmodified mcall.c
+compiled against the htslib stub; falls back to the plain-C port when that library was not built) with one process
+per host core over contiguous site shards.  Rank 0 alone runs it.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "sample_genotype_calls_per_s"
+UNIT = "calls/s"
+WORKLOAD = "C3"
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """SM clocks and throttle reasons sampled DURING the timed region (B200_PROFILING.md): NVML every ~5 ms,
+    falling back to the nvidia-smi query of the recipe when pynvml is unavailable."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.idx, self.stop_flag = gpu_index, False
+        self.sm, self.mx, self.reasons, self.power = [], [], set(), []
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n = self.nvml
+        self.sm.append(float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)))
+        self.mx.append(float(n.nvmlDeviceGetMaxClockInfo(self.h, n.NVML_CLOCK_SM)))
+        try:
+            self.power.append(n.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+        except Exception:
+            pass
+        r = n.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(n, "nvmlDeviceGetCurrentClocksEventReasons") \
+            else n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        for name, bit in (("hw_slowdown", 0x8), ("sw_power_cap", 0x4), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40)):
+            if r & bit:
+                self.reasons.add(name)
+
+    def _sample_smi(self):
+        out = subprocess.run(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                             capture_output=True, text=True, timeout=5).stdout.strip()
+        r = [x.strip() for x in out.split(",")]
+        if len(r) >= 9:
+            self.sm.append(float(r[1])); self.mx.append(float(r[2]))
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    self.reasons.add(name)
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                self._sample_nvml() if self.nvml else self._sample_smi()
+            except Exception:
+                pass
+            time.sleep(0.005 if self.nvml else 0.1)
+
+    def summary(self):
+        return dict(sm_mhz=float(np.median(self.sm)) if self.sm else None, sm_max_mhz=max(self.mx) if self.mx else None,
+                    reasons=sorted(self.reasons), samples=len(self.sm), power_w_max=max(self.power) if self.power else None,
+                    source="nvml" if self.nvml else "nvidia-smi")
+
+
+def shard_batch(batch, nproc):
+    """Contiguous site shards, one per process (built before the timed region)."""
+    R = batch.nsites
+    return [batch.subset(range(R * i // nproc, R * (i + 1) // nproc)) for i in range(nproc) if R * (i + 1) // nproc > R * i // nproc]
+
+
+class OraclePool:
+    """One forked worker per shard, started once; every step() runs the CPU oracle over all shards in parallel
+    and returns the wall seconds between the start and the end barrier (fork cost stays outside the timing)."""
+
+    def __init__(self, params, shards, tab, kind, nsteps):
+        import multiprocessing as mp
+        from oracle import pyoracle
+        pyoracle._load(kind)
+        ctx = mp.get_context("fork")
+        n = len(shards)
+        self.start, self.done = ctx.Barrier(n + 1), ctx.Barrier(n + 1)
+
+        def work(shard):
+            from bcftools_b200 import abi
+            res = abi.HostResult(shard)         # allocated once, outside the timed steps
+            for _ in range(nsteps):
+                self.start.wait()
+                pyoracle.call(kind, params, shard, tab, result=res)
+                self.done.wait()
+
+        self.procs = [ctx.Process(target=work, args=(sh,), daemon=True) for sh in shards]
+        for p in self.procs:
+            p.start()
+
+    def step(self):
+        self.start.wait()
+        t0 = time.perf_counter()
+        self.done.wait()
+        return time.perf_counter() - t0
+
+    def close(self):
+        for p in self.procs:
+            p.join(timeout=10)
+
+
+def run_reference(args, rank):
+    """`--impl reference`: the reference's own CPU implementation of the path on the host cores (rank 0 only)."""
+    if rank != 0:
+        return
+    from bcftools_b200 import synth
+    from oracle import pyoracle
+    pyoracle.build(want_ref=True)
+    kind = "reference" if pyoracle.have_ref() else "port"
+    ncores = os.cpu_count() or 1
+    sites = args.ref_sites
+    params, batch, tab = synth.make_batch(WORKLOAD, sites, with_groups=0)
+    shards = shard_batch(batch, ncores)
+    pool = OraclePool(params, shards, tab, kind, args.warmup + args.steps)
+    for _ in range(args.warmup):
+        pool.step()
+    dt = 0.0
+    for _ in range(args.steps):
+        dt += pool.step()
+    pool.close()
+    value = args.steps * sites * params.nsmpl / dt
+    line = dict(impl="reference", metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=1e3 * dt / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
+                data="synthetic", config=dict(workload=WORKLOAD, nsmpl=params.nsmpl, sites_per_step=sites,
+                                              note="bounded sample of the same synthetic workload; reference arithmetic is single-threaded "
+                                                   "(--threads n/a, vcfcall.c:692), parallelised as one process per core over site shards"),
+                cpu_baseline=dict(value=value, unit=UNIT, cores=ncores, kind=kind, sample=f"{sites} sites x {params.nsmpl} samples per step"),
+                e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--sites", type=int, default=16384, help="unique synthetic sites generated per rank")
+    ap.add_argument("--replicate", type=int, default=4, help="HBM copies of the unique sites forming one step")
+    ap.add_argument("--e2e-sites", type=int, default=8192)
+    ap.add_argument("--ref-sites", type=int, default=8192)
+    ap.add_argument("--cpu-sites", type=int, default=2048)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from bcftools_b200 import abi, device, mcall, synth
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- workload: each rank owns a contiguous range of sites (its own seed offset): weak scaling, no collective
+    params, hb, tab = synth.make_batch(WORKLOAD, args.sites, seed_offset=rank, with_groups=0)
+    params.device = local_rank
+    mc = mcall.MCaller(params, ploidy_tab=tab, options={"time_kernels": 1})
+    db = device.DeviceBatch(hb, device=f"cuda:{local_rank}", replicate=args.replicate)
+    dr = device.DeviceResult(db)
+    b, r = db.c_struct(), dr.c_struct()
+    stream = torch.cuda.current_stream().cuda_stream
+    calls_per_step = db.nsites * params.nsmpl
+
+    for _ in range(max(3, args.warmup)):
+        mc.call_device(b, r, stream)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ktimes = np.zeros(6)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        mc.call_device(b, r, stream)
+    e1.record()
+    barrier()
+    dev_s = e0.elapsed_time(e1) * 1e-3
+    launches = int(mc.stats()[0]) * args.steps
+    # per-class kernel times of one more (untimed) step for the roofline of the dominant kernel
+    per_class = []
+    for _ in range(5):
+        mc.call_device(b, r, stream)
+        per_class.append(mc.kernel_times_ms())
+    ktimes = np.median(np.array(per_class), axis=0)
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    # ---- parity spot check of this very run (rank 0): CUDA result of the first sites against the CPU oracle
+    res = dr.to_host()
+    rd_all, wr_all = synth.algorithmic_bytes(hb, res, params.output_tags)
+    parity = None
+    cpu = None
+    if rank == 0 and not args.no_cpu:
+        from oracle import pyoracle
+        from tests import parity as par
+        pyoracle.build(want_ref=True)
+        kind = "reference" if pyoracle.have_ref() else "port"
+        n = min(args.cpu_sites, hb.nsites)
+        sub = hb.subset(range(n))
+        t0 = time.perf_counter()
+        exp, secs = pyoracle.call(kind, params, sub, tab)
+        got = abi.HostResult(sub)
+        for name in abi.RESULT_FIELDS:
+            a = getattr(res, name)
+            if a is None or getattr(got, name) is None:
+                continue
+            if name in ("pl", "gp"):
+                getattr(got, name)[...] = a[:sub.pl.size]
+            else:
+                getattr(got, name)[...] = a[:n]
+        st = par.compare(got, exp, params)
+        parity = dict(sites=n, compared=st["compared"], near_ties=len(st["near_ties"]), qual_max_rel=st["qual_max_rel"], oracle=kind)
+        if world == 1:
+            cpu = dict(value=n * params.nsmpl / secs, unit=UNIT, cores=1, kind=kind,
+                       sample=f"first {n} sites x {params.nsmpl} samples of the step, time inside the per-record calls only")
+
+    # ---- end to end through the host entry point (pinned host buffers, copies inside the timed region)
+    e2e = None
+    if not args.no_e2e:
+        ne = min(args.e2e_sites, hb.nsites)
+        sub = mcall.pin_batch(hb.subset(range(ne)))
+        hres = mcall.pin_result(abi.HostResult(sub))
+        for _ in range(2):
+            mc.call_host(sub, hres)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            mc.call_host(sub, hres)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device=f"cuda:{local_rank}", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        h2d = sum(getattr(sub, k).nbytes for k in ("pl", "pl_off", "nals", "unseen", "qs") if getattr(sub, k) is not None)
+        d2h = sum(getattr(hres, k).nbytes for k in ("ret", "als_new", "als_map", "qual", "ac", "an", "site_flags", "diag", "gt", "gq", "pl")
+                  if getattr(hres, k) is not None)
+        e2e = dict(value=world * args.steps * ne * params.nsmpl / dt, unit=UNIT, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
+                   sites_per_step=ne, ms_per_step=1e3 * dt / args.steps)
+
+    # ---- max over ranks of the device time
+    if world > 1:
+        t = torch.tensor([dev_s], device=f"cuda:{local_rank}", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_s = float(t.item())
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        # dominant kernel = the biallelic site kernel: its sites' algorithmic bytes / its own device time
+        is2 = hb.nals == 2
+        sub2 = hb.subset(np.where(is2)[0]) if is2.any() else None
+        roof = None
+        if sub2 is not None and ktimes[2] > 0:
+            res2 = abi.HostResult(sub2)
+            idx = np.where(is2)[0]
+            res2.ret[...] = res.ret[idx]
+            res2.site_flags[...] = res.site_flags[idx]
+            rd2, wr2 = synth.algorithmic_bytes(sub2, res2, params.output_tags)
+            bytes2 = (rd2 + wr2) * args.replicate
+            ach = bytes2 / (ktimes[2] * 1e-3) / 1e9
+            roof = dict(bound="hbm", kernel="mcall_site_kernel<NALS=2> (70 % of the sites of a step)", achieved=ach, peak=peak, unit="GB/s",
+                        frac=ach / peak, traffic=None, peak_source=peak_src, algorithmic_bytes_per_launch=int(bytes2),
+                        kernel_ms=float(ktimes[2]), kernel_share_of_step=float(ktimes[2] / ktimes[0]),
+                        all_kernels=dict(achieved=(rd_all + wr_all) * args.replicate / (ktimes[0] * 1e-3) / 1e9,
+                                         ms_per_class={str(k): float(ktimes[k]) for k in range(1, 6)}))
+        value = world * args.steps * calls_per_step / dev_s
+        line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(3, args.warmup),
+                    ms_per_step=1e3 * dev_s / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
+                    data="synthetic",
+                    config=dict(workload=WORKLOAD, nsmpl=params.nsmpl, sites_per_step_per_gpu=db.nsites, unique_sites=hb.nsites,
+                                replicate=args.replicate, allele_mix="2:70%,3:20%,4:7%,5:3%", flags="call -m -a GQ",
+                                l2_policy="inputs larger than L2 (%.2f GB of PL per step)" % (db.pl_bytes() / 1e9),
+                                bytes_per_call=(rd_all + wr_all) / (hb.nsites * params.nsmpl), generator_version=synth.GENERATOR_VERSION),
+                    gpu_launches=launches, clocks=sampler.summary(), roofline=roof, cpu_baseline=cpu, e2e=e2e, parity=parity)
+        print(json.dumps(line, default=lambda o: o.item() if hasattr(o, 'item') else str(o)), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

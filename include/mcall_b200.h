@@ -162,6 +162,9 @@ int   mcb_get_stats(const mcb_ctx *ctx, int64_t stats[4]);
 /*  tuning knob for experiments (threads per block, tile samples, ...): see DESIGN.md */
 int   mcb_set_option(mcb_ctx *ctx, const char *key, int64_t value);
 int   mcb_version(void);
+/*  device milliseconds of the site kernel per allele-count class (ms[1..5], ms[0]=sum) of the last
+ *  mcb_call_device; requires mcb_set_option(ctx,"time_kernels",1) */
+int   mcb_get_kernel_times(mcb_ctx *ctx, float ms[6]);
 /*  device self-test of the shared-reciprocal IEEE division (mode 0: exhaustive 256^3 biallelic domain;
  *  mode 6/10/15: n random vectors of that many genotypes); *mismatch must come back 0 */
 int   mcb_selftest_div(mcb_ctx *ctx, int mode, uint64_t n, uint64_t seed, uint64_t *mismatch);
