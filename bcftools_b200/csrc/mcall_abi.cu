@@ -43,7 +43,11 @@ struct mcb_ctx
     HostSlab slab[2];
     /* options */
     int64_t opt_tile_bytes = 32768, opt_ring_bytes = 65536, opt_blocks_per_sm = 0, opt_slab_bytes = 256ll<<20, opt_block = 128;
-    int64_t opt_time_kernels = 0;
+    int64_t opt_time_kernels = 0, opt_concurrent = 1;
+    int64_t opt_ring_bytes_c[NCLASS] = {0,0,0,0,0,0};   /* per allele-count class override of ring_bytes (0 = opt_ring_bytes) */
+    int64_t opt_block_c[NCLASS] = {0,0,0,0,0,0};        /* per class override of the CTA size */
+    cudaStream_t cstream[NCLASS] = {};   /* one stream per allele-count class: their persistent grids overlap */
+    cudaEvent_t  cev_fork = nullptr, cev_join[NCLASS] = {};
     cudaEvent_t kev[NCLASS+1] = {};      /* events around the per-class launches (time_kernels=1) */
     bool kev_valid = false;
     /* stats */
@@ -133,6 +137,13 @@ extern "C" int mcb_set_option(mcb_ctx *ctx, const char *key, int64_t value)
     else if ( !strcmp(key,"blocks_per_sm") ) ctx->opt_blocks_per_sm = value;
     else if ( !strcmp(key,"slab_bytes") )    ctx->opt_slab_bytes = value;
     else if ( !strcmp(key,"time_kernels") )  ctx->opt_time_kernels = value;
+    else if ( !strcmp(key,"concurrent") )    ctx->opt_concurrent = value;
+    else if ( !strncmp(key,"ring_bytes_",11) && key[11]>='1' && key[11]<='5' && !key[12] ) ctx->opt_ring_bytes_c[key[11]-'0'] = value;
+    else if ( !strncmp(key,"block_",6) && key[6]>='1' && key[6]<='5' && !key[7] )
+    {
+        if ( value!=0 && value!=128 && value!=256 ) return MCB_EINVAL;
+        ctx->opt_block_c[key[6]-'0'] = value;
+    }
     else if ( !strcmp(key,"block") )         { if ( value!=128 && value!=256 ) return MCB_EINVAL; ctx->opt_block = value; }
     else return MCB_EINVAL;
     return MCB_OK;
@@ -208,6 +219,8 @@ extern "C" void mcb_destroy(mcb_ctx *ctx)
         cudaFree(ctx->slab[i].dev); cudaFree(ctx->slab[i].lists); cudaFree(ctx->slab[i].counts);
     }
     for (int i=0; i<=NCLASS; i++) if ( ctx->kev[i] ) cudaEventDestroy(ctx->kev[i]);
+    for (int i=1; i<NCLASS; i++) { if ( ctx->cstream[i] ) cudaStreamDestroy(ctx->cstream[i]); if ( ctx->cev_join[i] ) cudaEventDestroy(ctx->cev_join[i]); }
+    if ( ctx->cev_fork ) cudaEventDestroy(ctx->cev_fork);
     delete ctx;
 }
 
@@ -268,15 +281,18 @@ extern "C" int mcb_selftest_div(mcb_ctx *ctx, int mode, uint64_t n, uint64_t see
 }
 
 /* ---- launch geometry -------------------------------------------------------------------------------- */
+static int class_block(const mcb_ctx *ctx, int nals) { return (int)(ctx->opt_block_c[nals] ? ctx->opt_block_c[nals] : ctx->opt_block); }
+
 static void tile_geometry(const mcb_ctx *ctx, int nals, int *tile_smpl, int *nstage, size_t *ring_bytes)
 {
     int G = nals*(nals+1)/2, S = ctx->p.nsmpl;
     int ts = (int)(ctx->opt_tile_bytes/(4*G));
     ts = std::max(256, ts/256*256);
-    ts = std::min(ts, 32*(int)ctx->opt_block);      /* the AC counters of phase 2 allow at most 63 samples per thread and tile */
+    ts = std::min(ts, 32*class_block(ctx, nals));      /* the AC counters of phase 2 allow at most 63 samples per thread and tile */
     int ntiles = (S + ts - 1)/ts;
     size_t tile_bytes = (size_t)ts*G*4;
-    int cap = (int)std::max<int64_t>(2, ctx->opt_ring_bytes/(int64_t)tile_bytes);
+    const int64_t ring_cap = ctx->opt_ring_bytes_c[nals] ? ctx->opt_ring_bytes_c[nals] : ctx->opt_ring_bytes;
+    int cap = (int)std::max<int64_t>(2, ring_cap/(int64_t)tile_bytes);
     int ns = std::min(MAX_STAGE, std::min(ntiles, cap));
     if ( ns<1 ) ns = 1;
     *tile_smpl = ts; *nstage = ns; *ring_bytes = tile_bytes*ns;
@@ -299,23 +315,44 @@ static int enqueue(mcb_ctx *ctx, const mcb_batch *b, const mcb_result *r, int32_
     a.theta = ctx->theta_log; a.tie_eps = ctx->p.tie_eps; a.use_prior = ctx->p.use_prior;
     const bool ploidy = ctx->any_nondiploid;
     const bool timing = ctx->opt_time_kernels && lists==ctx->d_lists;
+    /*  timing mode serialises the classes on the caller's stream (per-class events); otherwise every class runs on
+     *  its own stream so that the small persistent grids of the 3-5 allele classes overlap the biallelic one  */
+    const bool fork = ctx->opt_concurrent && !timing;
     if ( timing )
     {
         for (int i=0; i<=NCLASS; i++) if ( !ctx->kev[i] ) CK(cudaEventCreate(&ctx->kev[i]));
         CK(cudaEventRecord(ctx->kev[0], st));
     }
-    for (int nals=1; nals<=5; nals++)
+    if ( fork )
     {
+        if ( !ctx->cev_fork )
+        {
+            CK(cudaEventCreateWithFlags(&ctx->cev_fork, cudaEventDisableTiming));
+            for (int i=1; i<NCLASS; i++)
+            {
+                CK(cudaStreamCreateWithFlags(&ctx->cstream[i], cudaStreamNonBlocking));
+                CK(cudaEventCreateWithFlags(&ctx->cev_join[i], cudaEventDisableTiming));
+            }
+        }
+        CK(cudaEventRecord(ctx->cev_fork, st));
+    }
+    for (int nals=5; nals>=1; nals--)       /* the heavy, low-occupancy classes first */
+    {
+        if ( timing ) nals = 6 - nals;      /* timing mode keeps the ascending order of the event list */
         size_t ring; tile_geometry(ctx, nals, &a.tile_smpl, &a.nstage, &ring);
+        const int block = class_block(ctx, nals);
         a.site_list = lists + (size_t)nals*list_stride; a.site_count = counts + nals;
         int nb = 1;
-        CK(site_kernel_occupancy(nals, ploidy, (int)ctx->opt_block, ring, &nb));
+        CK(site_kernel_occupancy(nals, ploidy, block, ring, &nb));
         if ( nb<1 ) return cuda_fail(ctx, cudaErrorLaunchOutOfResources, "site kernel does not fit on an SM");
         if ( ctx->opt_blocks_per_sm>0 ) nb = std::min<int>(nb, (int)ctx->opt_blocks_per_sm);
         int grid = (int)std::min<int64_t>((int64_t)b->nsites, (int64_t)ctx->nsm*nb);
-        CK(launch_site_kernel(nals, ploidy, (int)ctx->opt_block, a, grid, ring, st));
+        cudaStream_t cs = fork ? ctx->cstream[nals] : st;
+        if ( fork ) CK(cudaStreamWaitEvent(cs, ctx->cev_fork, 0));
+        CK(launch_site_kernel(nals, ploidy, block, a, grid, ring, cs));
         launches++;
-        if ( timing ) CK(cudaEventRecord(ctx->kev[nals], st));
+        if ( fork ) { CK(cudaEventRecord(ctx->cev_join[nals], cs)); CK(cudaStreamWaitEvent(st, ctx->cev_join[nals], 0)); }
+        if ( timing ) { CK(cudaEventRecord(ctx->kev[nals], st)); nals = 6 - nals; }
     }
     ctx->kev_valid = timing;
     CK(launch_unsupported(lists, counts, r->ret, r->site_flags, b->nals, st));

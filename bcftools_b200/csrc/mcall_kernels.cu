@@ -214,45 +214,48 @@ __device__ __noinline__ double big_pl_to_p(const DevTables *tab, int v, uint32_t
     return (unsigned)v < (unsigned)MCB_PL2P_BIG ? tab->pl2p_big[v] : 0.0;
 }
 
-/*  One sample's PLs, likelihoods p[j] = pl2p[PL[j]] and their sum in index order (mcall.c:462-474).
- *  row_s = shared address of the PL vector.  Returns false for "no data" samples.                 */
+/*  One sample per lane, called by ALL 32 lanes of a warp: PLs, likelihoods p[j] = pl2p[PL[j]] and their sum in
+ *  index order (mcall.c:462-474).  The rare cases -- missing / vector_end values, PL >= 256 -- are detected with
+ *  one warp vote so that the common path is straight-line code; `fast` (warp-uniform) tells the caller that every
+ *  valid lane has all PLs in 0..255.  Lanes with valid==false must pass the address of some readable row.
+ *  Returns true when the lane's sample carries data.                                                          */
 template<int NALS>
-__device__ __forceinline__ bool load_sample(uint32_t row_s, uint32_t pl2p_s, int unseen, const DevTables *tab,
-                                            int (&pl)[Shape<NALS>::G], double (&p)[Shape<NALS>::G], double &sum, int &orv, uint32_t &flags)
+__device__ __forceinline__ bool load_sample_w(uint32_t row_s, uint32_t pl2p_s, bool valid, int unseen, const DevTables *tab,
+                                              int (&pl)[Shape<NALS>::G], double (&p)[Shape<NALS>::G], double &sum, bool &fast, uint32_t &flags)
 {
     constexpr int G = Shape<NALS>::G;
-    auto load_pl = [&]()
-    {
-        orv = 0;
-        #pragma unroll
-        for (int j=0; j<G; j++)
-        {
-            const int v = lds32(row_s + 4u*(uint32_t)j);
-            pl[j] = v; orv |= v;
-        }
-    };
-    load_pl();
-    if ( orv < 0 )
-    {
-        if ( !fix_missing(row_s, NALS, unseen) ) return false;
-        load_pl();
-        if ( orv < 0 ) return false;
-    }
-    if ( orv==0 ) return false;         /* PL=0,..,0: sum==n_gt, no data (mcall.c:529-537) */
-    if ( orv & ~255 )
-    {
-        #pragma unroll
-        for (int j=0; j<G; j++) p[j] = pl[j] < 256 ? lds64(pl2p_s + 8u*(uint32_t)pl[j]) : big_pl_to_p(tab, pl[j], &flags);
-    }
-    else
+    int orv = 0;
+    #pragma unroll
+    for (int j=0; j<G; j++) { pl[j] = lds32(row_s + 4u*(uint32_t)j); orv |= pl[j]; }
+    const bool special = valid && (unsigned)orv > 255u;     /* negative (sentinels) or >= 256 */
+    fast = !__any_sync(0xffffffffu, special);
+    bool data = valid && orv!=0;            /* PL=0,..,0: sum==n_gt, no data (mcall.c:529-537) */
+    if ( fast )
     {
         #pragma unroll
         for (int j=0; j<G; j++) p[j] = lds64(pl2p_s + 8u*(uint32_t)pl[j]);
     }
+    else
+    {
+        if ( valid && orv<0 )
+        {
+            data = fix_missing(row_s, NALS, unseen);
+            if ( data )
+            {
+                orv = 0;
+                #pragma unroll
+                for (int j=0; j<G; j++) { pl[j] = lds32(row_s + 4u*(uint32_t)j); orv |= pl[j]; }
+                data = orv>0;
+            }
+        }
+        #pragma unroll
+        for (int j=0; j<G; j++)
+            p[j] = !data ? 1.0 : ((unsigned)pl[j] < 256u ? lds64(pl2p_s + 8u*(uint32_t)pl[j]) : big_pl_to_p(tab, pl[j], &flags));
+    }
     sum = p[0];
     #pragma unroll
     for (int j=1; j<G; j++) sum = __dadd_rn(sum, p[j]);
-    return true;
+    return data;
 }
 
 /* ------------------------------------------------------------------------------------------------
@@ -264,7 +267,16 @@ template<int NALS, int BLOCK> struct MinBlocks
 #define MCB_MINB2 4         /* CTAs of 256 threads per SM the 1-2 allele kernels are compiled for (register cap 65536/(256*n)) */
 #endif
     static constexpr int per256 = NALS<=2 ? MCB_MINB2 : (NALS==3 ? 2 : 1);
-    static constexpr int value  = BLOCK==256 ? per256 : (NALS<=2 ? 2*MCB_MINB2 : (NALS==3 ? 4 : (NALS==4 ? 3 : 2)));
+    #ifndef MCB_MINB3
+#define MCB_MINB3 6
+#endif
+#ifndef MCB_MINB4
+#define MCB_MINB4 4
+#endif
+#ifndef MCB_MINB5
+#define MCB_MINB5 3
+#endif
+    static constexpr int value  = BLOCK==256 ? per256 : (NALS<=2 ? 2*MCB_MINB2 : (NALS==3 ? MCB_MINB3 : (NALS==4 ? MCB_MINB4 : MCB_MINB5)));
 };
 
 template<int NALS, bool PLOIDY, int BLOCK>
@@ -426,7 +438,7 @@ __global__ void __launch_bounds__(BLOCK, (MinBlocks<NALS,BLOCK>::value)) mcall_s
         #pragma unroll
         for (int k=0; k<NALS; k++) { plsum[k] = 0; plsum32[k] = 0; }
         /* coefficients of the small shapes live in registers; larger shapes read them from shared memory */
-        constexpr bool CF_REG = NALS<=3;
+        constexpr bool CF_REG = NALS<=2;
         double cfp[CF_REG ? (NPAIR ? NPAIR : 1)*5 : 1], cft[CF_REG ? (NTRI ? NTRI : 1)*9 : 1];
         if ( CF_REG )
         {
@@ -452,16 +464,18 @@ __global__ void __launch_bounds__(BLOCK, (MinBlocks<NALS,BLOCK>::value)) mcall_s
             {
                 const bool do_pairs = pass==0, do_tri = S::SPLIT ? pass==1 : true;
                 #pragma unroll 1
-                for (int s=tid; s<n; s+=BLOCK)
+                for (int sb=0; sb<n; sb+=BLOCK)         /* uniform trip count: the loader votes across the warp */
                 {
-                    int pl[G]; double p[G]; double sum; int orv;
-                    if ( !load_sample<NALS>(tile_s + (uint32_t)(s*G*4), pl2p_s, unseen, a.tab, pl, p, sum, orv, tflags) ) continue;
+                    const int s = min(sb + tid, n-1);
+                    const bool valid = sb + tid < n;
+                    int pl[G]; double p[G]; double sum; bool fast;
+                    if ( !load_sample_w<NALS>(tile_s + (uint32_t)(s*G*4), pl2p_s, valid, unseen, a.tab, pl, p, sum, fast, tflags) ) continue;
                     int pld = 2;
                     if ( PLOIDY ) pld = __ldg(ploidy + s0 + s);
                     if ( pass==0 )
                     {
                         /* single-allele sets: log(pdg[aa]) = -PL*ln10/10 - log(sum), every sample incl. ploidy 0 (mcall.c:607-611) */
-                        if ( orv & ~255 )
+                        if ( !fast )
                         {
                             #pragma unroll
                             for (int k=0; k<NALS; k++) plsum[k] += pl[hom_idx(k)];
@@ -832,11 +846,13 @@ __global__ void __launch_bounds__(BLOCK, (MinBlocks<NALS,BLOCK>::value)) mcall_s
                 if ( acc_n + (TS + BLOCK - 1)/BLOCK > 63 ) flush_ac();     /* uniform across the block: safe to shuffle */
                 acc_n += (TS + BLOCK - 1)/BLOCK;
                 #pragma unroll 1
-                for (int s=tid; s<n; s+=BLOCK)
+                for (int sb=0; sb<n; sb+=BLOCK)         /* uniform trip count: the loader votes across the warp */
                 {
-                    int pl[G]; double p[G]; double sum = 1; int orv;
+                    const int s = min(sb + tid, n-1);
+                    const bool valid = sb + tid < n;
+                    int pl[G]; double p[G]; double sum = 1; bool fast;
                     const uint32_t row_s = tile_s + (uint32_t)(s*G*4);
-                    const bool has = load_sample<NALS>(row_s, pl2p_s, unseen, a.tab, pl, p, sum, orv, tflags2);
+                    const bool has = load_sample_w<NALS>(row_s, pl2p_s, valid, unseen, a.tab, pl, p, sum, fast, tflags2);
                     const int pld = PLOIDY ? __ldg(ploidy + s0 + s) : 2;
                     int4 outc = make_int4(MCB_GT_MISSING, pld==2 ? MCB_GT_MISSING : I32_VEC_END, 0, 0);
                     int gq = 0;
@@ -851,8 +867,7 @@ __global__ void __launch_bounds__(BLOCK, (MinBlocks<NALS,BLOCK>::value)) mcall_s
                     else                        /* mcall.c:787-840, literal arithmetic */
                     {
                         called = true;
-                        const bool fast = !(orv & ~255);
-                        const double r = fast ? rcp_shared(sum) : 0.0;
+                        const double r = fast ? rcp_shared(sum) : 0.0;     /* `fast` is warp-uniform */
                         auto pdg_of = [&](int k) -> double
                         {
                             double pk;
@@ -954,6 +969,7 @@ __global__ void __launch_bounds__(BLOCK, (MinBlocks<NALS,BLOCK>::value)) mcall_s
                             }
                         }
                     }
+                    if ( !valid ) continue;
                     acc += (unsigned long long)(uint32_t)outc.z | ((unsigned long long)(uint32_t)outc.w << 32);
                     const int sg = s0 + s;
                     if ( out_gt ) out_gt[sg] = make_int2(outc.x, outc.y);
