@@ -37,7 +37,8 @@ struct mcb_ctx
     DevTables *d_tab = nullptr;
     uint8_t  *d_ploidy = nullptr;  int nploidy = 0, ploidy_cap = 0;  bool any_nondiploid = false;
     std::vector<uint8_t> h_ploidy;
-    uint32_t *d_grp_off = nullptr, *d_grp_smpl = nullptr;
+    uint32_t *d_grp_off = nullptr, *d_grp_smpl = nullptr, *d_smpl2grp = nullptr;  int ngroups = 1;
+    void *d_grp_scratch = nullptr;  size_t grp_scratch_bytes = 0;
     /* device-path scratch */
     int32_t *d_lists = nullptr, *d_counts = nullptr;  int list_cap = 0;
     HostSlab slab[2];
@@ -167,7 +168,7 @@ static int upload_ploidy(mcb_ctx *ctx)
 extern "C" int mcb_init(mcb_ctx **out, const mcb_params *params)
 {
     if ( !out || !params || params->nsmpl<=0 || params->max_nals<1 || params->max_nals>MCB_MAX_NALS ) return MCB_EINVAL;
-    if ( params->ngroups > 1 ) return MCB_EINVAL;                       /* -G groups: not in this build yet */
+    if ( params->ngroups > 1 && (!params->grp_off || !params->grp_smpl) ) return MCB_EINVAL;
     int ndev = 0;
     if ( cudaGetDeviceCount(&ndev)!=cudaSuccess || ndev<=0 ) return MCB_ENODEV;
     if ( params->device<0 || params->device>=ndev ) return MCB_EINVAL;
@@ -196,6 +197,26 @@ extern "C" int mcb_init(mcb_ctx **out, const mcb_params *params)
     int rc = upload_ploidy(ctx);
     if ( rc ) return rc;
     CK(cudaMalloc(&ctx->d_counts, sizeof(int32_t)*NCLASS));
+    if ( params->ngroups > 1 )         /* smpl_grp_t.smpl lists (mcall.c:250-349): every sample in exactly one group */
+    {
+        const int Q = params->ngroups, S = params->nsmpl;
+        if ( params->grp_off[0]!=0 || params->grp_off[Q]!=(uint32_t)S ) return MCB_EINVAL;
+        std::vector<uint32_t> s2g(S, 0xffffffffu);
+        for (int g=0; g<Q; g++)
+            for (uint32_t i=params->grp_off[g]; i<params->grp_off[g+1]; i++)
+            {
+                uint32_t smp = params->grp_smpl[i];
+                if ( smp>=(uint32_t)S || s2g[smp]!=0xffffffffu ) return MCB_EINVAL;
+                s2g[smp] = g;
+            }
+        ctx->ngroups = Q;
+        CK(cudaMalloc(&ctx->d_grp_off, sizeof(uint32_t)*(Q+1)));
+        CK(cudaMalloc(&ctx->d_grp_smpl, sizeof(uint32_t)*S));
+        CK(cudaMalloc(&ctx->d_smpl2grp, sizeof(uint32_t)*S));
+        CK(cudaMemcpy(ctx->d_grp_off, params->grp_off, sizeof(uint32_t)*(Q+1), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(ctx->d_grp_smpl, params->grp_smpl, sizeof(uint32_t)*S, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(ctx->d_smpl2grp, s2g.data(), sizeof(uint32_t)*S, cudaMemcpyHostToDevice));
+    }
     for (int i=0; i<2; i++)
     {
         CK(cudaStreamCreateWithFlags(&ctx->slab[i].stream, cudaStreamNonBlocking));
@@ -209,7 +230,7 @@ extern "C" void mcb_destroy(mcb_ctx *ctx)
 {
     if ( !ctx ) return;
     cudaSetDevice(ctx->device);
-    cudaFree(ctx->d_tab); cudaFree(ctx->d_ploidy); cudaFree(ctx->d_grp_off); cudaFree(ctx->d_grp_smpl);
+    cudaFree(ctx->d_tab); cudaFree(ctx->d_ploidy); cudaFree(ctx->d_grp_off); cudaFree(ctx->d_grp_smpl); cudaFree(ctx->d_smpl2grp); cudaFree(ctx->d_grp_scratch);
     cudaFree(ctx->d_lists); cudaFree(ctx->d_counts);
     for (int i=0; i<2; i++)
     {
@@ -314,6 +335,33 @@ static int enqueue(mcb_ctx *ctx, const mcb_batch *b, const mcb_result *r, int32_
     a.nsmpl = ctx->p.nsmpl; a.max_nals = ctx->p.max_nals; a.flag = ctx->p.flag; a.output_tags = ctx->p.output_tags;
     a.theta = ctx->theta_log; a.tie_eps = ctx->p.tie_eps; a.use_prior = ctx->p.use_prior;
     const bool ploidy = ctx->any_nondiploid;
+    if ( ctx->ngroups > 1 )         /* grouped calling (-G): the correctness-first kernel of mcall_groups.cu */
+    {
+        if ( !b->ad || !b->ad_off || !b->nad ) return MCB_EQS;      /* mcall.c:1476 */
+        a.grp_off = ctx->d_grp_off; a.grp_smpl = ctx->d_grp_smpl; a.smpl2grp = ctx->d_smpl2grp; a.ngroups = ctx->ngroups;
+        int grid = std::min(b->nsites, ctx->nsm*8);
+        const size_t per_cta = groups_scratch_bytes(1, ctx->ngroups);
+        grid = (int)std::max<int64_t>(1, std::min<int64_t>(grid, (int64_t)(512ll<<20)/(int64_t)per_cta));
+        const size_t need = groups_scratch_bytes(grid, ctx->ngroups);
+        if ( need > ctx->grp_scratch_bytes )
+        {
+            CK(cudaStreamSynchronize(st));
+            if ( ctx->d_grp_scratch ) CK(cudaFree(ctx->d_grp_scratch));
+            CK(cudaMalloc(&ctx->d_grp_scratch, need));
+            ctx->grp_scratch_bytes = need;
+        }
+        for (int nals=1; nals<=5; nals++)
+        {
+            a.site_list = lists + (size_t)nals*list_stride; a.site_count = counts + nals;
+            CK(launch_groups_kernel(nals, a, ctx->d_grp_scratch, grid, st));
+            launches++;
+        }
+        CK(launch_unsupported(lists, counts, r->ret, r->site_flags, b->nals, st));
+        ctx->stats[0] += launches + 1;
+        ctx->stats[1] += b->nsites;
+        ctx->kev_valid = false;
+        return MCB_OK;
+    }
     const bool timing = ctx->opt_time_kernels && lists==ctx->d_lists;
     /*  timing mode serialises the classes on the caller's stream (per-class events); otherwise every class runs on
      *  its own stream so that the small persistent grids of the 3-5 allele classes overlap the biallelic one  */
@@ -398,6 +446,13 @@ extern "C" int mcb_call_host(mcb_ctx *ctx, const mcb_batch *b, const mcb_result 
         ext[i] = (( (int64_t)S*n*(n+1)/2 ) + 3) & ~(int64_t)3;
         if ( (b->pl_off[i] & 3) || (i && b->pl_off[i] < b->pl_off[i-1] + ext[i-1]) ) return MCB_EINVAL;
     }
+    const bool have_ad = ctx->ngroups>1 && b->ad && b->ad_off && b->nad;
+    std::vector<int64_t> aext(have_ad ? R : 0);
+    for (int i=0; have_ad && i<R; i++)
+    {
+        aext[i] = (((int64_t)S*b->nad[i]) + 3) & ~(int64_t)3;
+        if ( i && b->ad_off[i] < b->ad_off[i-1] + aext[i-1] ) return MCB_EINVAL;
+    }
     const bool want_pl = r->pl != nullptr, want_gt = r->gt != nullptr;
     const bool want_gq = r->gq && (ctx->p.output_tags & (MCB_CALL_FMT_GQ|MCB_CALL_FMT_GP));
     const bool want_gp = r->gp && (ctx->p.output_tags & MCB_CALL_FMT_GP);
@@ -423,6 +478,8 @@ extern "C" int mcb_call_host(mcb_ctx *ctx, const mcb_batch *b, const mcb_result 
         size_t o_ret = carve(4*(size_t)n), o_als = carve(4*(size_t)n), o_map = carve((size_t)n*M), o_qual = carve(4*(size_t)n);
         size_t o_ac = carve(4*(size_t)n*M), o_an = carve(4*(size_t)n), o_fl = carve(4*(size_t)n), o_diag = carve(32*(size_t)n);
         size_t o_gt = want_gt ? carve(8*(size_t)n*S) : 0, o_gq = want_gq ? carve(4*(size_t)n*S) : 0;
+        const int64_t ad0 = have_ad ? b->ad_off[beg] : 0, ad_ints = have_ad ? b->ad_off[end-1] + aext[end-1] - ad0 : 0;
+        size_t o_ad = have_ad ? carve((size_t)ad_ints*4) : 0, o_adoff = have_ad ? carve(sizeof(int64_t)*n) : 0, o_nad = have_ad ? carve(n) : 0;
         if ( off > sl.dev_bytes )
         {
             if ( sl.dev ) CK(cudaFree(sl.dev));
@@ -448,6 +505,12 @@ extern "C" int mcb_call_host(mcb_ctx *ctx, const mcb_batch *b, const mcb_result 
         if ( b->nqs ) H2D(o_nqs, b->nqs + beg, n);
         if ( b->prior_an ) H2D(o_pan, b->prior_an + beg, sizeof(int32_t)*n);
         if ( b->prior_ac ) H2D(o_pac, b->prior_ac + (size_t)beg*M, sizeof(int32_t)*(size_t)n*M);
+        if ( have_ad )
+        {
+            H2D(o_ad, b->ad + ad0, (size_t)ad_ints*4);
+            H2D(o_adoff, b->ad_off + beg, sizeof(int64_t)*n);
+            H2D(o_nad, b->nad + beg, n);
+        }
 #undef H2D
         /* device views: pl pointers are biased by -pl0 so that the absolute pl_off[] stay valid */
         mcb_batch db; memset(&db, 0, sizeof db);
@@ -460,6 +523,10 @@ extern "C" int mcb_call_host(mcb_ctx *ctx, const mcb_batch *b, const mcb_result 
         db.nqs = b->nqs ? (const uint8_t*)(base+o_nqs) : nullptr;
         db.prior_an = b->prior_an ? (const int32_t*)(base+o_pan) : nullptr;
         db.prior_ac = b->prior_ac ? (const int32_t*)(base+o_pac) : nullptr;
+        if ( have_ad )
+        {
+            db.ad = (const int32_t*)(base+o_ad) - ad0; db.ad_off = (const int64_t*)(base+o_adoff); db.nad = (const uint8_t*)(base+o_nad);
+        }
         mcb_result dr; memset(&dr, 0, sizeof dr);
         dr.ret = (int32_t*)(base+o_ret); dr.als_new = (uint32_t*)(base+o_als); dr.als_map = (int8_t*)(base+o_map);
         dr.qual = (float*)(base+o_qual); dr.ac = (int32_t*)(base+o_ac); dr.an = (int32_t*)(base+o_an);

@@ -1,0 +1,565 @@
+/*  mcall_groups.cu -- site kernel for grouped calling (`call -m -G`, call->nsmpl_grp > 1; mcall.c:250-349, 1466-1504,
+ *  1546-1561, 1608-1614).  Correctness-first: one CTA per site, 1..5 alleles.
+ *
+ *    phase A  one WARP per sample group, lane k <-> allele set k (<= 25 sets): the group's quality sums from
+ *             FORMAT/AD in float32, sequential in group order exactly like mcall.c:1478-1503 (lane a <-> allele a);
+ *             then the group's samples are walked sequentially, every lane accumulating its own set as an
+ *             exponent-tracked product (same numerics as the pooled kernel); the set epilogue is the pooled one.
+ *    phase B  thread 0 combines the groups: als_new = OR of the groups' sets | REF, the QUAL candidate of the group
+ *             with the largest QUAL (mcall.c:1546-1575), trimming maps (mcall.c:547-570).
+ *    phase C  one THREAD per sample: literal mcall_call_genotypes() with the sample's own group record
+ *             (mcall.c:745-886), GQ/GP, PL trimming, AC.
+ *
+ *  PLs are read from global memory directly (L2 serves the second read); the per-group records live in a global
+ *  scratch area owned by the CTA.
+ */
+#include "mcall_device.cuh"
+
+namespace mcb {
+
+#define GBLOCK 128
+#define GNW    (GBLOCK/32)
+
+struct GroupRec
+{
+    double q[5];            /* (double)(float)qsum, normalised (mcall.c:1530-1535) */
+    double qual, ref_lk, lk_sum;
+    uint32_t als;           /* grp->als */
+    int nals, has_max, pad;
+};
+
+struct GSite                /* site decision record, shared memory */
+{
+    double max_qual, lk_sum, ref_lk;
+    uint32_t als_new, flags;
+    int nals_new, is_variant, ret_early, pl_dropped, ref_gt;
+    int als_map[5], pl_map[15], ac[8];
+};
+
+/*  set_pdg's missing-value fill (mcall.c:495-527) on a thread-local PL row  */
+__device__ __noinline__ int fix_missing_local(int *pl, int nals, int unseen)
+{
+    const int G = nals*(nals+1)/2;
+    int j;
+    for (j=0; j<G; j++)
+    {
+        if ( pl[j]==I32_VEC_END ) return 0;
+        if ( pl[j]==I32_MISSING ) break;
+    }
+    if ( j==0 || j==G ) return 0;
+    j = 0;
+    for (int ia=0; ia<nals; ia++)
+        for (int ib=0; ib<=ia; ib++)
+        {
+            if ( pl[j]==I32_MISSING )
+            {
+                int k = gt_idx(ia,unseen);
+                if ( pl[k]==I32_MISSING ) k = gt_idx(ib,unseen);
+                if ( pl[k]==I32_MISSING ) k = gt_idx(unseen,unseen);
+                pl[j] = pl[k]==I32_MISSING ? 255 : pl[k];
+            }
+            else if ( pl[j] < 0 ) return 0;
+            j++;
+        }
+    return 1;
+}
+
+__device__ __forceinline__ double pl_to_p_dev(const double *s_pl2p, const DevTables *tab, int v, uint32_t *flags)
+{
+    if ( (unsigned)v < 256u ) return s_pl2p[v];
+    if ( v > 2500 ) *flags |= MCB_SITE_PL_RANGE;
+    return (unsigned)v < (unsigned)MCB_PL2P_BIG ? tab->pl2p_big[v] : 0.0;
+}
+
+template<int NALS>
+__global__ void __launch_bounds__(GBLOCK) mcall_groups_kernel(const KArgs a, GroupRec *scratch)
+{
+    using S = Shape<NALS>;
+    constexpr int G = S::G, NPAIR = S::NPAIR, NSUB = S::NSUB;
+    constexpr double LN2 = 0.693147180559945309417232121458;
+
+    __shared__ double s_pl2p[256];
+    __shared__ double s_thr[130];
+    __shared__ double s_p[GNW][16];
+    __shared__ int    s_pl[GNW][16];
+    __shared__ GSite  st;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nsmpl = a.nsmpl, ngrp = a.ngroups;
+    GroupRec *grec = scratch + (size_t)blockIdx.x*ngrp;
+
+    for (int i=tid; i<256; i+=GBLOCK) s_pl2p[i] = a.tab->pl2p[i];
+    for (int i=tid; i<130; i+=GBLOCK) s_thr[i] = i<128 ? a.tab->gq_thr[i] : -1.0;
+    __syncthreads();
+
+    const int nsites = *a.site_count;
+    for (int isite = blockIdx.x; isite < nsites; isite += gridDim.x)
+    {
+        const int site = a.site_list[isite];
+        const int64_t site_off = a.pl_off[site];
+        const int32_t *site_pl = a.pl + site_off;
+        const int unseen = a.unseen ? a.unseen[site] : 0;
+        int pid = a.ploidy_id ? a.ploidy_id[site] : 0;
+        if ( pid >= a.nploidy ) pid = 0;
+        const uint8_t *ploidy = a.ploidy_tab + (size_t)pid*nsmpl;
+        const int nad = a.nad ? a.nad[site] : 0;
+        const int32_t *site_ad = a.ad ? a.ad + a.ad_off[site] : nullptr;
+        if ( tid==0 ) { st.flags = (site_ad && nad>0) ? 0 : MCB_SITE_NO_QS; for (int j=0; j<8; j++) st.ac[j] = 0; }
+        __syncthreads();
+
+        /* =========================== phase A: one warp per group =============================== */
+        for (int g=warp; g<ngrp; g+=GNW)
+        {
+            const int beg = a.grp_off[g], end = a.grp_off[g+1];
+            /* ---- quality sums from FORMAT/AD: float32, sequential over the group's samples (mcall.c:1484-1501) */
+            float qa = 0;
+            if ( lane<NALS && site_ad )
+                for (int i=beg; i<beg+(end-beg); i++)
+                {
+                    const int32_t *ptr = site_ad + (size_t)a.grp_smpl[i]*nad;
+                    float sum = 0; int e = nad;
+                    for (int j=0; j<nad; j++)
+                    {
+                        const int v = ptr[j];
+                        if ( v==I32_VEC_END ) { e = j; break; }
+                        if ( v!=I32_MISSING ) sum = __fadd_rn(sum, (float)v);
+                    }
+                    if ( sum!=0 && lane<e )
+                    {
+                        const int v = ptr[lane];
+                        if ( v!=I32_MISSING ) qa = __fadd_rn(qa, __fdiv_rn((float)v, sum));
+                    }
+                }
+            float qf[NALS];
+            #pragma unroll
+            for (int j=0; j<NALS; j++) qf[j] = __shfl_sync(0xffffffffu, qa, j);
+            /* ---- -F prior (mcall.c:1507-1527) with this group's sample count, then normalisation (1530-1535) */
+            if ( a.use_prior && a.prior_an && a.prior_ac )
+            {
+                const int an = a.prior_an[site];
+                if ( an!=I32_MISSING && an>0 )
+                {
+                    const int32_t *pac = a.prior_ac + (size_t)site*a.max_nals;
+                    const double den = __dadd_rn((double)(uint32_t)(end-beg), __dmul_rn(0.5,(double)an));
+                    int ac0 = an;
+                    for (int j=0; j<NALS-1; j++)
+                    {
+                        if ( pac[j]==I32_VEC_END ) break;
+                        if ( pac[j]==I32_MISSING ) continue;
+                        ac0 -= pac[j];
+                        qf[j+1] = (float)__ddiv_rn(__dadd_rn((double)qf[j+1], __dmul_rn(0.5,(double)pac[j])), den);
+                    }
+                    if ( ac0<0 && lane==0 ) atomicOr(&st.flags, MCB_SITE_BAD_PRIOR);
+                    qf[0] = (float)__ddiv_rn(__dadd_rn((double)qf[0], __dmul_rn(0.5,(double)ac0)), den);
+                }
+            }
+            {
+                float qs = 0;
+                #pragma unroll
+                for (int j=0; j<NALS; j++) qs = __fadd_rn(qs, qf[j]);
+                if ( qs!=0 )
+                {
+                    #pragma unroll
+                    for (int j=0; j<NALS; j++) qf[j] = __fdiv_rn(qf[j], qs);
+                }
+            }
+            /* ---- lane k: its allele set, in the reference's enumeration order (mcall.c:601-698) */
+            int sa = 0, sb = -1, sc = -1;       /* alleles of the set, sa > sb > sc */
+            bool live = false;
+            if ( lane < NALS ) { sa = lane; live = true; }
+            else if ( lane < NALS+NPAIR )
+            {
+                int k = lane-NALS; sa = 1; while ( sa*(sa+1)/2 <= k ) sa++;
+                sb = k - sa*(sa-1)/2;
+            }
+            else if ( lane < NSUB )
+            {
+                int k = lane-NALS-NPAIR; sa = 2; while ( (sa+1)*sa*(sa-1)/6 <= k ) sa++;
+                int r = k - sa*(sa-1)*(sa-2)/6; sb = 1; while ( sb*(sb+1)/2 <= r ) sb++;
+                sc = r - sb*(sb-1)/2;
+            }
+            auto QF = [&](int j) -> float { float v = 0; for (int t=0; t<NALS; t++) if ( t==j ) v = qf[t]; return v; };
+            /* terms: up to 3 homozygous (diploid coefficient cd, haploid ch) then up to 3 heterozygous (cd only) */
+            int tix[6] = {0,0,0,0,0,0}; double cd[6] = {0,0,0,0,0,0}, ch[3] = {0,0,0};
+            uint32_t mask = 0; int nonref = 0;
+            if ( lane < NALS ) { tix[0] = hom_idx(sa); cd[0] = 1; ch[0] = 1; mask = 1u<<sa; nonref = sa!=0; }
+            else if ( lane < NALS+NPAIR )
+            {
+                const float fqa = QF(sa), fqb = QF(sb);
+                mask = 1u<<sa | 1u<<sb; nonref = (sa!=0) + (sb!=0);
+                if ( fqa!=0 && fqb!=0 )
+                {
+                    live = true;
+                    const float den = __fadd_rn(fqa,fqb);
+                    const double fa = (double)__fdiv_rn(fqa,den), fb = (double)__fdiv_rn(fqb,den);
+                    tix[0] = hom_idx(sa); tix[1] = hom_idx(sb); tix[3] = gt_idx(sa,sb);
+                    cd[0] = __dmul_rn(fa,fa); cd[1] = __dmul_rn(fb,fb); cd[3] = __dmul_rn(__dmul_rn(2.0,fa),fb);
+                    ch[0] = fa; ch[1] = fb;
+                }
+            }
+            else if ( lane < NSUB )
+            {
+                const float fqa = QF(sa), fqb = QF(sb), fqc = QF(sc);
+                mask = 1u<<sa | 1u<<sb | 1u<<sc; nonref = (sa!=0) + (sb!=0) + (sc!=0);
+                if ( fqa!=0 && fqb!=0 && fqc!=0 )
+                {
+                    live = true;
+                    const float den = __fadd_rn(__fadd_rn(fqa,fqb),fqc);
+                    const double fa = (double)__fdiv_rn(fqa,den), fb = (double)__fdiv_rn(fqb,den), fc = (double)__fdiv_rn(fqc,den);
+                    tix[0] = hom_idx(sa); tix[1] = hom_idx(sb); tix[2] = hom_idx(sc);
+                    tix[3] = gt_idx(sa,sb); tix[4] = gt_idx(sa,sc); tix[5] = gt_idx(sb,sc);
+                    cd[0] = __dmul_rn(fa,fa); cd[1] = __dmul_rn(fb,fb); cd[2] = __dmul_rn(fc,fc);
+                    cd[3] = __dmul_rn(__dmul_rn(2.0,fa),fb); cd[4] = __dmul_rn(__dmul_rn(2.0,fa),fc); cd[5] = __dmul_rn(__dmul_rn(2.0,fb),fc);
+                    ch[0] = fa; ch[1] = fb; ch[2] = fc;
+                }
+            }
+            const bool single = lane < NALS;
+
+            /* ---- walk the group's samples; lane k accumulates prod val_s and prod sum_s of ITS set */
+            double M = 1, MN = 1; int E = 0, EN = 0, cnt = 0, since = 0;
+            uint32_t wflags = 0;
+            for (int i=beg; i<end; i++)
+            {
+                const int s = a.grp_smpl[i];
+                int v = lane<G ? site_pl[(size_t)s*G + lane] : 0;
+                bool data = true;
+                if ( __any_sync(0xffffffffu, v<0) )
+                {
+                    if ( lane<G ) s_pl[warp][lane] = v;
+                    __syncwarp();
+                    int ok = 0;
+                    if ( lane==0 ) ok = fix_missing_local(s_pl[warp], NALS, unseen);
+                    ok = __shfl_sync(0xffffffffu, ok, 0);
+                    __syncwarp();
+                    if ( lane<G ) v = s_pl[warp][lane];
+                    data = ok && !__any_sync(0xffffffffu, v<0);
+                    __syncwarp();
+                }
+                if ( !__any_sync(0xffffffffu, v!=0) ) data = false;      /* PL=0,..,0: no data (mcall.c:529-537) */
+                if ( !data ) continue;
+                if ( lane<G ) s_p[warp][lane] = pl_to_p_dev(s_pl2p, a.tab, v, &wflags);
+                __syncwarp();
+                double sum = s_p[warp][0];
+                #pragma unroll
+                for (int j=1; j<G; j++) sum = __dadd_rn(sum, s_p[warp][j]);
+                const int pld = ploidy[s];
+                if ( live && lane<NSUB )
+                {
+                    double val = 0; bool use = false;
+                    if ( single ) { val = s_p[warp][tix[0]]; use = true; }     /* every sample, also ploidy 0 (mcall.c:607-611) */
+                    else if ( pld==2 )
+                    {
+                        val = cd[0]*s_p[warp][tix[0]];
+                        val = fma(cd[1], s_p[warp][tix[1]], val);
+                        if ( sc>=0 ) val = fma(cd[2], s_p[warp][tix[2]], val);
+                        val = fma(cd[3], s_p[warp][tix[3]], val);
+                        if ( sc>=0 ) { val = fma(cd[4], s_p[warp][tix[4]], val); val = fma(cd[5], s_p[warp][tix[5]], val); }
+                        use = true;
+                    }
+                    else if ( pld==1 )
+                    {
+                        val = ch[0]*s_p[warp][tix[0]];
+                        val = fma(ch[1], s_p[warp][tix[1]], val);
+                        if ( sc>=0 ) val = fma(ch[2], s_p[warp][tix[2]], val);
+                        use = true;
+                    }
+                    if ( use && val!=0 ) { acc_mul(M, E, val); acc_mul(MN, EN, sum); cnt++; }
+                }
+                if ( ++since >= 256 ) { acc_renorm(M, E); acc_renorm(MN, EN); since = 0; }
+                __syncwarp();
+            }
+            /* ---- set totals and the group's best set (same epilogue as the pooled kernel) */
+            double lk = 0;
+            const bool cand = live && lane<NSUB && cnt>0;
+            if ( cand ) lk = (log(M) + (double)(E - 1023*cnt)*LN2) - (log(MN) + (double)(EN - 1023*cnt)*LN2);
+            if ( lane<NSUB ) for (int j=0; j<nonref; j++) lk += a.theta;
+            const bool in_sum = cand && !(single && sa==0);
+            double best = cand ? lk : -CUDART_INF; int best_lane = cand ? lane : 64;
+            #pragma unroll
+            for (int off=16; off; off>>=1)
+            {
+                double ob = __shfl_xor_sync(0xffffffffu, best, off);
+                int    ol = __shfl_xor_sync(0xffffffffu, best_lane, off);
+                if ( ob > best || (ob==best && ol < best_lane) ) { best = ob; best_lane = ol; }
+            }
+            double second = (cand && lane!=best_lane) ? lk : -CUDART_INF;
+            #pragma unroll
+            for (int off=16; off; off>>=1) second = fmax(second, __shfl_xor_sync(0xffffffffu, second, off));
+            double mx = in_sum ? lk : -CUDART_INF;
+            #pragma unroll
+            for (int off=16; off; off>>=1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+            double term = in_sum ? exp(lk - mx) : 0.0;
+            #pragma unroll
+            for (int off=16; off; off>>=1) term += __shfl_xor_sync(0xffffffffu, term, off);
+            #pragma unroll
+            for (int off=16; off; off>>=1) wflags |= __shfl_xor_sync(0xffffffffu, wflags, off);
+            const double g_lk_sum = mx > -CUDART_INF ? mx + log(term) : -CUDART_INF;
+            const double g_ref_lk = __shfl_sync(0xffffffffu, lk, 0);
+            const uint32_t g_als = __shfl_sync(0xffffffffu, mask, best_lane & 31);
+            if ( lane==0 )
+            {
+                const bool any = best_lane < 64;
+                GroupRec &r = grec[g];
+                #pragma unroll
+                for (int j=0; j<NALS; j++) r.q[j] = (double)qf[j];
+                r.als = any ? g_als : 0;
+                int n = 0;
+                for (int j=0; j<NALS; j++) n += (r.als>>j)&1u;
+                r.nals = n; r.has_max = any;
+                r.ref_lk = g_ref_lk; r.lk_sum = g_lk_sum;
+                r.qual = any ? -4.343*(g_ref_lk - logsumexp2_dev(g_lk_sum, g_ref_lk)) : -CUDART_INF;
+                uint32_t f = wflags;
+                if ( any && best - second < a.tie_eps ) f |= MCB_SITE_NEAR_TIE;
+                if ( f ) atomicOr(&st.flags, f);
+            }
+        }
+        __threadfence_block();
+        __syncthreads();
+
+        /* =========================== phase B: combine the groups (mcall.c:1546-1577) ============= */
+        if ( tid==0 )
+        {
+            uint32_t als_new = 0, flags = st.flags;
+            double ref_lk = -CUDART_INF, lk_sum = -CUDART_INF, max_qual = -CUDART_INF;
+            for (int g=0; g<ngrp; g++)
+            {
+                const GroupRec &r = grec[g];
+                als_new |= r.als;
+                if ( !r.has_max ) continue;
+                if ( max_qual < r.qual ) { max_qual = r.qual; lk_sum = r.lk_sum; ref_lk = r.ref_lk; }
+            }
+            als_new |= 1u;
+            const int is_variant = als_new!=1;
+            st.ret_early = ((a.flag & MCB_CALL_VARONLY) && !is_variant) || (flags & MCB_SITE_NO_QS);
+            int nals_new = 0;
+            for (int j=0; j<NALS; j++)
+            {
+                if ( j>0 && j==unseen ) continue;
+                if ( a.flag & MCB_CALL_KEEPALT ) als_new |= 1u<<j;
+                if ( als_new & (1u<<j) ) nals_new++;
+            }
+            int nout = 0, kk = 0, l = 0;
+            for (int x=0; x<NALS; x++) st.als_map[x] = (als_new & (1u<<x)) ? nout++ : -1;
+            for (int x=0; x<NALS; x++)
+                for (int y=0; y<=x; y++) { if ( (als_new & (1u<<x)) && (als_new & (1u<<y)) ) { if ( kk<15 ) st.pl_map[kk] = l; kk++; } l++; }
+            for (; kk<15; kk++) st.pl_map[kk] = 0;
+            if ( unseen && (als_new & (1u<<unseen)) ) flags |= MCB_SITE_UNSEEN_SEL;
+            st.pl_dropped = als_new==1;
+            st.ref_gt = (als_new==1) || !is_variant;
+            if ( st.pl_dropped ) flags |= MCB_SITE_PL_DROPPED;
+            if ( st.ref_gt ) flags |= MCB_SITE_REF_GT;
+            st.als_new = als_new; st.nals_new = nals_new; st.is_variant = is_variant; st.flags = flags;
+            st.max_qual = max_qual; st.lk_sum = lk_sum; st.ref_lk = ref_lk;
+        }
+        __syncthreads();
+        if ( st.ret_early )
+        {
+            if ( tid==0 ) { a.ret[site] = 0; if ( a.site_flags ) a.site_flags[site] = st.flags; }
+            __syncthreads();
+            continue;
+        }
+
+        /* =========================== phase C: per-sample genotypes (mcall.c:745-886) ============== */
+        {
+            const int nals_new = st.nals_new, ngt_new = nals_new*(nals_new+1)/2;
+            const bool ref_gt = st.ref_gt;
+            const bool want_gq = a.gq && (a.output_tags & (MCB_CALL_FMT_GQ|MCB_CALL_FMT_GP));
+            const bool want_gp = a.gp && (a.output_tags & MCB_CALL_FMT_GP) && !ref_gt;
+            int32_t *out_pl = (a.out_pl && !st.pl_dropped) ? a.out_pl + site_off : nullptr;
+            float   *out_gp = want_gp ? a.gp + site_off : nullptr;
+            int2 *out_gt = a.gt ? reinterpret_cast<int2*>(a.gt) + (size_t)site*nsmpl : nullptr;
+            int32_t *out_gq = want_gq ? a.gq + (size_t)site*nsmpl : nullptr;
+            uint32_t tflags = 0;
+            for (int s=tid; s<nsmpl; s+=GBLOCK)
+            {
+                const GroupRec &r = grec[a.smpl2grp[s]];
+                int pl[G]; double p[G];
+                int orv = 0;
+                #pragma unroll
+                for (int j=0; j<G; j++) { pl[j] = site_pl[(size_t)s*G + j]; orv |= pl[j]; }
+                bool has = true;
+                if ( orv<0 )
+                {
+                    int tmp[16];
+                    #pragma unroll
+                    for (int j=0; j<G; j++) tmp[j] = pl[j];
+                    has = fix_missing_local(tmp, NALS, unseen);
+                    orv = 0;
+                    #pragma unroll
+                    for (int j=0; j<G; j++) { if ( has ) pl[j] = tmp[j]; orv |= pl[j]; }
+                    if ( orv<0 ) has = false;
+                }
+                if ( orv==0 ) has = false;
+                double sum = 1;
+                if ( has )
+                {
+                    #pragma unroll
+                    for (int j=0; j<G; j++) p[j] = pl_to_p_dev(s_pl2p, a.tab, pl[j], &tflags);
+                    sum = p[0];
+                    #pragma unroll
+                    for (int j=1; j<G; j++) sum = __dadd_rn(sum, p[j]);
+                }
+                const int pld = ploidy[s];
+                int gt0, gt1, gq = 0;
+                bool called = false;
+                float gps[G];               /* FORMAT/GP scratch in the NEW genotype order, zeroed like mcall.c:1605 */
+                #pragma unroll
+                for (int j=0; j<G; j++) gps[j] = 0.f;
+                double gsum = 0;
+                if ( !pld ) { gt0 = MCB_GT_MISSING; gt1 = I32_VEC_END; }
+                else if ( !has ) { gt0 = MCB_GT_MISSING; gt1 = pld==2 ? MCB_GT_MISSING : I32_VEC_END; }
+                else if ( ref_gt )
+                {
+                    gt0 = MCB_GT_UNPHASED(0); gt1 = pld==2 ? MCB_GT_UNPHASED(0) : I32_VEC_END;
+                    atomicAdd(&st.ac[0], pld);
+                }
+                else
+                {
+                    called = true;
+                    double best = 0; int g0 = 0, g1 = 0;
+                    #pragma unroll
+                    for (int x=0; x<NALS; x++)          /* homozygous / haploid (mcall.c:793-808) */
+                    {
+                        if ( !(r.als & (1u<<x)) ) continue;
+                        const double pdg = __ddiv_rn(p[hom_idx(x)], sum);
+                        const double lk = pld==2 ? __dmul_rn(__dmul_rn(pdg, r.q[x]), r.q[x]) : __dmul_rn(pdg, r.q[x]);
+                        const int nx = st.als_map[x];
+                        const int igt = pld==2 ? hom_idx(nx) : nx;
+                        #pragma unroll
+                        for (int j=0; j<G; j++) if ( j==igt ) gps[j] = __double2float_rn(lk);
+                        if ( best < lk ) { best = lk; g0 = nx; }
+                    }
+                    if ( pld==2 )
+                    {
+                        g1 = g0;
+                        #pragma unroll
+                        for (int x=1; x<NALS; x++)      /* heterozygous (mcall.c:812-834) */
+                            #pragma unroll
+                            for (int y=0; y<x; y++)
+                            {
+                                if ( !(r.als & (1u<<x)) || !(r.als & (1u<<y)) ) continue;
+                                const double pdg = __ddiv_rn(p[gt_idx(x,y)], sum);
+                                const double lk = __dmul_rn(__dmul_rn(__dmul_rn(2.0,pdg), r.q[x]), r.q[y]);
+                                const int igt = gt_idx(st.als_map[x], st.als_map[y]);
+                                #pragma unroll
+                                for (int j=0; j<G; j++) if ( j==igt ) gps[j] = __double2float_rn(lk);
+                                if ( best < lk ) { best = lk; g0 = st.als_map[y]; g1 = st.als_map[x]; }
+                            }
+                        gt0 = MCB_GT_UNPHASED(g0); gt1 = MCB_GT_UNPHASED(g1);
+                        atomicAdd(&st.ac[min(g0,7)], 1); atomicAdd(&st.ac[min(g1,7)], 1);
+                    }
+                    else
+                    {
+                        gt0 = MCB_GT_UNPHASED(g0); gt1 = I32_VEC_END;
+                        atomicAdd(&st.ac[min(g0,7)], 1);
+                    }
+                    if ( want_gq || want_gp )           /* mcall.c:843-878 */
+                    {
+                        const int nmax = pld==2 ? ngt_new : r.nals;
+                        double gmax = 0;
+                        #pragma unroll
+                        for (int j=0; j<G; j++)
+                            if ( j<nmax )
+                            {
+                                const double gv = (double)gps[j];
+                                if ( gmax < gv ) gmax = gv;
+                                gsum = __dadd_rn(gsum, gv);
+                            }
+                        const double xx = __dadd_rn(1.0, -__ddiv_rn(gmax, gsum));
+                        if ( !(xx==xx) ) gq = 127;
+                        else
+                        {
+                            int k = __float2int_rz(-3.0102999f*lg2_approx((float)xx));
+                            k = max(0, min(127, k));
+                            if ( xx <= s_thr[k+1] ) { k++; while ( xx <= s_thr[k+1] ) k++; }
+                            else while ( xx > s_thr[k] ) k--;
+                            gq = k;
+                        }
+                    }
+                }
+                if ( out_gt ) out_gt[s] = make_int2(gt0, gt1);
+                if ( out_gq ) out_gq[s] = gq;
+                if ( out_pl )               /* mcall.c:1158-1194 on the filled PLs */
+                {
+                    int32_t *dst = out_pl + (size_t)s*ngt_new;
+                    #pragma unroll
+                    for (int k=0; k<G; k++)
+                    {
+                        if ( k>=ngt_new ) continue;
+                        int v;
+                        if ( pld==2 || (pld==1 && k<nals_new) )
+                        {
+                            const int src = pld==2 ? st.pl_map[k] : st.pl_map[hom_idx(k)];
+                            v = 0;
+                            #pragma unroll
+                            for (int j=0; j<G; j++) if ( j==src ) v = pl[j];
+                        }
+                        else v = (pld==0 && k==0) ? I32_MISSING : I32_VEC_END;
+                        dst[k] = v;
+                    }
+                }
+                if ( out_gp )               /* mcall.c:859-884 */
+                {
+                    float *dst = out_gp + (size_t)s*ngt_new;
+                    const int nmax = pld==2 ? ngt_new : (pld==1 ? r.nals : 0);
+                    if ( !called )
+                    {
+                        for (int k=0; k<ngt_new; k++) dst[k] = 0.f;
+                        if ( nmax==0 ) { dst[0] = __uint_as_float(MCB_FLOAT_MISSING_BITS); if ( 1<ngt_new ) dst[1] = __uint_as_float(MCB_FLOAT_VECTOR_END_BITS); }
+                        else if ( nmax<ngt_new ) dst[nmax] = __uint_as_float(MCB_FLOAT_VECTOR_END_BITS);
+                    }
+                    else
+                    {
+                        #pragma unroll
+                        for (int k=0; k<G; k++)
+                            if ( k<ngt_new ) dst[k] = k<nmax ? (float)__ddiv_rn((double)gps[k], gsum) : __uint_as_float(MCB_FLOAT_VECTOR_END_BITS);
+                    }
+                }
+            }
+            if ( tflags ) atomicOr(&st.flags, tflags);
+        }
+        __syncthreads();
+
+        /* ---- site record (mcall.c:1631-1650) */
+        if ( tid==0 )
+        {
+            int nAC = 0;
+            if ( !st.ref_gt ) for (int j=1; j<st.nals_new && j<8; j++) nAC += st.ac[j];
+            int ret = st.nals_new;
+            if ( !st.ref_gt && !nAC && (a.flag & MCB_CALL_VARONLY) ) ret = 0;
+            float qual;
+            if ( nAC ) qual = (float)st.max_qual;
+            else if ( st.lk_sum != -CUDART_INF ) qual = (float)(-4.343*(st.lk_sum - logsumexp2_dev(st.lk_sum, st.ref_lk)));
+            else if ( st.ac[0] ) qual = a.theta ? (float)(-4.343*a.theta) : 0.f;
+            else qual = __uint_as_float(MCB_FLOAT_MISSING_BITS);
+            a.ret[site] = ret;
+            if ( a.als_new ) a.als_new[site] = st.als_new;
+            if ( a.als_map ) for (int j=0; j<a.max_nals; j++) a.als_map[(size_t)site*a.max_nals + j] = j<NALS ? (int8_t)st.als_map[j] : (int8_t)-1;
+            if ( a.qual ) a.qual[site] = qual;
+            if ( a.ac ) for (int j=0; j<a.max_nals; j++) a.ac[(size_t)site*a.max_nals + j] = (j<st.nals_new && j<8) ? st.ac[j] : 0;
+            if ( a.an ) a.an[site] = nAC + st.ac[0];
+            if ( a.site_flags ) a.site_flags[site] = st.flags;
+            if ( a.diag ) { double *d = a.diag + (size_t)site*4; d[0] = st.max_qual; d[1] = st.lk_sum; d[2] = st.ref_lk; d[3] = 0; }
+        }
+        __syncthreads();
+    }
+}
+
+size_t groups_scratch_bytes(int grid, int ngroups) { return (size_t)grid*ngroups*sizeof(GroupRec); }
+
+cudaError_t launch_groups_kernel(int nals, const KArgs &a, void *scratch, int grid, cudaStream_t st)
+{
+    GroupRec *sc = (GroupRec*) scratch;
+    switch ( nals )
+    {
+        case 1: mcall_groups_kernel<1><<<grid, GBLOCK, 0, st>>>(a, sc); break;
+        case 2: mcall_groups_kernel<2><<<grid, GBLOCK, 0, st>>>(a, sc); break;
+        case 3: mcall_groups_kernel<3><<<grid, GBLOCK, 0, st>>>(a, sc); break;
+        case 4: mcall_groups_kernel<4><<<grid, GBLOCK, 0, st>>>(a, sc); break;
+        case 5: mcall_groups_kernel<5><<<grid, GBLOCK, 0, st>>>(a, sc); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+}   // namespace mcb

@@ -1,131 +1,10 @@
 /*  mcall_kernels.cu -- the fused site kernel (phase 1 site reduction + phase 2 per-sample genotype).
  *  See mcall_kernels.cuh for the design summary and the reference line map.
  */
-#include "mcall_kernels.cuh"
-#include <math_constants.h>
 
-/*  ALL shared memory of the site kernel is one dynamic array with C linkage: its 32-bit shared address is a
- *  link-time constant that inline PTX can name (`mov.u32 r, mcb_smem`), so hot-loop accesses become
- *  LDS [reg+imm] instead of generic-pointer arithmetic.  Layout: Shared<> state at 0, PL tile ring behind it.  */
-extern "C" { extern __shared__ __align__(128) unsigned char mcb_smem[]; }
+#include "mcall_device.cuh"
 
 namespace mcb {
-
-#define I32_MISSING   INT32_MIN
-#define I32_VEC_END   (INT32_MIN+1)
-#define MAX_STAGE     16
-
-__device__ __forceinline__ uint32_t smem_base() { uint32_t b; asm("mov.u32 %0, mcb_smem;" : "=r"(b)); return b; }
-__host__ __device__ constexpr size_t align128(size_t n) { return (n + 127) & ~(size_t)127; }
-
-/* ------------------------------------------------------------------------------------------------
- *  bulk-copy engine + mbarrier (PTX; SASS: UBLKCP / SYNCS)
- * ---------------------------------------------------------------------------------------------- */
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, int count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
-{
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-        "@P1 bra DONE;\n"
-        "bra LAB_WAIT;\n"
-        "DONE:\n"
-        "}\n" :: "r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void fence_mbar_init()   { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-
-/* ------------------------------------------------------------------------------------------------
- *  small helpers
- * ---------------------------------------------------------------------------------------------- */
-__host__ __device__ constexpr int hom_idx(int a) { return (a+1)*(a+2)/2 - 1; }           /* a/a, mcall.c:605 */
-__host__ __device__ constexpr int gt_idx(int a, int b) { return a>b ? a*(a+1)/2+b : b*(b+1)/2+a; }   /* bcf_alleles2gt */
-__host__ __device__ constexpr int pair_idx(int a, int b) { return a*(a-1)/2 + b; }       /* a>b, enumeration order of mcall.c:620-624 */
-__host__ __device__ constexpr int tri_idx(int a, int b, int c) { return a*(a-1)*(a-2)/6 + b*(b-1)/2 + c; }  /* a>b>c, mcall.c:656-665 */
-
-/*  running product with the exponent tracked separately: log(prod) = log(M) + (E - 1023*n)*ln2  */
-__device__ __forceinline__ void acc_mul(double &M, int &E, double v)
-{
-    int hi = __double2hiint(v), lo = __double2loint(v);
-    E += hi >> 20;
-    M = __dmul_rn(M, __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo));
-}
-__device__ __forceinline__ void acc_renorm(double &M, int &E)
-{
-    int hi = __double2hiint(M), lo = __double2loint(M);
-    E += (hi >> 20) - 1023;
-    M = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
-}
-__device__ __forceinline__ double logsumexp2_dev(double a, double b)       /* mcall.c:573-579 */
-{
-    if ( a>b ) return log(1 + exp(b-a)) + a;
-    return log(1 + exp(a-b)) + b;
-}
-
-/*  IEEE-754 double division with the reciprocal shared between several numerators.
- *  This is the fast path of the compiler's own `a/b` (MUFU.RCP64H seed, two Newton steps, one
- *  residual correction) with the divisor-only part hoisted; the quotient is the correctly rounded
- *  a/b for a >= 2^-969 and b in the normal range, which the caller guarantees (PL <= 255 =>
- *  a >= 10^-25.5, 10^-25.5 <= b <= 528).  tests/test_gpu_division.py checks bit-identity with `/`
- *  over the whole 256^3 biallelic table domain and random multi-allelic sums.                   */
-__device__ __forceinline__ double rcp_shared(double b)
-{
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
-    double e = fma(-b, r, 1.0);
-    e = fma(e, e, e);
-    r = fma(r, e, r);
-    e = fma(-b, r, 1.0);
-    return fma(r, e, r);
-}
-__device__ __forceinline__ double div_shared(double a, double b, double r)
-{
-    double q = __dmul_rn(a, r);
-    double rem = fma(-b, q, a);
-    return fma(r, rem, q);
-}
-
-/* ------------------------------------------------------------------------------------------------
- *  explicit shared-space accesses with 32-bit addresses.  Going through generic pointers makes the
- *  compiler rebuild the shared-window base (S2R SR_CgaCtaId ...) in front of every access (measured:
- *  ~60 of 445 instructions per sample in the first version of this kernel).
- * ---------------------------------------------------------------------------------------------- */
-__device__ __forceinline__ int lds32(uint32_t a) { int v; asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
-template<int OFF> __device__ __forceinline__ int lds32o(uint32_t a) { int v; asm volatile("ld.shared.s32 %0, [%1+%2];" : "=r"(v) : "r"(a), "n"(OFF)); return v; }
-__device__ __forceinline__ double lds64(uint32_t a) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a)); return v; }
-template<int OFF> __device__ __forceinline__ double lds64o(uint32_t a) { double v; asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(v) : "r"(a), "n"(OFF)); return v; }
-__device__ __forceinline__ int4 lds128(uint32_t a)
-{
-    int4 v; asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); return v;
-}
-__device__ __forceinline__ float lg2_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-
-template<int NALS> struct Shape
-{
-    static constexpr int G      = NALS*(NALS+1)/2;
-    static constexpr int NPAIR  = NALS*(NALS-1)/2;
-    static constexpr int NTRI   = NALS*(NALS-1)*(NALS-2)/6;
-    static constexpr int NSUB   = NALS + NPAIR + NTRI;
-    static constexpr int NACC   = NPAIR + NTRI + 2;         /* products: pairs, triples, N_all, N_called */
-    static constexpr bool SPLIT = NALS >= 5;                /* accumulate pairs and triples in separate sample loops */
-    static constexpr int MAXSEL = NALS<3 ? NALS : 3;        /* an allele set has at most 3 alleles (mcall.c:589-590) */
-    static constexpr int NSLOT  = MAXSEL*(MAXSEL+1)/2;      /* genotypes spanned by the selected alleles */
-};
 
 /*  per-site constants of phase 2: the group's selected alleles s0<s1<s2 span at most 6 genotypes ("slots"),
  *  kept in the output (igt) order  k: 0=(s0,s0) 1=(s1,s0) 2=(s1,s1) 3=(s2,s0) 4=(s2,s1) 5=(s2,s2)        */

@@ -53,7 +53,7 @@ struct KArgs
     /* context */
     const DevTables *tab;
     const uint8_t *ploidy_tab;  int nploidy;
-    const uint32_t *grp_off;  const uint32_t *grp_smpl;  int ngroups;
+    const uint32_t *grp_off;  const uint32_t *grp_smpl;  const uint32_t *smpl2grp;  int ngroups;
     const int32_t *site_list;  const int32_t *site_count;      /* the sites of this allele-count class */
     int nsmpl, max_nals;
     uint32_t flag, output_tags;
@@ -70,5 +70,7 @@ cudaError_t launch_site_kernel(int nals, bool ploidy, int block, const KArgs &a,
 cudaError_t launch_classify(const uint8_t *nals, int nsites, int32_t *lists, int32_t *counts, int list_stride, cudaStream_t st);
 cudaError_t launch_unsupported(const int32_t *list, const int32_t *count, int32_t *ret, uint32_t *site_flags, const uint8_t *nals, cudaStream_t st);
 cudaError_t site_kernel_occupancy(int nals, bool ploidy, int block, size_t ring_bytes, int *blocks_per_sm);
+size_t groups_scratch_bytes(int grid, int ngroups);
+cudaError_t launch_groups_kernel(int nals, const KArgs &a, void *scratch, int grid, cudaStream_t st);
 cudaError_t launch_selftest_div(const DevTables *tab, int mode, unsigned long long n, unsigned long long seed, unsigned long long *mismatch, cudaStream_t st);
 }

@@ -26,11 +26,9 @@ def _run(params, batch, tab, oracle_built, options=None, kind="port"):
     return st
 
 
-@pytest.mark.parametrize("cfg,nsites", [("C1", 10000), ("C2", 300), ("C3", 300)])
+@pytest.mark.parametrize("cfg,nsites", [("C1", 10000), ("C2", 300), ("C3", 300), ("C5", 120)])
 def test_synthetic_configs(cfg, nsites, oracle_built):
     params, batch, tab = synth.make_batch(cfg, nsites)
-    if params.ngroups > 1:
-        pytest.skip("-G groups not in this build yet")
     st = _run(params, batch, tab, oracle_built)
     assert st["compared"] > 0 and not st["near_ties"], st
 
@@ -73,6 +71,22 @@ def test_mixed_ploidy(S, oracle_built):
     assert st["compared"] > 0, st
 
 
+@pytest.mark.parametrize("S,maxA,mode,flag", [(30, 5, 3, 0), (9, 4, "single", abi.CALL_VARONLY), (200, 5, 7, abi.CALL_KEEPALT), (64, 3, 2, 0)])
+def test_sample_groups(S, maxA, mode, flag, oracle_built):
+    """-G: per-group quality sums from FORMAT/AD (float32, group order), per-group allele sets, union of the sets,
+    QUAL of the best group, per-sample genotypes with the sample's own group (mcall.c:1466-1504, 1546-1561, 1608-1614)."""
+    rng = np.random.default_rng([S, maxA, 99])
+    batch = parity.random_batch(rng, 80, S, maxA)
+    groups = [[s] for s in range(S)] if mode == "single" else [list(range(k, S, mode)) for k in range(mode)]
+    tab = np.full((2, S), 2, np.uint8)
+    tab[1, ::3] = 1
+    tab[1, 1::7] = 0
+    batch.ploidy_id = rng.integers(0, 2, batch.nsites).astype(np.uint16)
+    params = abi.CallParams(S, maxA, flag=flag, output_tags=abi.CALL_FMT_GQ, groups=groups)
+    st = _run(params, batch, tab, oracle_built)
+    assert st["compared"] > 0, st
+
+
 def test_streaming_ring_matches_resident(oracle_built):
     """Small tiles force the streaming (two TMA passes) path; results must not depend on the tiling."""
     params, batch, tab = synth.make_batch("C3", 64)
@@ -98,8 +112,6 @@ def test_cuda_reproduces_reference_goldens(name):
     """The CUDA path against the reference's own golden records (tests/golden, from test/test.pl:276-308)."""
     from bcftools_b200 import mcall
     params, batch, tab, case = golden_util.load_case(name)
-    if params.ngroups > 1:
-        pytest.skip("-G groups not in this build yet")
     want_gp = bool(params.output_tags & abi.CALL_FMT_GP)
     with mcall.MCaller(params, ploidy_tab=tab) as mc:
         res = mc.call_host(batch, want_gp=want_gp)
