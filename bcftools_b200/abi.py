@@ -56,7 +56,7 @@ class McbResult(C.Structure):
     _fields_ = [
         ("ret", C.c_void_p), ("als_new", C.c_void_p), ("als_map", C.c_void_p), ("qual", C.c_void_p),
         ("ac", C.c_void_p), ("an", C.c_void_p), ("site_flags", C.c_void_p), ("diag", C.c_void_p),
-        ("gt", C.c_void_p), ("gq", C.c_void_p), ("gp", C.c_void_p), ("pl", C.c_void_p),
+        ("gt", C.c_void_p), ("gq", C.c_void_p), ("gp", C.c_void_p), ("pl", C.c_void_p), ("pl_off_out", C.c_void_p),
     ]
 
 
@@ -68,7 +68,7 @@ BATCH_FIELDS = {  # name -> numpy dtype
 RESULT_FIELDS = {
     "ret": np.int32, "als_new": np.uint32, "als_map": np.int8, "qual": np.float32, "ac": np.int32,
     "an": np.int32, "site_flags": np.uint32, "diag": np.float64, "gt": np.int32, "gq": np.int32,
-    "gp": np.float32, "pl": np.int32,
+    "gp": np.float32, "pl": np.int32, "pl_off_out": np.int64,
 }
 
 
@@ -190,7 +190,7 @@ class HostBatch:
 class HostResult:
     """numpy arrays of one mcb_result (host memory), sized for a HostBatch."""
 
-    def __init__(self, batch, want_gp=False, fill=True):
+    def __init__(self, batch, want_gp=False, fill=True, compact=False):
         R, S, M = batch.nsites, batch.nsmpl, batch.max_nals
         self.batch = batch
         self.ret = np.zeros(R, np.int32)
@@ -205,6 +205,11 @@ class HostResult:
         self.gq = np.zeros((R, S), np.int32)
         self.gp = np.zeros(batch.pl.size, np.float32) if want_gp else None
         self.pl = np.zeros(batch.pl.size, np.int32)
+        # compact=True: trimmed PL/GP blocks are packed at the front of pl/gp, site i at pl_off_out[i]
+        self.pl_off_out = np.full(R, -1, np.int64) if compact else None
+
+    def _out_off(self, i):
+        return self.batch.pl_off[i] if self.pl_off_out is None else self.pl_off_out[i]
 
     def c_struct(self):
         r = McbResult()
@@ -216,11 +221,11 @@ class HostResult:
         """Trimmed PL block of site i: [nsmpl][G'] with G' from ret[i]."""
         n = int(self.ret[i])
         g = n * (n + 1) // 2
-        o = self.batch.pl_off[i]
+        o = self._out_off(i)
         return self.pl[o:o + self.batch.nsmpl * g].reshape(self.batch.nsmpl, g)
 
     def site_gp(self, i):
         n = int(self.ret[i])
         g = n * (n + 1) // 2
-        o = self.batch.pl_off[i]
+        o = self._out_off(i)
         return self.gp[o:o + self.batch.nsmpl * g].reshape(self.batch.nsmpl, g)

@@ -12,6 +12,7 @@
 #include <string>
 #include <vector>
 #include <algorithm>
+#include <utility>
 #include "mcall_b200.h"
 #include "mcall_kernels.cuh"
 
@@ -26,6 +27,8 @@ struct HostSlab                 /* one half of the host-path double buffer */
     cudaEvent_t  done = nullptr;
     void  *dev = nullptr;  size_t dev_bytes = 0;    /* one arena, carved per slab */
     int32_t *lists = nullptr, *counts = nullptr;  int list_cap = 0;
+    unsigned long long *cursor = nullptr;           /* device: compacted-PL allocation cursor (int32 units) */
+    unsigned long long *h_cursor = nullptr;         /* pinned host copy */
 };
 
 struct mcb_ctx
@@ -41,9 +44,10 @@ struct mcb_ctx
     void *d_grp_scratch = nullptr;  size_t grp_scratch_bytes = 0;
     /* device-path scratch */
     int32_t *d_lists = nullptr, *d_counts = nullptr;  int list_cap = 0;
+    unsigned long long *d_cursor = nullptr;
     HostSlab slab[2];
     /* options */
-    int64_t opt_tile_bytes = 32768, opt_ring_bytes = 65536, opt_blocks_per_sm = 0, opt_slab_bytes = 256ll<<20, opt_block = 128;
+    int64_t opt_tile_bytes = 32768, opt_ring_bytes = 65536, opt_blocks_per_sm = 0, opt_slab_bytes = 64ll<<20, opt_block = 128;
     int64_t opt_time_kernels = 0, opt_concurrent = 1;
     int64_t opt_ring_bytes_c[NCLASS] = {0,0,0,0,0,0};   /* per allele-count class override of ring_bytes (0 = opt_ring_bytes) */
     int64_t opt_block_c[NCLASS] = {0,0,0,0,0,0};        /* per class override of the CTA size */
@@ -197,6 +201,7 @@ extern "C" int mcb_init(mcb_ctx **out, const mcb_params *params)
     int rc = upload_ploidy(ctx);
     if ( rc ) return rc;
     CK(cudaMalloc(&ctx->d_counts, sizeof(int32_t)*NCLASS));
+    CK(cudaMalloc(&ctx->d_cursor, sizeof(unsigned long long)));
     if ( params->ngroups > 1 )         /* smpl_grp_t.smpl lists (mcall.c:250-349): every sample in exactly one group */
     {
         const int Q = params->ngroups, S = params->nsmpl;
@@ -222,6 +227,8 @@ extern "C" int mcb_init(mcb_ctx **out, const mcb_params *params)
         CK(cudaStreamCreateWithFlags(&ctx->slab[i].stream, cudaStreamNonBlocking));
         CK(cudaEventCreateWithFlags(&ctx->slab[i].done, cudaEventDisableTiming));
         CK(cudaMalloc(&ctx->slab[i].counts, sizeof(int32_t)*NCLASS));
+        CK(cudaMalloc(&ctx->slab[i].cursor, sizeof(unsigned long long)));
+        CK(cudaHostAlloc(&ctx->slab[i].h_cursor, sizeof(unsigned long long), cudaHostAllocDefault));
     }
     return MCB_OK;
 }
@@ -231,13 +238,14 @@ extern "C" void mcb_destroy(mcb_ctx *ctx)
     if ( !ctx ) return;
     cudaSetDevice(ctx->device);
     cudaFree(ctx->d_tab); cudaFree(ctx->d_ploidy); cudaFree(ctx->d_grp_off); cudaFree(ctx->d_grp_smpl); cudaFree(ctx->d_smpl2grp); cudaFree(ctx->d_grp_scratch);
-    cudaFree(ctx->d_lists); cudaFree(ctx->d_counts);
+    cudaFree(ctx->d_lists); cudaFree(ctx->d_counts); cudaFree(ctx->d_cursor);
     for (int i=0; i<2; i++)
     {
         if ( ctx->slab[i].stream ) cudaStreamDestroy(ctx->slab[i].stream);
         if ( ctx->slab[i].done ) cudaEventDestroy(ctx->slab[i].done);
         
-        cudaFree(ctx->slab[i].dev); cudaFree(ctx->slab[i].lists); cudaFree(ctx->slab[i].counts);
+        cudaFree(ctx->slab[i].dev); cudaFree(ctx->slab[i].lists); cudaFree(ctx->slab[i].counts); cudaFree(ctx->slab[i].cursor);
+        if ( ctx->slab[i].h_cursor ) cudaFreeHost(ctx->slab[i].h_cursor);
     }
     for (int i=0; i<=NCLASS; i++) if ( ctx->kev[i] ) cudaEventDestroy(ctx->kev[i]);
     for (int i=1; i<NCLASS; i++) { if ( ctx->cstream[i] ) cudaStreamDestroy(ctx->cstream[i]); if ( ctx->cev_join[i] ) cudaEventDestroy(ctx->cev_join[i]); }
@@ -319,9 +327,10 @@ static void tile_geometry(const mcb_ctx *ctx, int nals, int *tile_smpl, int *nst
     *tile_smpl = ts; *nstage = ns; *ring_bytes = tile_bytes*ns;
 }
 
-static int enqueue(mcb_ctx *ctx, const mcb_batch *b, const mcb_result *r, int32_t *lists, int32_t *counts, int list_stride, cudaStream_t st)
+static int enqueue(mcb_ctx *ctx, const mcb_batch *b, const mcb_result *r, int32_t *lists, int32_t *counts, int list_stride, unsigned long long *cursor, cudaStream_t st)
 {
     CK(cudaMemsetAsync(counts, 0, sizeof(int32_t)*NCLASS, st));
+    if ( r->pl_off_out ) CK(cudaMemsetAsync(cursor, 0, sizeof(unsigned long long), st));
     CK(launch_classify(b->nals, b->nsites, lists, counts, list_stride, st));
     int launches = 1;
     KArgs a;
@@ -331,6 +340,7 @@ static int enqueue(mcb_ctx *ctx, const mcb_batch *b, const mcb_result *r, int32_
     a.prior_an = b->prior_an; a.prior_ac = b->prior_ac;
     a.ret = r->ret; a.als_new = r->als_new; a.als_map = r->als_map; a.qual = r->qual; a.ac = r->ac; a.an = r->an;
     a.site_flags = r->site_flags; a.diag = r->diag; a.gt = r->gt; a.gq = r->gq; a.gp = r->gp; a.out_pl = r->pl;
+    a.pl_off_out = r->pl_off_out; a.pl_cursor = r->pl_off_out ? cursor : nullptr;
     a.tab = ctx->d_tab; a.ploidy_tab = ctx->d_ploidy; a.nploidy = ctx->nploidy;
     a.nsmpl = ctx->p.nsmpl; a.max_nals = ctx->p.max_nals; a.flag = ctx->p.flag; a.output_tags = ctx->p.output_tags;
     a.theta = ctx->theta_log; a.tie_eps = ctx->p.tie_eps; a.use_prior = ctx->p.use_prior;
@@ -424,7 +434,7 @@ extern "C" int mcb_call_device(mcb_ctx *ctx, const mcb_batch *b, const mcb_resul
         CK(cudaMalloc(&ctx->d_lists, sizeof(int32_t)*(size_t)NCLASS*ctx->list_cap));
     }
     ctx->stats[0] = ctx->stats[1] = 0;
-    return enqueue(ctx, b, r, ctx->d_lists, ctx->d_counts, ctx->list_cap, st);
+    return enqueue(ctx, b, r, ctx->d_lists, ctx->d_counts, ctx->list_cap, ctx->d_cursor, st);
 }
 
 /* ---- host path: slabs double-buffered over two streams ---------------------------------------------- */
@@ -456,6 +466,9 @@ extern "C" int mcb_call_host(mcb_ctx *ctx, const mcb_batch *b, const mcb_result 
     const bool want_pl = r->pl != nullptr, want_gt = r->gt != nullptr;
     const bool want_gq = r->gq && (ctx->p.output_tags & (MCB_CALL_FMT_GQ|MCB_CALL_FMT_GP));
     const bool want_gp = r->gp && (ctx->p.output_tags & MCB_CALL_FMT_GP);
+    const bool compact = r->pl_off_out != nullptr;      /* trimmed PL/GP leave the device compacted */
+    int64_t out_total = 0;                              /* int32 units already placed in r->pl */
+    std::vector<std::pair<int,int64_t>> slab_base;      /* (first site, base) per slab, applied to pl_off_out at the end */
 
     int beg = 0, islab = 0;
     while ( beg < R )
@@ -478,6 +491,7 @@ extern "C" int mcb_call_host(mcb_ctx *ctx, const mcb_batch *b, const mcb_result 
         size_t o_ret = carve(4*(size_t)n), o_als = carve(4*(size_t)n), o_map = carve((size_t)n*M), o_qual = carve(4*(size_t)n);
         size_t o_ac = carve(4*(size_t)n*M), o_an = carve(4*(size_t)n), o_fl = carve(4*(size_t)n), o_diag = carve(32*(size_t)n);
         size_t o_gt = want_gt ? carve(8*(size_t)n*S) : 0, o_gq = want_gq ? carve(4*(size_t)n*S) : 0;
+        size_t o_ploo = compact ? carve(sizeof(int64_t)*n) : 0;
         const int64_t ad0 = have_ad ? b->ad_off[beg] : 0, ad_ints = have_ad ? b->ad_off[end-1] + aext[end-1] - ad0 : 0;
         size_t o_ad = have_ad ? carve((size_t)ad_ints*4) : 0, o_adoff = have_ad ? carve(sizeof(int64_t)*n) : 0, o_nad = have_ad ? carve(n) : 0;
         if ( off > sl.dev_bytes )
@@ -535,8 +549,14 @@ extern "C" int mcb_call_host(mcb_ctx *ctx, const mcb_batch *b, const mcb_result 
         dr.gq = want_gq ? (int32_t*)(base+o_gq) : nullptr;
         dr.pl = want_pl ? (int32_t*)(base+o_plout) - pl0 : nullptr;
         dr.gp = want_gp ? (float*)(base+o_gp) - pl0 : nullptr;
+        if ( compact )
+        {
+            dr.pl = want_pl ? (int32_t*)(base+o_plout) : nullptr;
+            dr.gp = want_gp ? (float*)(base+o_gp) : nullptr;
+            dr.pl_off_out = (int64_t*)(base+o_ploo);
+        }
 
-        int rc = enqueue(ctx, &db, &dr, sl.lists, sl.counts, sl.list_cap, st);
+        int rc = enqueue(ctx, &db, &dr, sl.lists, sl.counts, sl.list_cap, sl.cursor, st);
         if ( rc ) return rc;
 
 #define D2H(dst,src,bytes) CK(cudaMemcpyAsync((dst), base+(src), (bytes), cudaMemcpyDeviceToHost, st))
@@ -550,13 +570,34 @@ extern "C" int mcb_call_host(mcb_ctx *ctx, const mcb_batch *b, const mcb_result 
         if ( r->diag ) D2H(r->diag + (size_t)beg*4, o_diag, 32*(size_t)n);
         if ( want_gt ) D2H(r->gt + (size_t)beg*S*2, o_gt, 8*(size_t)n*S);
         if ( want_gq ) D2H(r->gq + (size_t)beg*S, o_gq, 4*(size_t)n*S);
-        if ( want_pl ) D2H(r->pl + pl0, o_plout, (size_t)pl_ints*4);
-        if ( want_gp ) D2H(r->gp + pl0, o_gp, (size_t)pl_ints*4);
+        if ( !compact )
+        {
+            if ( want_pl ) D2H(r->pl + pl0, o_plout, (size_t)pl_ints*4);
+            if ( want_gp ) D2H(r->gp + pl0, o_gp, (size_t)pl_ints*4);
+        }
+        else
+        {
+            /* the number of used int32 is only known once the kernels of this slab have run */
+            CK(cudaMemcpyAsync(sl.h_cursor, sl.cursor, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+            D2H(r->pl_off_out + beg, o_ploo, sizeof(int64_t)*n);
+            CK(cudaStreamSynchronize(st));
+            const int64_t used = (int64_t)*sl.h_cursor;
+            if ( want_pl && used ) D2H(r->pl + out_total, o_plout, (size_t)used*4);
+            if ( want_gp && used ) D2H(r->gp + out_total, o_gp, (size_t)used*4);
+            slab_base.push_back(std::make_pair(beg, out_total));
+            out_total += used;
+        }
 #undef D2H
         CK(cudaEventRecord(sl.done, st));
         beg = end; islab++;
     }
     CK(cudaStreamSynchronize(ctx->slab[0].stream));
     CK(cudaStreamSynchronize(ctx->slab[1].stream));
+    for (size_t k=0; k<slab_base.size(); k++)           /* slab-local offsets -> offsets into r->pl */
+    {
+        const int first = slab_base[k].first, last = k+1<slab_base.size() ? slab_base[k+1].first : R;
+        for (int i=first; i<last; i++) if ( r->pl_off_out[i] >= 0 ) r->pl_off_out[i] += slab_base[k].second;
+    }
+    ctx->stats[2] = out_total;
     return MCB_OK;
 }

@@ -33,6 +33,7 @@ struct GSite                /* site decision record, shared memory */
     double max_qual, lk_sum, ref_lk;
     uint32_t als_new, flags;
     int nals_new, is_variant, ret_early, pl_dropped, ref_gt;
+    long long out_off;
     int als_map[5], pl_map[15], ac[8];
 };
 
@@ -348,6 +349,17 @@ __global__ void __launch_bounds__(GBLOCK) mcall_groups_kernel(const KArgs a, Gro
             st.ref_gt = (als_new==1) || !is_variant;
             if ( st.pl_dropped ) flags |= MCB_SITE_PL_DROPPED;
             if ( st.ref_gt ) flags |= MCB_SITE_REF_GT;
+            {
+                long long off = site_off;
+                if ( a.pl_off_out )
+                {
+                    off = -1;
+                    if ( !st.pl_dropped && !st.ret_early )
+                        off = (long long)atomicAdd(a.pl_cursor, (unsigned long long)(((long long)nsmpl*(nals_new*(nals_new+1)/2) + 3) & ~3ll));
+                    a.pl_off_out[site] = off;
+                }
+                st.out_off = off;
+            }
             st.als_new = als_new; st.nals_new = nals_new; st.is_variant = is_variant; st.flags = flags;
             st.max_qual = max_qual; st.lk_sum = lk_sum; st.ref_lk = ref_lk;
         }
@@ -365,8 +377,8 @@ __global__ void __launch_bounds__(GBLOCK) mcall_groups_kernel(const KArgs a, Gro
             const bool ref_gt = st.ref_gt;
             const bool want_gq = a.gq && (a.output_tags & (MCB_CALL_FMT_GQ|MCB_CALL_FMT_GP));
             const bool want_gp = a.gp && (a.output_tags & MCB_CALL_FMT_GP) && !ref_gt;
-            int32_t *out_pl = (a.out_pl && !st.pl_dropped) ? a.out_pl + site_off : nullptr;
-            float   *out_gp = want_gp ? a.gp + site_off : nullptr;
+            int32_t *out_pl = (a.out_pl && !st.pl_dropped) ? a.out_pl + st.out_off : nullptr;
+            float   *out_gp = want_gp ? a.gp + st.out_off : nullptr;
             int2 *out_gt = a.gt ? reinterpret_cast<int2*>(a.gt) + (size_t)site*nsmpl : nullptr;
             int32_t *out_gq = want_gq ? a.gq + (size_t)site*nsmpl : nullptr;
             uint32_t tflags = 0;

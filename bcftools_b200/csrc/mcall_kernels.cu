@@ -4,7 +4,16 @@
 
 #include "mcall_device.cuh"
 
+#ifndef MCB_UNROLL1
+#define MCB_UNROLL1 1       /* unroll factor of the phase-1 sample loop */
+#endif
+#ifndef MCB_UNROLL2
+#define MCB_UNROLL2 1       /* unroll factor of the phase-2 sample loop */
+#endif
+
 namespace mcb {
+
+constexpr int kUnroll1 = MCB_UNROLL1, kUnroll2 = MCB_UNROLL2;
 
 /*  per-site constants of phase 2: the group's selected alleles s0<s1<s2 span at most 6 genotypes ("slots"),
  *  kept in the output (igt) order  k: 0=(s0,s0) 1=(s1,s0) 2=(s1,s1) 3=(s2,s0) 4=(s2,s1) 5=(s2,s2)        */
@@ -42,6 +51,7 @@ template<int NALS, int BLOCK> struct Shared
     double   max_qual, lk_sum, ref_lk, gap;
     uint32_t grp_als, als_new, flags;
     int      grp_nals, nals_new, is_variant, ret_early, pl_dropped, ref_gt;
+    long long out_off;       /* where this site's trimmed PL / GP block goes */
     int      als_map[NALS];
     int      pl_map[S::G];
     int      ac[8];
@@ -112,7 +122,7 @@ __device__ __forceinline__ bool load_sample_w(uint32_t row_s, uint32_t pl2p_s, b
     if ( fast )
     {
         #pragma unroll
-        for (int j=0; j<G; j++) p[j] = lds64(pl2p_s + 8u*(uint32_t)pl[j]);
+        for (int j=0; j<G; j++) p[j] = lds64c(pl2p_s + 8u*(uint32_t)pl[j]);
     }
     else
     {
@@ -342,7 +352,7 @@ __global__ void __launch_bounds__(BLOCK, (MinBlocks<NALS,BLOCK>::value)) mcall_s
             for (int pass=0; pass<(S::SPLIT ? 2 : 1); pass++)
             {
                 const bool do_pairs = pass==0, do_tri = S::SPLIT ? pass==1 : true;
-                #pragma unroll 1
+                #pragma unroll (kUnroll1)
                 for (int sb=0; sb<n; sb+=BLOCK)         /* uniform trip count: the loader votes across the warp */
                 {
                     const int s = min(sb + tid, n-1);
@@ -607,6 +617,17 @@ __global__ void __launch_bounds__(BLOCK, (MinBlocks<NALS,BLOCK>::value)) mcall_s
                 if ( unseen && (als_new & (1u<<unseen)) ) flags |= MCB_SITE_UNSEEN_SEL;
                 sh.pl_dropped = als_new==1;
                 sh.ref_gt = (als_new==1) || !is_variant;
+                {
+                    long long off = site_off;
+                    if ( a.pl_off_out )
+                    {
+                        off = -1;
+                        if ( !sh.pl_dropped && !ret_early )
+                            off = (long long)atomicAdd(a.pl_cursor, (unsigned long long)(((long long)nsmpl*(nals_new*(nals_new+1)/2) + 3) & ~3ll));
+                        a.pl_off_out[site] = off;
+                    }
+                    sh.out_off = off;
+                }
                 if ( sh.pl_dropped ) flags |= MCB_SITE_PL_DROPPED;
                 if ( sh.ref_gt ) flags |= MCB_SITE_REF_GT;
                 int gn = 0;
@@ -675,8 +696,8 @@ __global__ void __launch_bounds__(BLOCK, (MinBlocks<NALS,BLOCK>::value)) mcall_s
             const bool want_gq = a.gq && (a.output_tags & (MCB_CALL_FMT_GQ|MCB_CALL_FMT_GP));
             const bool want_gp = a.gp && (a.output_tags & MCB_CALL_FMT_GP) && !ref_gt;
             const bool want_gqm = want_gq || want_gp;       /* the max/sum arithmetic is shared by GQ and GP */
-            int32_t *out_pl = (a.out_pl && !pl_dropped) ? a.out_pl + site_off : nullptr;
-            float   *out_gp = want_gp ? a.gp + site_off : nullptr;
+            int32_t *out_pl = (a.out_pl && !pl_dropped) ? a.out_pl + sh.out_off : nullptr;
+            float   *out_gp = want_gp ? a.gp + sh.out_off : nullptr;
             int2 *out_gt = a.gt ? reinterpret_cast<int2*>(a.gt) + (size_t)site*nsmpl : nullptr;
             int32_t *out_gq = want_gq ? a.gq + (size_t)site*nsmpl : nullptr;
             /* per-site constants into registers */
@@ -724,7 +745,7 @@ __global__ void __launch_bounds__(BLOCK, (MinBlocks<NALS,BLOCK>::value)) mcall_s
                 const int s0 = t*TS, n = min(TS, nsmpl - s0);
                 if ( acc_n + (TS + BLOCK - 1)/BLOCK > 63 ) flush_ac();     /* uniform across the block: safe to shuffle */
                 acc_n += (TS + BLOCK - 1)/BLOCK;
-                #pragma unroll 1
+                #pragma unroll (kUnroll2)
                 for (int sb=0; sb<n; sb+=BLOCK)         /* uniform trip count: the loader votes across the warp */
                 {
                     const int s = min(sb + tid, n-1);
@@ -842,8 +863,8 @@ __global__ void __launch_bounds__(BLOCK, (MinBlocks<NALS,BLOCK>::value)) mcall_s
                                 /* (int)(-4.34294*log(x)) from host-libm thresholds: float estimate, exact fix-up */
                                 int k = __float2int_rz(-3.0102999f*lg2_approx((float)xx));
                                 k = max(0, min(127, k));
-                                if ( xx <= lds64(thr_s + 8u*(uint32_t)(k+1)) ) { k++; while ( xx <= lds64(thr_s + 8u*(uint32_t)(k+1)) ) k++; }
-                                else while ( xx > lds64(thr_s + 8u*(uint32_t)k) ) k--;
+                                if ( xx <= lds64c(thr_s + 8u*(uint32_t)(k+1)) ) { k++; while ( xx <= lds64c(thr_s + 8u*(uint32_t)(k+1)) ) k++; }
+                                else while ( xx > lds64c(thr_s + 8u*(uint32_t)k) ) k--;
                                 gq = k;
                             }
                         }

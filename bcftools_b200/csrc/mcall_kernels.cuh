@@ -50,6 +50,7 @@ struct KArgs
     /* result (device pointers, may be NULL) */
     int32_t *ret;  uint32_t *als_new;  int8_t *als_map;  float *qual;  int32_t *ac;  int32_t *an;
     uint32_t *site_flags;  double *diag;  int32_t *gt;  int32_t *gq;  float *gp;  int32_t *out_pl;
+    int64_t *pl_off_out;  unsigned long long *pl_cursor;     /* compacted PL/GP output (optional) */
     /* context */
     const DevTables *tab;
     const uint8_t *ploidy_tab;  int nploidy;

@@ -282,7 +282,7 @@ def main():
     if not args.no_e2e:
         ne = min(args.e2e_sites, hb.nsites)
         sub = mcall.pin_batch(hb.subset(range(ne)))
-        hres = mcall.pin_result(abi.HostResult(sub))
+        hres = mcall.pin_result(abi.HostResult(sub, compact=True))      # trimmed PLs leave the device compacted
         for _ in range(2):
             mc.call_host(sub, hres)
         barrier()
@@ -296,8 +296,8 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
         h2d = sum(getattr(sub, k).nbytes for k in ("pl", "pl_off", "nals", "unseen", "qs") if getattr(sub, k) is not None)
-        d2h = sum(getattr(hres, k).nbytes for k in ("ret", "als_new", "als_map", "qual", "ac", "an", "site_flags", "diag", "gt", "gq", "pl")
-                  if getattr(hres, k) is not None)
+        d2h = sum(getattr(hres, k).nbytes for k in ("ret", "als_new", "als_map", "qual", "ac", "an", "site_flags", "diag", "gt", "gq", "pl_off_out")
+                  if getattr(hres, k) is not None) + 4 * int(mc.stats()[2])        # + the used (compacted) part of the PL buffer
         e2e = dict(value=world * args.steps * ne * params.nsmpl / dt, unit=UNIT, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
                    sites_per_step=ne, ms_per_step=1e3 * dt / args.steps)
 

@@ -127,6 +127,9 @@ typedef struct mcb_result
     int32_t  *gq;           /* [nsites][nsmpl] FORMAT/GQ (only with MCB_CALL_FMT_GQ|GP) */
     float    *gp;           /* FORMAT/GP, site i at gp + pl_off[i], [nsmpl][G'_i] (only with MCB_CALL_FMT_GP) */
     int32_t  *pl;           /* trimmed FORMAT/PL, site i at pl + pl_off[i], [nsmpl][G'_i], G'_i from ret[i] */
+    int64_t  *pl_off_out;   /* [nsites] optional.  If non-NULL the trimmed PLs (and GP) are written COMPACTED: site i lies
+                               at pl + pl_off_out[i] (16-byte aligned blocks in no particular order, -1 when the site has
+                               no PL); the used prefix of pl is all that travels device->host in mcb_call_host */
 }
 mcb_result;
 

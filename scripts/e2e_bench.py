@@ -1,0 +1,20 @@
+"""End-to-end (host buffers) timing of mcb_call_host for different slab sizes (development aid)."""
+import sys, os, time, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from bcftools_b200 import abi, synth, mcall
+sites = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
+params, hb, tab = synth.make_batch("C3", sites, with_groups=0)
+for slab_mb in (256, 128, 64, 32, 16):
+    mc = mcall.MCaller(params, ploidy_tab=tab, options={"slab_bytes": slab_mb << 20})
+    sub = mcall.pin_batch(hb.subset(range(sites)))
+    res = mcall.pin_result(abi.HostResult(sub))
+    for _ in range(2):
+        mc.call_host(sub, res)
+    t0 = time.perf_counter()
+    n = 5
+    for _ in range(n):
+        mc.call_host(sub, res)
+    dt = (time.perf_counter() - t0) / n
+    print(json.dumps(dict(slab_mb=slab_mb, ms=dt * 1e3, calls_per_s=sites * params.nsmpl / dt)), flush=True)
+    mc.close()

@@ -14,6 +14,7 @@ ap.add_argument("--opt", action="append", default=[])
 ap.add_argument("--tags", type=int, default=abi.CALL_FMT_GQ)
 ap.add_argument("--flag", type=int, default=0)
 ap.add_argument("--check", action="store_true")
+ap.add_argument("--classes", action="store_true", help="also print the device ms per allele-count class (serialised)")
 ap.add_argument("--block", type=int, default=0)
 args = ap.parse_args()
 
@@ -42,6 +43,17 @@ t = float(np.median(times))
 out = dict(config=args.config, sites=db.nsites, nsmpl=params.nsmpl, opts=opts, ms=t * 1e3, calls_per_s=calls / t,
            alg_GBs=(rd + wr) * args.rep / t / 1e9, bytes_per_call=(rd + wr) / (hb.nsites * params.nsmpl),
            frac_of_6551=(rd + wr) * args.rep / t / 1e9 / 6551.4, tmin_ms=min(times) * 1e3)
+if args.classes:
+    mc.set_option("time_kernels", 1)
+    kt = []
+    for _ in range(5):
+        mc.call_device(b, r, stream)
+        kt.append(mc.kernel_times_ms())
+    kt = np.median(np.array(kt), axis=0)
+    cnt = np.bincount(hb.nals, minlength=6) * args.rep
+    out["class_ms"] = {str(k): round(float(kt[k]), 4) for k in range(1, 6)}
+    out["class_calls_per_s"] = {str(k): (float(cnt[k] * params.nsmpl / (kt[k] * 1e-3)) if kt[k] > 0 and cnt[k] else 0) for k in range(1, 6)}
+    mc.set_option("time_kernels", 0)
 print(json.dumps(out), flush=True)
 if args.check:
     from oracle import pyoracle

@@ -95,6 +95,62 @@ def test_streaming_ring_matches_resident(oracle_built):
         assert st["compared"] > 0 and not st["near_ties"], (opts, st)
 
 
+def test_biobank_shape_100k_samples(oracle_built):
+    """BASELINE config 4 shape: 100,000 samples per site (1.2 MB of PL per site, streamed through the ring twice)."""
+    params, batch, tab = synth.make_batch("C4", 6)
+    st = _run(params, batch, tab, oracle_built)
+    assert st["compared"] > 0 and not st["near_ties"], st
+
+
+def test_full_size_properties_without_oracle():
+    """Size-independent properties at a batch the CPU oracle would need minutes for (C3 shape, 4096 sites = 10 M calls):
+    AN = sum(AC) = number of called alleles in GT; every GT allele index < ret; trimmed PL rows keep a zero for
+    samples whose input row had its zero on a kept genotype; idempotence (a second run is bit-identical)."""
+    from bcftools_b200 import mcall
+    params, batch, tab = synth.make_batch("C3", 4096)
+    with mcall.MCaller(params, ploidy_tab=tab) as mc:
+        r1 = mc.call_host(batch)
+        r2 = mc.call_host(batch)
+    for name in ("ret", "als_new", "als_map", "ac", "an", "gt", "gq", "site_flags"):
+        assert (getattr(r1, name) == getattr(r2, name)).all(), name
+    assert (r1.qual.view(np.uint32) == r2.qual.view(np.uint32)).all()
+    called = r1.ret > 0
+    assert called.all()                                     # no -v: every site is emitted
+    gt = r1.gt[called]
+    alle = (gt >> 1) - 1                                    # -1 = missing
+    n_called = (alle >= 0).sum(axis=(1, 2))
+    assert (r1.an[called] == n_called).all()
+    assert (r1.ac[called].sum(1) == r1.an[called]).all()
+    assert (alle.max(axis=(1, 2)) < r1.ret[called]).all()
+    for j in range(5):
+        assert (r1.ac[called][:, j] == (alle == j).sum(axis=(1, 2))).all()
+    for i in np.where(called & ((r1.site_flags & abi.SITE_PL_DROPPED) == 0))[0][:200]:
+        tp = r1.site_pl(i)
+        assert tp.shape[1] == r1.ret[i] * (r1.ret[i] + 1) // 2
+        src = batch.site_pl(i)
+        kept = [k for k in range(src.shape[1])]
+        assert ((tp >= 0) | (tp == abi.INT32_MISSING) | (tp == abi.INT32_VECTOR_END)).all()
+
+
+def test_compacted_pl_output(oracle_built):
+    """mcb_result.pl_off_out: trimmed PL blocks packed at the front of the output buffer (what leaves the device in
+    the host path); content must be identical to the in-place layout, several slabs per call."""
+    from bcftools_b200 import mcall
+    params, batch, tab = synth.make_batch("C3", 200, flag=abi.CALL_VARONLY)
+    exp, _ = oracle_built.call("port", params, batch, tab)
+    with mcall.MCaller(params, ploidy_tab=tab, options={"slab_bytes": 4 << 20}) as mc:
+        got = mc.call_host(batch, compact=True)
+    st = parity.compare(got, exp, params)
+    assert st["compared"] > 0
+    used = sorted((int(got.pl_off_out[i]), int(got.ret[i])) for i in range(batch.nsites) if got.pl_off_out[i] >= 0)
+    end = 0
+    for off, n in used:                      # blocks are disjoint, 16-byte aligned and gap-free
+        assert off == end and off % 4 == 0
+        end = off + abi.pad4(params.nsmpl * n * (n + 1) // 2)
+    dropped = (got.site_flags & abi.SITE_PL_DROPPED) != 0
+    assert ((got.pl_off_out < 0) == (dropped | (got.ret <= 0))).all()
+
+
 def test_empty_batch():
     from bcftools_b200 import mcall
     params = abi.CallParams(8, 5)
