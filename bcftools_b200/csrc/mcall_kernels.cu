@@ -713,6 +713,7 @@ __global__ void __launch_bounds__(BLOCK, (MinBlocks<NALS,BLOCK>::value)) mcall_s
             int plm4[NPLM];
             #pragma unroll
             for (int k=0; k<NPLM; k++) plm4[k] = 4*sh.pl_map[k];
+            const uint32_t oflags = (out_gt ? 1u : 0u) | (out_gq ? 2u : 0u) | (out_pl ? 4u : 0u) | (out_gp ? 8u : 0u);
             unsigned long long acc = 0;     /* AC: 12-bit counters, new allele j at bits [12j,12j+12) */
             int acc_n = 0;
             uint32_t tflags2 = 0;
@@ -872,30 +873,56 @@ __global__ void __launch_bounds__(BLOCK, (MinBlocks<NALS,BLOCK>::value)) mcall_s
                     if ( !valid ) continue;
                     acc += (unsigned long long)(uint32_t)outc.z | ((unsigned long long)(uint32_t)outc.w << 32);
                     const int sg = s0 + s;
-                    if ( out_gt ) out_gt[sg] = make_int2(outc.x, outc.y);
-                    if ( out_gq ) out_gq[sg] = gq;
-                    if ( out_pl )               /* mcall.c:1158-1194; the ring row holds the filled PLs */
+                    /* stores: one address computation per output array, explicit PTX so that it is not rebuilt per value */
+                    if ( oflags & 1u )
                     {
-                        int32_t *dst = out_pl + (size_t)sg*ngt_new;
-                        if ( pld==2 )
+                        const int2 *p2 = out_gt + sg;
+                        asm volatile("st.global.v2.s32 [%0], {%1,%2};" :: "l"(p2), "r"(outc.x), "r"(outc.y) : "memory");
+                    }
+                    if ( oflags & 2u )
+                    {
+                        const int32_t *p1 = out_gq + sg;
+                        asm volatile("st.global.s32 [%0], %1;" :: "l"(p1), "r"(gq) : "memory");
+                    }
+                    if ( oflags & 4u )          /* mcall.c:1158-1194; the ring row holds the filled PLs */
+                    {
+                        const int32_t *dst = out_pl + (size_t)sg*ngt_new;
+                        if ( G<=3 || ngt_new<=3 )       /* at most 3 values: the common, fully unrolled case */
                         {
-                            #pragma unroll
-                            for (int k=0; k<G; k++)
-                                if ( k<ngt_new ) dst[k] = lds32(row_s + (uint32_t)(k<NPLM ? plm4[k<NPLM?k:0] : 4*sh.pl_map[k]));
-                        }
-                        else if ( pld==1 )
-                        {
-                            #pragma unroll
-                            for (int k=0; k<G; k++)
-                                if ( k<ngt_new ) dst[k] = k<nals_new ? lds32(row_s + 4u*(uint32_t)sh.pl_map[hom_idx(k)]) : I32_VEC_END;
+                            int v0, v1 = I32_VEC_END, v2 = I32_VEC_END;
+                            if ( pld==2 )
+                            {
+                                v0 = lds32(row_s + (uint32_t)plm4[0]);
+                                if ( G>1 ) { v1 = lds32(row_s + (uint32_t)plm4[G>1?1:0]); v2 = lds32(row_s + (uint32_t)plm4[G>2?2:0]); }
+                            }
+                            else if ( pld==1 )
+                            {
+                                v0 = lds32(row_s + (uint32_t)plm4[0]);                             /* hom_idx(0) = 0 */
+                                if ( G>1 && nals_new>1 ) v1 = lds32(row_s + (uint32_t)plm4[G>2?2:0]);  /* hom_idx(1) = 2 */
+                            }
+                            else v0 = I32_MISSING;
+                            asm volatile("st.global.s32 [%0], %1;" :: "l"(dst), "r"(v0) : "memory");
+                            if ( ngt_new>1 )
+                            {
+                                asm volatile("st.global.s32 [%0+4], %1;" :: "l"(dst), "r"(v1) : "memory");
+                                asm volatile("st.global.s32 [%0+8], %1;" :: "l"(dst), "r"(v2) : "memory");
+                            }
                         }
                         else
                         {
                             #pragma unroll
-                            for (int k=0; k<G; k++) if ( k<ngt_new ) dst[k] = k==0 ? I32_MISSING : I32_VEC_END;
+                            for (int k=0; k<G; k++)
+                            {
+                                if ( k>=ngt_new ) continue;
+                                int v;
+                                if ( pld==2 ) v = lds32(row_s + (uint32_t)(k<NPLM ? plm4[k<NPLM?k:0] : 4*sh.pl_map[k]));
+                                else if ( pld==1 ) v = k<nals_new ? lds32(row_s + 4u*(uint32_t)sh.pl_map[hom_idx(k)]) : I32_VEC_END;
+                                else v = k==0 ? I32_MISSING : I32_VEC_END;
+                                asm volatile("st.global.s32 [%0], %1;" :: "l"(dst + k), "r"(v) : "memory");
+                            }
                         }
                     }
-                    if ( out_gp )               /* FORMAT/GP, mcall.c:859-884 (gv[] holds the float32-rounded values) */
+                    if ( oflags & 8u )          /* FORMAT/GP, mcall.c:859-884 (gv[] holds the float32-rounded values) */
                     {
                         float *dst = out_gp + (size_t)sg*ngt_new;
                         const int nmax = pld==2 ? ngt_new : (pld==1 ? grp_nals : 0);

@@ -1,0 +1,91 @@
+/*  b200_call.h -- host side of the B200 `call -m` path, in C, mirroring the reference's calling interface.
+ *
+ *  The reference exposes  void mcall_init(call_t*); int mcall(call_t*, bcf1_t*); void mcall_destroy(call_t*)
+ *  (call.h:131-147) and drives them one record at a time from main_vcfcall() (vcfcall.c:1089-1148).  A GPU cannot be
+ *  fed one record at a time, so this layer keeps the same three hooks but batches: b200_mcall() queues the record
+ *  (after unpacking what mcall() would fetch with bcf_get_format_int32 / bcf_get_info_float, mcall.c:1444-1510, into
+ *  pinned structure-of-arrays slabs) and flushes through the C-ABI (mcall_b200.h) when the batch is full.
+ *  b200_call_t carries the call_t fields this path reads (call.h:72-123), with the same names and meaning.
+ *  htslib-free: the caller hands the already-unpacked arrays (see INTEGRATION.md for the htslib glue).
+ */
+#ifndef B200_CALL_H
+#define B200_CALL_H
+#include <stdint.h>
+#include "mcall_b200.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* same values as call.h:32-39 */
+#define CALL_KEEPALT   1
+#define CALL_VARONLY   (1<<1)
+#define CALL_FMT_GQ    (1<<6)
+#define CALL_FMT_GP    (1<<7)
+
+typedef struct b200_batcher b200_batcher_t;
+
+typedef struct
+{
+    /* ---- set by the driver before b200_mcall_init, like vcfcall.c does for call_t ---- */
+    int      nsmpl;             /* bcf_hdr_nsamples(call->hdr) */
+    uint32_t flag;              /* CALL_KEEPALT | CALL_VARONLY            (call.h:112) */
+    uint32_t output_tags;       /* CALL_FMT_GQ | CALL_FMT_GP              (call.h:93)  */
+    double   theta;             /* prior, vcfcall.c:933; turned into log(theta*aM) by init (mcall.c:397-416) */
+    uint8_t *ploidy;            /* [nsmpl] 0/1/2, rewritten per region by the driver (vcfcall.c:807-825); call.h:113 */
+    uint8_t  unseen;            /* index of <*>, 0 = none (vcfcall.c:1101-1111); call.h:113 */
+    int      nsmpl_grp;         /* number of -G groups, <=1 = pooled      (call.h:98-99) */
+    const uint32_t *grp_off;    /* [nsmpl_grp+1] */
+    const uint32_t *grp_smpl;   /* [nsmpl] smpl_grp_t.smpl lists, group after group (call.h:58) */
+    int      use_prior;         /* -F prior_AN,prior_AC given (call.h:94) */
+    int      max_records;       /* records per batch, 0 = 4096 */
+    int      max_nals;          /* 0 = 5 (B2B_MAX_ALLELES, bam2bcf.h:64) */
+    int      device;            /* CUDA device ordinal */
+    /* ---- owned by this layer ---- */
+    b200_batcher_t *batcher;
+}
+b200_call_t;
+
+/*  What mcall() pulls out of one bcf1_t (mcall.c:1438-1510).  Pointers are only read during b200_mcall().  */
+typedef struct
+{
+    int n_allele;               /* rec->n_allele */
+    const int32_t *PLs; int nPLs;   /* bcf_get_format_int32(..."PL"...): nsmpl*G values (mcall.c:1444) */
+    const float   *QS;  int nQS;    /* bcf_get_info_float(..."QS"...) (mcall.c:1456); pooled calling */
+    const int32_t *ADs; int nADs;   /* FORMAT/AD for -G (mcall.c:1475): nsmpl*nad values */
+    int32_t prior_an;               /* -F: INFO AN or INT32_MIN if absent (mcall.c:1507) */
+    const int32_t *prior_ac; int n_prior_ac;
+    void *user;                 /* e.g. the retained bcf1_t*, handed back with the result */
+}
+b200_rec_t;
+
+/*  What mcall() writes back into the record (mcall.c:1546-1657), valid until the next b200_mcall on the same call.  */
+typedef struct
+{
+    int ret;                    /* mcall()'s return value: 0 = not a variant / skipped, else number of output alleles */
+    uint32_t als_new;           /* call->als_new */
+    const int8_t *als_map;      /* [max_nals] call->als_map */
+    float qual;                 /* rec->qual */
+    const int32_t *ac; int an;  /* call->ac[0..ret), INFO/AN */
+    uint32_t site_flags;        /* MCB_SITE_* (PL dropped, near tie, ...) */
+    const int32_t *gts;         /* [nsmpl*2] call->gts */
+    const int32_t *GQs;         /* [nsmpl] or NULL */
+    const int32_t *PLs; int nPLs;   /* trimmed PLs: nsmpl*G' values, NULL when the tag is dropped (mcall.c:1583) */
+    void *user;
+}
+b200_out_t;
+
+/*  error handler: default prints and exit(-1) like error() in version.c:40-47  */
+void b200_set_error_handler(void (*handler)(const char *msg));
+
+void b200_mcall_init(b200_call_t *call);                            /* = mcall_init, vcfcall.c:697-698 */
+/*  = mcall(), vcfcall.c:1136-1137, batched: queues the record.  Returns the number of results that became
+ *  available (0 while the batch is filling, the batch size after an automatic flush).                     */
+int  b200_mcall(b200_call_t *call, const b200_rec_t *rec);
+int  b200_mcall_flush(b200_call_t *call);                           /* run the partial batch; returns results available */
+int  b200_mcall_result(b200_call_t *call, int i, b200_out_t *out);  /* i-th result of the last flush, in input order */
+void b200_mcall_destroy(b200_call_t *call);                         /* = mcall_destroy, vcfcall.c:722-723 */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

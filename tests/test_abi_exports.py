@@ -24,6 +24,17 @@ def test_header_symbols_are_exported():
     assert sorted(mcall.EXPORTS) == syms, (sorted(mcall.EXPORTS), syms)
 
 
+def test_host_layer_symbols_are_exported():
+    """include/b200_call.h: the C mirror of mcall_init / mcall / mcall_destroy."""
+    from bcftools_b200 import host_call, mcall
+    hdr = open(os.path.join(ROOT, "include", "b200_call.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    syms = sorted(set(re.findall(r"\b(b200_[a-z0-9_]+)\s*\(", hdr)))
+    L = mcall.lib()
+    assert syms == sorted(host_call.HOST_EXPORTS), syms
+    assert all(hasattr(L, s) for s in syms)
+
+
 def test_struct_layouts_match_header():
     """ctypes mirrors must have the field order of the C structs (a mismatch would silently scramble pointers)."""
     from bcftools_b200 import abi

@@ -172,3 +172,17 @@ def test_cuda_reproduces_reference_goldens(name):
     with mcall.MCaller(params, ploidy_tab=tab) as mc:
         res = mc.call_host(batch, want_gp=want_gp)
     assert golden_util.check_against_expect(case, params, batch, res) == len(case["expect"])
+
+
+@pytest.mark.parametrize("name", golden_util.case_names())
+def test_host_batcher_replays_reference_goldens(name):
+    """The C host layer (include/b200_call.h): records pushed one at a time through b200_mcall(), the way
+    vcfcall.c:1089-1148 drives mcall(), small batches so that several flushes happen."""
+    from bcftools_b200 import host_call
+    params, batch, tab, case = golden_util.load_case(name)
+    if params.output_tags & abi.CALL_FMT_GP:
+        pytest.skip("the C batcher does not carry FORMAT/GP yet")
+    if any(s.get("qs") is None for s in case["sites"]) and params.ngroups <= 1:
+        pytest.skip("no QS")
+    res = host_call.replay(params, batch, tab, max_records=16)
+    assert golden_util.check_against_expect(case, params, batch, res) == len(case["expect"])
