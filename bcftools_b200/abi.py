@@ -49,6 +49,7 @@ class McbBatch(C.Structure):
         ("qs", C.c_void_p), ("nqs", C.c_void_p),
         ("ad", C.c_void_p), ("ad_off", C.c_void_p), ("nad", C.c_void_p),
         ("prior_an", C.c_void_p), ("prior_ac", C.c_void_p),
+        ("pl_type", C.c_int32),
     ]
 
 
@@ -163,6 +164,8 @@ class HostBatch:
             a = np.asarray(prior_ac, np.int32)
             self.prior_ac[:, :a.shape[1]] = a
 
+    pl_type = 0
+
     def site_pl(self, i):
         return self.pl[self.pl_off[i]:self.pl_off[i] + self.nsmpl * int(self.ngt[i])].reshape(self.nsmpl, -1)
 
@@ -171,7 +174,27 @@ class HostBatch:
         b.nsites = self.nsites
         for name in BATCH_FIELDS:
             setattr(b, name, _ptr(getattr(self, name)))
+        b.pl_type = getattr(self, "pl_type", 0)
         return b
+
+    def to_int16(self):
+        """Same batch with the PL slab as BCF-style int16 typed vectors (sentinels INT16_MIN / INT16_MIN+1), sites on
+        16-byte boundaries.  Values must fit (PL <= 32767)."""
+        import copy
+        nb = copy.copy(self)
+        S = self.nsmpl
+        sizes = (S * self.ngt + 7) & ~7
+        nb.pl_off = np.zeros(self.nsites, np.int64)
+        if self.nsites:
+            nb.pl_off[1:] = np.cumsum(sizes)[:-1]
+        nb.pl = np.full(int(sizes.sum()) if self.nsites else 0, -32767, np.int16)
+        for i in range(self.nsites):
+            src = self.pl[self.pl_off[i]:self.pl_off[i] + S * int(self.ngt[i])]
+            dst = np.where(src == INT32_MISSING, -32768, np.where(src == INT32_VECTOR_END, -32767, src))
+            assert dst.max(initial=0) <= 32767
+            nb.pl[nb.pl_off[i]:nb.pl_off[i] + src.size] = dst.astype(np.int16)
+        nb.pl_type = 2
+        return nb
 
     def subset(self, idx):
         """Batch restricted to the given sites (copies)."""

@@ -312,14 +312,14 @@ extern "C" int mcb_selftest_div(mcb_ctx *ctx, int mode, uint64_t n, uint64_t see
 /* ---- launch geometry -------------------------------------------------------------------------------- */
 static int class_block(const mcb_ctx *ctx, int nals) { return (int)(ctx->opt_block_c[nals] ? ctx->opt_block_c[nals] : ctx->opt_block); }
 
-static void tile_geometry(const mcb_ctx *ctx, int nals, int *tile_smpl, int *nstage, size_t *ring_bytes)
+static void tile_geometry(const mcb_ctx *ctx, int nals, int es, int *tile_smpl, int *nstage, size_t *ring_bytes)
 {
     int G = nals*(nals+1)/2, S = ctx->p.nsmpl;
-    int ts = (int)(ctx->opt_tile_bytes/(4*G));
+    int ts = (int)(ctx->opt_tile_bytes/(es*G));
     ts = std::max(256, ts/256*256);
     ts = std::min(ts, 32*class_block(ctx, nals));      /* the AC counters of phase 2 allow at most 63 samples per thread and tile */
     int ntiles = (S + ts - 1)/ts;
-    size_t tile_bytes = (size_t)ts*G*4;
+    size_t tile_bytes = (size_t)ts*G*es;
     const int64_t ring_cap = ctx->opt_ring_bytes_c[nals] ? ctx->opt_ring_bytes_c[nals] : ctx->opt_ring_bytes;
     int cap = (int)std::max<int64_t>(2, ring_cap/(int64_t)tile_bytes);
     int ns = std::min(MAX_STAGE, std::min(ntiles, cap));
@@ -345,6 +345,9 @@ static int enqueue(mcb_ctx *ctx, const mcb_batch *b, const mcb_result *r, int32_
     a.nsmpl = ctx->p.nsmpl; a.max_nals = ctx->p.max_nals; a.flag = ctx->p.flag; a.output_tags = ctx->p.output_tags;
     a.theta = ctx->theta_log; a.tie_eps = ctx->p.tie_eps; a.use_prior = ctx->p.use_prior;
     const bool ploidy = ctx->any_nondiploid;
+    const int pl_es = b->pl_type==2 ? 2 : 4;
+    if ( b->pl_type!=0 && b->pl_type!=4 && b->pl_type!=2 ) return MCB_EINVAL;
+    if ( ctx->ngroups > 1 && pl_es!=4 ) return MCB_EINVAL;        /* grouped calling takes int32 PLs only */
     if ( ctx->ngroups > 1 )         /* grouped calling (-G): the correctness-first kernel of mcall_groups.cu */
     {
         if ( !b->ad || !b->ad_off || !b->nad ) return MCB_EQS;      /* mcall.c:1476 */
@@ -397,17 +400,26 @@ static int enqueue(mcb_ctx *ctx, const mcb_batch *b, const mcb_result *r, int32_
     for (int nals=5; nals>=1; nals--)       /* the heavy, low-occupancy classes first */
     {
         if ( timing ) nals = 6 - nals;      /* timing mode keeps the ascending order of the event list */
-        size_t ring; tile_geometry(ctx, nals, &a.tile_smpl, &a.nstage, &ring);
-        const int block = class_block(ctx, nals);
+        size_t ring; tile_geometry(ctx, nals, pl_es, &a.tile_smpl, &a.nstage, &ring);
+        const int block = pl_es==2 ? 128 : class_block(ctx, nals);
         a.site_list = lists + (size_t)nals*list_stride; a.site_count = counts + nals;
         int nb = 1;
-        CK(site_kernel_occupancy(nals, ploidy, block, ring, &nb));
+        CK(site_kernel_occupancy(nals, ploidy, block, pl_es, ring, &nb));
         if ( nb<1 ) return cuda_fail(ctx, cudaErrorLaunchOutOfResources, "site kernel does not fit on an SM");
         if ( ctx->opt_blocks_per_sm>0 ) nb = std::min<int>(nb, (int)ctx->opt_blocks_per_sm);
         int grid = (int)std::min<int64_t>((int64_t)b->nsites, (int64_t)ctx->nsm*nb);
         cudaStream_t cs = fork ? ctx->cstream[nals] : st;
         if ( fork ) CK(cudaStreamWaitEvent(cs, ctx->cev_fork, 0));
-        CK(launch_site_kernel(nals, ploidy, block, a, grid, ring, cs));
+        {
+            cudaError_t le = launch_site_kernel(nals, ploidy, block, pl_es, a, grid, ring, cs);
+            if ( le==cudaSuccess && getenv("MCB_DEBUG_SYNC") ) le = cudaStreamSynchronize(cs);
+            if ( le!=cudaSuccess )
+            {
+                char what[160];
+                snprintf(what, sizeof what, "site kernel nals=%d block=%d pl_es=%d grid=%d ring=%zu tile_smpl=%d nstage=%d", nals, block, pl_es, grid, ring, a.tile_smpl, a.nstage);
+                return cuda_fail(ctx, le, what);
+            }
+        }
         launches++;
         if ( fork ) { CK(cudaEventRecord(ctx->cev_join[nals], cs)); CK(cudaStreamWaitEvent(st, ctx->cev_join[nals], 0)); }
         if ( timing ) { CK(cudaEventRecord(ctx->kev[nals], st)); nals = 6 - nals; }
@@ -449,12 +461,15 @@ extern "C" int mcb_call_host(mcb_ctx *ctx, const mcb_batch *b, const mcb_result 
     ctx->stats[0] = ctx->stats[1] = 0;
 
     /* per-site PL extents (host knows nals) and a monotonicity check: slabs copy one contiguous PL range */
+    if ( b->pl_type!=0 && b->pl_type!=4 && b->pl_type!=2 ) return MCB_EINVAL;
+    const int es = b->pl_type==2 ? 2 : 4;               /* bytes per input PL element */
+    const int64_t amask = 16/es - 1;                    /* sites start on 16-byte boundaries */
     std::vector<int64_t> ext(R);
     for (int i=0; i<R; i++)
     {
         int n = b->nals[i];
-        ext[i] = (( (int64_t)S*n*(n+1)/2 ) + 3) & ~(int64_t)3;
-        if ( (b->pl_off[i] & 3) || (i && b->pl_off[i] < b->pl_off[i-1] + ext[i-1]) ) return MCB_EINVAL;
+        ext[i] = (( (int64_t)S*n*(n+1)/2 ) + amask) & ~amask;
+        if ( (b->pl_off[i] & amask) || (i && b->pl_off[i] < b->pl_off[i-1] + ext[i-1]) ) return MCB_EINVAL;
     }
     const bool have_ad = ctx->ngroups>1 && b->ad && b->ad_off && b->nad;
     std::vector<int64_t> aext(have_ad ? R : 0);
@@ -475,7 +490,7 @@ extern "C" int mcb_call_host(mcb_ctx *ctx, const mcb_batch *b, const mcb_result 
     {
         /* slab = as many sites as fit opt_slab_bytes of PL */
         int end = beg; int64_t pl_ints = 0;
-        while ( end < R && (end==beg || (pl_ints + ext[end])*4 <= ctx->opt_slab_bytes) ) { pl_ints = b->pl_off[end] + ext[end] - b->pl_off[beg]; end++; }
+        while ( end < R && (end==beg || (pl_ints + ext[end])*es <= ctx->opt_slab_bytes) ) { pl_ints = b->pl_off[end] + ext[end] - b->pl_off[beg]; end++; }
         const int n = end - beg;
         HostSlab &sl = ctx->slab[islab & 1];
         CK(cudaEventSynchronize(sl.done));      /* previous use of this half finished (event starts signalled) */
@@ -483,7 +498,7 @@ extern "C" int mcb_call_host(mcb_ctx *ctx, const mcb_batch *b, const mcb_result 
         /* carve the arena */
         size_t off = 0;
         auto carve = [&](size_t bytes) { size_t o = off; off += pad256(bytes); return o; };
-        size_t o_pl = carve((size_t)pl_ints*4), o_plout = want_pl ? carve((size_t)pl_ints*4) : 0;
+        size_t o_pl = carve((size_t)pl_ints*es), o_plout = want_pl ? carve((size_t)pl_ints*4) : 0;
         size_t o_gp = want_gp ? carve((size_t)pl_ints*4) : 0;
         size_t o_ploff = carve(sizeof(int64_t)*n), o_nals = carve(n), o_unseen = carve(n), o_pid = carve(2*(size_t)n);
         size_t o_qs = carve(sizeof(float)*(size_t)n*M), o_nqs = carve(n);
@@ -510,7 +525,7 @@ extern "C" int mcb_call_host(mcb_ctx *ctx, const mcb_batch *b, const mcb_result 
         cudaStream_t st = sl.stream;
         const int64_t pl0 = b->pl_off[beg];
 #define H2D(dst,src,bytes) CK(cudaMemcpyAsync(base+(dst), (src), (bytes), cudaMemcpyHostToDevice, st))
-        H2D(o_pl, b->pl + pl0, (size_t)pl_ints*4);
+        H2D(o_pl, (const char*)b->pl + (size_t)pl0*es, (size_t)pl_ints*es);
         H2D(o_ploff, b->pl_off + beg, sizeof(int64_t)*n);
         H2D(o_nals, b->nals + beg, n);
         if ( b->unseen ) H2D(o_unseen, b->unseen + beg, n);
@@ -529,7 +544,8 @@ extern "C" int mcb_call_host(mcb_ctx *ctx, const mcb_batch *b, const mcb_result 
         /* device views: pl pointers are biased by -pl0 so that the absolute pl_off[] stay valid */
         mcb_batch db; memset(&db, 0, sizeof db);
         db.nsites = n;
-        db.pl = (const int32_t*)(base+o_pl) - pl0; db.pl_off = (const int64_t*)(base+o_ploff);
+        db.pl = (const int32_t*)((const char*)(base+o_pl) - (size_t)pl0*es); db.pl_off = (const int64_t*)(base+o_ploff);
+        db.pl_type = b->pl_type;
         db.nals = (const uint8_t*)(base+o_nals);
         db.unseen = b->unseen ? (const uint8_t*)(base+o_unseen) : nullptr;
         db.ploidy_id = b->ploidy_id ? (const uint16_t*)(base+o_pid) : nullptr;

@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(GBLOCK) mcall_groups_kernel(const KArgs a, Gro
     {
         const int site = a.site_list[isite];
         const int64_t site_off = a.pl_off[site];
-        const int32_t *site_pl = a.pl + site_off;
+        const int32_t *site_pl = reinterpret_cast<const int32_t*>(a.pl) + site_off;     /* int32 only in the grouped kernel */
         const int unseen = a.unseen ? a.unseen[site] : 0;
         int pid = a.ploidy_id ? a.ploidy_id[site] : 0;
         if ( pid >= a.nploidy ) pid = 0;

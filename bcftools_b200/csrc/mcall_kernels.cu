@@ -64,10 +64,12 @@ template<int NALS, int BLOCK> struct Shared
  *  because the filled values are what gets trimmed and output later.  Returns 0 when the sample has
  *  no data (all missing).
  * ---------------------------------------------------------------------------------------------- */
+template<typename PT>
 __device__ __noinline__ int fix_missing(uint32_t row_s, int nals, int unseen)
 {
+    using P = PLType<PT>;
     const int G = nals*(nals+1)/2;
-    auto PL = [&](int j) -> int { int v; asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(row_s + 4u*(uint32_t)j)); return v; };
+    auto PL = [&](int j) -> int { return P::widen(P::ld(row_s + (uint32_t)(P::ES*j))); };
     int j;
     for (j=0; j<G; j++)
     {
@@ -88,7 +90,7 @@ __device__ __noinline__ int fix_missing(uint32_t row_s, int nals, int unseen)
                 if ( PL(k)==I32_MISSING ) k = gt_idx(ib,unseen);
                 if ( PL(k)==I32_MISSING ) k = gt_idx(unseen,unseen);
                 const int w = PL(k)==I32_MISSING ? 255 : PL(k);
-                asm volatile("st.shared.s32 [%0], %1;" :: "r"(row_s + 4u*(uint32_t)j), "r"(w) : "memory");
+                P::st(row_s + (uint32_t)(P::ES*j), w);
             }
             else if ( v < 0 ) return 0;         /* vector_end behind a missing value: undefined in the reference */
             j++;
@@ -108,15 +110,17 @@ __device__ __noinline__ double big_pl_to_p(const DevTables *tab, int v, uint32_t
  *  one warp vote so that the common path is straight-line code; `fast` (warp-uniform) tells the caller that every
  *  valid lane has all PLs in 0..255.  Lanes with valid==false must pass the address of some readable row.
  *  Returns true when the lane's sample carries data.                                                          */
-template<int NALS>
+template<int NALS, typename PT>
 __device__ __forceinline__ bool load_sample_w(uint32_t row_s, uint32_t pl2p_s, bool valid, int unseen, const DevTables *tab,
                                               int (&pl)[Shape<NALS>::G], double (&p)[Shape<NALS>::G], double &sum, bool &fast, uint32_t &flags)
 {
     constexpr int G = Shape<NALS>::G;
     int orv = 0;
     #pragma unroll
-    for (int j=0; j<G; j++) { pl[j] = lds32(row_s + 4u*(uint32_t)j); orv |= pl[j]; }
-    const bool special = valid && (unsigned)orv > 255u;     /* negative (sentinels) or >= 256 */
+    for (int j=0; j<G; j++) { pl[j] = PLType<PT>::ld(row_s + (uint32_t)(PLType<PT>::ES*j)); orv |= pl[j]; }
+    /* negative (sentinels) or >= 256.  Lanes past the end of the tile re-read the last row: they must vote too, or an
+       all-idle warp would index the table with that row's sentinel. */
+    const bool special = (unsigned)orv > 255u;
     fast = !__any_sync(0xffffffffu, special);
     bool data = valid && orv!=0;            /* PL=0,..,0: sum==n_gt, no data (mcall.c:529-537) */
     if ( fast )
@@ -128,12 +132,12 @@ __device__ __forceinline__ bool load_sample_w(uint32_t row_s, uint32_t pl2p_s, b
     {
         if ( valid && orv<0 )
         {
-            data = fix_missing(row_s, NALS, unseen);
+            data = fix_missing<PT>(row_s, NALS, unseen);
             if ( data )
             {
                 orv = 0;
                 #pragma unroll
-                for (int j=0; j<G; j++) { pl[j] = lds32(row_s + 4u*(uint32_t)j); orv |= pl[j]; }
+                for (int j=0; j<G; j++) { pl[j] = PLType<PT>::widen(PLType<PT>::ld(row_s + (uint32_t)(PLType<PT>::ES*j))); orv |= pl[j]; }
                 data = orv>0;
             }
         }
@@ -168,9 +172,11 @@ template<int NALS, int BLOCK> struct MinBlocks
     static constexpr int value  = BLOCK==256 ? per256 : (NALS<=2 ? 2*MCB_MINB2 : (NALS==3 ? MCB_MINB3 : (NALS==4 ? MCB_MINB4 : MCB_MINB5)));
 };
 
-template<int NALS, bool PLOIDY, int BLOCK>
+template<int NALS, bool PLOIDY, int BLOCK, typename PT>
 __global__ void __launch_bounds__(BLOCK, (MinBlocks<NALS,BLOCK>::value)) mcall_site_kernel(const KArgs a)
 {
+    using PLT = PLType<PT>;
+    constexpr int ES = PLT::ES;                 /* bytes per PL element in the slab and in the tile ring */
     using S = Shape<NALS>;
     constexpr int G = S::G, NPAIR = S::NPAIR, NTRI = S::NTRI, NSUB = S::NSUB, NACC = S::NACC;
     constexpr int MAXSEL = S::MAXSEL, NSLOT = S::NSLOT, NW = BLOCK/32;
@@ -207,7 +213,7 @@ __global__ void __launch_bounds__(BLOCK, (MinBlocks<NALS,BLOCK>::value)) mcall_s
     {
         const int site = a.site_list[isite];
         const int64_t site_off = a.pl_off[site];
-        const int32_t *site_pl = a.pl + site_off;
+        const PT *site_pl = reinterpret_cast<const PT*>(a.pl) + site_off;
         const int unseen = a.unseen ? a.unseen[site] : 0;
         const uint8_t *ploidy = nullptr;
         if ( PLOIDY )
@@ -221,9 +227,9 @@ __global__ void __launch_bounds__(BLOCK, (MinBlocks<NALS,BLOCK>::value)) mcall_s
         {
             int t = v % ntiles, stage = v % nstage;
             int n = min(TS, nsmpl - t*TS);
-            uint32_t bytes = ((uint32_t)(n*G*4) + 15u) & ~15u;
+            uint32_t bytes = ((uint32_t)(n*G*ES) + 15u) & ~15u;
             mbar_expect_tx(bars_s + 8*stage, bytes);
-            bulk_g2s(ring_s + 4u*(uint32_t)(stage*tile_ints), site_pl + (size_t)t*tile_ints, bytes, bars_s + 8*stage);
+            bulk_g2s(ring_s + (uint32_t)(ES*stage*tile_ints), site_pl + (size_t)t*tile_ints, bytes, bars_s + 8*stage);
         };
         if ( tid==0 )
             for (int v=0; v<nstage && v<total_visits; v++) issue(v);
@@ -345,7 +351,7 @@ __global__ void __launch_bounds__(BLOCK, (MinBlocks<NALS,BLOCK>::value)) mcall_s
             const int stage = t % nstage;
             mbar_wait(bars_s + 8*stage, (phase_bits>>stage)&1u);
             phase_bits ^= 1u<<stage;
-            const uint32_t tile_s = ring_s + 4u*(uint32_t)(stage*tile_ints);
+            const uint32_t tile_s = ring_s + (uint32_t)(ES*stage*tile_ints);
             const int s0 = t*TS, n = min(TS, nsmpl - s0);
             /* pass 0: normalisers, single-allele sums, pairs (+ triples unless SPLIT); pass 1 (SPLIT): triples */
             #pragma unroll 1
@@ -358,7 +364,7 @@ __global__ void __launch_bounds__(BLOCK, (MinBlocks<NALS,BLOCK>::value)) mcall_s
                     const int s = min(sb + tid, n-1);
                     const bool valid = sb + tid < n;
                     int pl[G]; double p[G]; double sum; bool fast;
-                    if ( !load_sample_w<NALS>(tile_s + (uint32_t)(s*G*4), pl2p_s, valid, unseen, a.tab, pl, p, sum, fast, tflags) ) continue;
+                    if ( !load_sample_w<NALS,PT>(tile_s + (uint32_t)(s*G*ES), pl2p_s, valid, unseen, a.tab, pl, p, sum, fast, tflags) ) continue;
                     int pld = 2;
                     if ( PLOIDY ) pld = __ldg(ploidy + s0 + s);
                     if ( pass==0 )
@@ -657,7 +663,7 @@ __global__ void __launch_bounds__(BLOCK, (MinBlocks<NALS,BLOCK>::value)) mcall_s
                         {
                             int k = x*(x+1)/2 + y;
                             int ny = y<ns ? amap[sel[y]] : 0;
-                            c.jgt4[k] = (x<ns) ? 4*gt_idx(sel[x], sel[y]) : 0;
+                            c.jgt4[k] = (x<ns) ? ES*gt_idx(sel[x], sel[y]) : 0;
                             int ig = gt_idx(nx, ny);
                             c.igt[k] = ig;
                             if ( x<ns && ig < ngt_new ) c.inc_dip |= 1u<<k;
@@ -712,7 +718,7 @@ __global__ void __launch_bounds__(BLOCK, (MinBlocks<NALS,BLOCK>::value)) mcall_s
             constexpr int NPLM = G<6 ? G : 6;
             int plm4[NPLM];
             #pragma unroll
-            for (int k=0; k<NPLM; k++) plm4[k] = 4*sh.pl_map[k];
+            for (int k=0; k<NPLM; k++) plm4[k] = ES*sh.pl_map[k];
             const uint32_t oflags = (out_gt ? 1u : 0u) | (out_gq ? 2u : 0u) | (out_pl ? 4u : 0u) | (out_gp ? 8u : 0u);
             unsigned long long acc = 0;     /* AC: 12-bit counters, new allele j at bits [12j,12j+12) */
             int acc_n = 0;
@@ -742,7 +748,7 @@ __global__ void __launch_bounds__(BLOCK, (MinBlocks<NALS,BLOCK>::value)) mcall_s
                     mbar_wait(bars_s + 8*stage, (phase_bits>>stage)&1u);
                     phase_bits ^= 1u<<stage;
                 }
-                const uint32_t tile_s = ring_s + 4u*(uint32_t)(stage*tile_ints);
+                const uint32_t tile_s = ring_s + (uint32_t)(ES*stage*tile_ints);
                 const int s0 = t*TS, n = min(TS, nsmpl - s0);
                 if ( acc_n + (TS + BLOCK - 1)/BLOCK > 63 ) flush_ac();     /* uniform across the block: safe to shuffle */
                 acc_n += (TS + BLOCK - 1)/BLOCK;
@@ -752,8 +758,8 @@ __global__ void __launch_bounds__(BLOCK, (MinBlocks<NALS,BLOCK>::value)) mcall_s
                     const int s = min(sb + tid, n-1);
                     const bool valid = sb + tid < n;
                     int pl[G]; double p[G]; double sum = 1; bool fast;
-                    const uint32_t row_s = tile_s + (uint32_t)(s*G*4);
-                    const bool has = load_sample_w<NALS>(row_s, pl2p_s, valid, unseen, a.tab, pl, p, sum, fast, tflags2);
+                    const uint32_t row_s = tile_s + (uint32_t)(s*G*ES);
+                    const bool has = load_sample_w<NALS,PT>(row_s, pl2p_s, valid, unseen, a.tab, pl, p, sum, fast, tflags2);
                     const int pld = PLOIDY ? __ldg(ploidy + s0 + s) : 2;
                     int4 outc = make_int4(MCB_GT_MISSING, pld==2 ? MCB_GT_MISSING : I32_VEC_END, 0, 0);
                     int gq = 0;
@@ -776,7 +782,7 @@ __global__ void __launch_bounds__(BLOCK, (MinBlocks<NALS,BLOCK>::value)) mcall_s
                             else if ( NALS==2 ) pk = k==1 ? p[1] : (k==2 ? p[2] : (jgt4[0] ? p[2] : p[0]));
                             else
                             {
-                                const int v = lds32(row_s + (uint32_t)jgt4[k<NSLOT?k:0]);
+                                const int v = PLT::ld(row_s + (uint32_t)jgt4[k<NSLOT?k:0]);
                                 pk = (fast || v<256) ? lds64(pl2p_s + 8u*(uint32_t)(v & 255)) : big_pl_to_p(a.tab, v, &tflags2);
                             }
                             return fast ? div_shared(pk, sum, r) : __ddiv_rn(pk, sum);
@@ -892,13 +898,13 @@ __global__ void __launch_bounds__(BLOCK, (MinBlocks<NALS,BLOCK>::value)) mcall_s
                             int v0, v1 = I32_VEC_END, v2 = I32_VEC_END;
                             if ( pld==2 )
                             {
-                                v0 = lds32(row_s + (uint32_t)plm4[0]);
-                                if ( G>1 ) { v1 = lds32(row_s + (uint32_t)plm4[G>1?1:0]); v2 = lds32(row_s + (uint32_t)plm4[G>2?2:0]); }
+                                v0 = PLT::widen(PLT::ld(row_s + (uint32_t)plm4[0]));
+                                if ( G>1 ) { v1 = PLT::widen(PLT::ld(row_s + (uint32_t)plm4[G>1?1:0])); v2 = PLT::widen(PLT::ld(row_s + (uint32_t)plm4[G>2?2:0])); }
                             }
                             else if ( pld==1 )
                             {
-                                v0 = lds32(row_s + (uint32_t)plm4[0]);                             /* hom_idx(0) = 0 */
-                                if ( G>1 && nals_new>1 ) v1 = lds32(row_s + (uint32_t)plm4[G>2?2:0]);  /* hom_idx(1) = 2 */
+                                v0 = PLT::widen(PLT::ld(row_s + (uint32_t)plm4[0]));                   /* hom_idx(0) = 0 */
+                                if ( G>1 && nals_new>1 ) v1 = PLT::widen(PLT::ld(row_s + (uint32_t)plm4[G>2?2:0]));  /* hom_idx(1) = 2 */
                             }
                             else v0 = I32_MISSING;
                             asm volatile("st.global.s32 [%0], %1;" :: "l"(dst), "r"(v0) : "memory");
@@ -915,8 +921,8 @@ __global__ void __launch_bounds__(BLOCK, (MinBlocks<NALS,BLOCK>::value)) mcall_s
                             {
                                 if ( k>=ngt_new ) continue;
                                 int v;
-                                if ( pld==2 ) v = lds32(row_s + (uint32_t)(k<NPLM ? plm4[k<NPLM?k:0] : 4*sh.pl_map[k]));
-                                else if ( pld==1 ) v = k<nals_new ? lds32(row_s + 4u*(uint32_t)sh.pl_map[hom_idx(k)]) : I32_VEC_END;
+                                if ( pld==2 ) v = PLT::widen(PLT::ld(row_s + (uint32_t)(k<NPLM ? plm4[k<NPLM?k:0] : ES*sh.pl_map[k])));
+                                else if ( pld==1 ) v = k<nals_new ? PLT::widen(PLT::ld(row_s + (uint32_t)(ES*sh.pl_map[hom_idx(k)]))) : I32_VEC_END;
                                 else v = k==0 ? I32_MISSING : I32_VEC_END;
                                 asm volatile("st.global.s32 [%0], %1;" :: "l"(dst + k), "r"(v) : "memory");
                             }
@@ -1057,20 +1063,20 @@ __global__ void unsupported_sites_kernel(const int32_t *list, const int32_t *cou
     }
 }
 
-template<int NALS, bool PLOIDY, int BLOCK>
+template<int NALS, bool PLOIDY, int BLOCK, typename PT>
 static cudaError_t launch_one(const KArgs &a, int grid, size_t ring_bytes, cudaStream_t st)
 {
-    auto kern = mcall_site_kernel<NALS,PLOIDY,BLOCK>;
+    auto kern = mcall_site_kernel<NALS,PLOIDY,BLOCK,PT>;
     const size_t smem = align128(sizeof(Shared<NALS,BLOCK>)) + ring_bytes;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if ( e!=cudaSuccess ) return e;
     kern<<<grid, BLOCK, smem, st>>>(a);
     return cudaGetLastError();
 }
-template<int NALS, bool PLOIDY, int BLOCK>
+template<int NALS, bool PLOIDY, int BLOCK, typename PT>
 static cudaError_t occ_one(size_t ring_bytes, int *nb)
 {
-    auto kern = mcall_site_kernel<NALS,PLOIDY,BLOCK>;
+    auto kern = mcall_site_kernel<NALS,PLOIDY,BLOCK,PT>;
     const size_t smem = align128(sizeof(Shared<NALS,BLOCK>)) + ring_bytes;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if ( e!=cudaSuccess ) return e;
@@ -1078,33 +1084,40 @@ static cudaError_t occ_one(size_t ring_bytes, int *nb)
 }
 /*  one dispatcher for launch (nb==NULL) and occupancy query (nb!=NULL)  */
 template<int NALS>
-static cudaError_t dispatch(bool ploidy, int block, const KArgs *a, int grid, size_t ring_bytes, cudaStream_t st, int *nb)
+static cudaError_t dispatch(bool ploidy, int block, int pl_es, const KArgs *a, int grid, size_t ring_bytes, cudaStream_t st, int *nb)
 {
-#define MCB_CASE(P,B) return nb ? occ_one<NALS,P,B>(ring_bytes, nb) : launch_one<NALS,P,B>(*a, grid, ring_bytes, st)
-    if ( block==128 ) { if ( ploidy ) MCB_CASE(true,128); MCB_CASE(false,128); }
-    if ( block==256 ) { if ( ploidy ) MCB_CASE(true,256); MCB_CASE(false,256); }
+#define MCB_CASE(P,B,T) return nb ? occ_one<NALS,P,B,T>(ring_bytes, nb) : launch_one<NALS,P,B,T>(*a, grid, ring_bytes, st)
+    if ( pl_es==4 )
+    {
+        if ( block==128 ) { if ( ploidy ) MCB_CASE(true,128,int32_t); MCB_CASE(false,128,int32_t); }
+        if ( block==256 ) { if ( ploidy ) MCB_CASE(true,256,int32_t); MCB_CASE(false,256,int32_t); }
+    }
+    if ( pl_es==2 )         /* BCF int16 typed vectors: 128-thread CTAs only */
+    {
+        if ( ploidy ) MCB_CASE(true,128,int16_t); MCB_CASE(false,128,int16_t);
+    }
 #undef MCB_CASE
     return cudaErrorInvalidValue;
 }
-static cudaError_t dispatch_nals(int nals, bool ploidy, int block, const KArgs *a, int grid, size_t ring_bytes, cudaStream_t st, int *nb)
+static cudaError_t dispatch_nals(int nals, bool ploidy, int block, int pl_es, const KArgs *a, int grid, size_t ring_bytes, cudaStream_t st, int *nb)
 {
     switch ( nals )
     {
-        case 1: return dispatch<1>(ploidy, block, a, grid, ring_bytes, st, nb);
-        case 2: return dispatch<2>(ploidy, block, a, grid, ring_bytes, st, nb);
-        case 3: return dispatch<3>(ploidy, block, a, grid, ring_bytes, st, nb);
-        case 4: return dispatch<4>(ploidy, block, a, grid, ring_bytes, st, nb);
-        case 5: return dispatch<5>(ploidy, block, a, grid, ring_bytes, st, nb);
+        case 1: return dispatch<1>(ploidy, block, pl_es, a, grid, ring_bytes, st, nb);
+        case 2: return dispatch<2>(ploidy, block, pl_es, a, grid, ring_bytes, st, nb);
+        case 3: return dispatch<3>(ploidy, block, pl_es, a, grid, ring_bytes, st, nb);
+        case 4: return dispatch<4>(ploidy, block, pl_es, a, grid, ring_bytes, st, nb);
+        case 5: return dispatch<5>(ploidy, block, pl_es, a, grid, ring_bytes, st, nb);
     }
     return cudaErrorInvalidValue;
 }
-cudaError_t launch_site_kernel(int nals, bool ploidy, int block, const KArgs &a, int grid, size_t ring_bytes, cudaStream_t st)
+cudaError_t launch_site_kernel(int nals, bool ploidy, int block, int pl_es, const KArgs &a, int grid, size_t ring_bytes, cudaStream_t st)
 {
-    return dispatch_nals(nals, ploidy, block, &a, grid, ring_bytes, st, nullptr);
+    return dispatch_nals(nals, ploidy, block, pl_es, &a, grid, ring_bytes, st, nullptr);
 }
-cudaError_t site_kernel_occupancy(int nals, bool ploidy, int block, size_t ring_bytes, int *nb)
+cudaError_t site_kernel_occupancy(int nals, bool ploidy, int block, int pl_es, size_t ring_bytes, int *nb)
 {
-    return dispatch_nals(nals, ploidy, block, nullptr, 0, ring_bytes, nullptr, nb);
+    return dispatch_nals(nals, ploidy, block, pl_es, nullptr, 0, ring_bytes, nullptr, nb);
 }
 
 cudaError_t launch_classify(const uint8_t *nals, int nsites, int32_t *lists, int32_t *counts, int list_stride, cudaStream_t st)

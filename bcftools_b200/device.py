@@ -57,6 +57,7 @@ class DeviceBatch:
         for name in abi.BATCH_FIELDS:
             v = self.t.get(name)
             setattr(b, name, None if v is None else v.data_ptr())
+        b.pl_type = getattr(self.host, "pl_type", 0)
         return b
 
     def pl_bytes(self):

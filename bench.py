@@ -299,7 +299,24 @@ def main():
         d2h = sum(getattr(hres, k).nbytes for k in ("ret", "als_new", "als_map", "qual", "ac", "an", "site_flags", "diag", "gt", "gq", "pl_off_out")
                   if getattr(hres, k) is not None) + 4 * int(mc.stats()[2])        # + the used (compacted) part of the PL buffer
         e2e = dict(value=world * args.steps * ne * params.nsmpl / dt, unit=UNIT, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
-                   sites_per_step=ne, ms_per_step=1e3 * dt / args.steps)
+                   sites_per_step=ne, ms_per_step=1e3 * dt / args.steps, pl_transport="int32 (bcf_get_format_int32 layout)")
+        # secondary: the same call with the PL slab shipped as BCF int16 typed vectors (mcb_batch.pl_type=2)
+        sub16 = mcall.pin_batch(hb.subset(range(ne)).to_int16())
+        hres16 = mcall.pin_result(abi.HostResult(sub16, compact=True))
+        for _ in range(2):
+            mc.call_host(sub16, hres16)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            mc.call_host(sub16, hres16)
+        torch.cuda.synchronize()
+        dt16 = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt16], device=f"cuda:{local_rank}", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt16 = float(t.item())
+        e2e["int16_pl_transport"] = dict(value=world * args.steps * ne * params.nsmpl / dt16, h2d_bytes_per_step=int(sub16.pl.nbytes + h2d - sub.pl.nbytes),
+                                         ms_per_step=1e3 * dt16 / args.steps)
 
     # ---- max over ranks of the device time
     if world > 1:

@@ -107,6 +107,10 @@ typedef struct mcb_batch
     const uint8_t  *nad;        /* [nsites] values per sample in ad (mcall.c:1477) */
     const int32_t  *prior_an;   /* [nsites] -F: AN, <=0 or MCB_INT32_MISSING = absent (mcall.c:1507-1510) */
     const int32_t  *prior_ac;   /* [nsites][max_nals] -F: AC for ALT 1..A-1 in [0..A-2], MCB_INT32_VECTOR_END-terminated */
+    int32_t  pl_type;           /* element type of `pl`: 0 or 4 = int32 (bcf_get_format_int32), 2 = int16 = the BCF on-disk
+                                   typed vector (BCF_BT_INT16, sentinels INT16_MIN / INT16_MIN+1) shipped as is and widened
+                                   on the device.  pl_off stays in ELEMENTS; pl + pl_off[i] must be 16-byte aligned
+                                   (pl_off[i] % 8 == 0 for int16).  Outputs are int32 in either case. */
 }
 mcb_batch;
 

@@ -132,6 +132,52 @@ def test_full_size_properties_without_oracle():
         assert ((tp >= 0) | (tp == abi.INT32_MISSING) | (tp == abi.INT32_VECTOR_END)).all()
 
 
+@pytest.mark.parametrize("cfg,nsites,flag", [("C3", 200, 0), ("C2", 100, abi.CALL_VARONLY)])
+def test_int16_pl_transport(cfg, nsites, flag, oracle_built):
+    """mcb_batch.pl_type = 2: the BCF on-disk int16 typed vectors are shipped as they are and widened on the device
+    (SURVEY.md 8f N1); results must equal the int32 path bit for bit, including missing values and the PL fill."""
+    from bcftools_b200 import mcall
+    params, batch, tab = synth.make_batch(cfg, nsites, flag=flag)
+    exp, _ = oracle_built.call("port", params, batch, tab)
+    b16 = batch.to_int16()
+    with mcall.MCaller(params, ploidy_tab=tab) as mc:
+        got = mc.call_host(b16, compact=True)
+    st = parity.compare(got, exp, params)
+    assert st["compared"] > 0 and not st["near_ties"], st
+    rng = np.random.default_rng(5)
+    rb = parity.random_batch(rng, 120, 40, 5)
+    tabr = np.full((2, 40), 2, np.uint8)
+    tabr[1, ::3] = 1
+    tabr[1, 1::7] = 0
+    rb.ploidy_id = rng.integers(0, 2, rb.nsites).astype(np.uint16)
+    pr = abi.CallParams(40, 5, output_tags=abi.CALL_FMT_GQ)
+    expr, _ = oracle_built.call("port", pr, rb, tabr)
+    with mcall.MCaller(pr, ploidy_tab=tabr) as mc:
+        gotr = mc.call_host(rb.to_int16())
+    assert parity.compare(gotr, expr, pr)["compared"] > 0
+
+
+@pytest.mark.parametrize("int16", [False, True])
+def test_idle_warps_do_not_index_the_table_with_sentinels(int16, oracle_built):
+    """Regression: with 40 samples and 128-thread CTAs, warps 2-3 have no valid lane and re-read the last row; when that
+    row is a missing-value row its sentinel must not reach the pl2p table lookup (it faulted with int16 PLs and was
+    silently masked by 32-bit wrap-around with int32 PLs)."""
+    from bcftools_b200 import mcall
+    rng = np.random.default_rng(100)
+    rb = parity.random_batch(rng, 60, 40, 1, minA=1, miss=True)
+    for i in range(rb.nsites):                   # make the LAST row of every site a missing row
+        rb.site_pl(i)[-1, :] = abi.INT32_MISSING
+    rb.max_nals = 5
+    qs = np.zeros((rb.nsites, 5), np.float32)
+    qs[:, :rb.qs.shape[1]] = rb.qs
+    rb.qs = qs
+    pr = abi.CallParams(40, 5, output_tags=abi.CALL_FMT_GQ)
+    exp, _ = oracle_built.call("port", pr, rb, None)
+    with mcall.MCaller(pr) as mc:
+        got = mc.call_host(rb.to_int16() if int16 else rb)
+    assert parity.compare(got, exp, pr)["compared"] > 0
+
+
 def test_compacted_pl_output(oracle_built):
     """mcb_result.pl_off_out: trimmed PL blocks packed at the front of the output buffer (what leaves the device in
     the host path); content must be identical to the in-place layout, several slabs per call."""
