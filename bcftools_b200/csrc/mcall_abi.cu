@@ -47,10 +47,11 @@ struct mcb_ctx
     unsigned long long *d_cursor = nullptr;
     HostSlab slab[2];
     /* options */
-    int64_t opt_tile_bytes = 32768, opt_ring_bytes = 65536, opt_blocks_per_sm = 0, opt_slab_bytes = 64ll<<20, opt_block = 128;
+    int64_t opt_tile_bytes = 0, opt_ring_bytes = 0, opt_blocks_per_sm = 0, opt_slab_bytes = 64ll<<20, opt_block = 0;     /* 0 = automatic */
     int64_t opt_time_kernels = 0, opt_concurrent = 1;
     int64_t opt_ring_bytes_c[NCLASS] = {0,0,0,0,0,0};   /* per allele-count class override of ring_bytes (0 = opt_ring_bytes) */
     int64_t opt_block_c[NCLASS] = {0,0,0,0,0,0};        /* per class override of the CTA size */
+    int64_t opt_tile_bytes_c[NCLASS] = {0,0,0,0,0,0};   /* per class override of tile_bytes */
     cudaStream_t cstream[NCLASS] = {};   /* one stream per allele-count class: their persistent grids overlap */
     cudaEvent_t  cev_fork = nullptr, cev_join[NCLASS] = {};
     cudaEvent_t kev[NCLASS+1] = {};      /* events around the per-class launches (time_kernels=1) */
@@ -146,10 +147,11 @@ extern "C" int mcb_set_option(mcb_ctx *ctx, const char *key, int64_t value)
     else if ( !strncmp(key,"ring_bytes_",11) && key[11]>='1' && key[11]<='5' && !key[12] ) ctx->opt_ring_bytes_c[key[11]-'0'] = value;
     else if ( !strncmp(key,"block_",6) && key[6]>='1' && key[6]<='5' && !key[7] )
     {
-        if ( value!=0 && value!=128 && value!=256 ) return MCB_EINVAL;
+        if ( value!=0 && value!=32 && value!=64 && value!=128 && value!=256 ) return MCB_EINVAL;
         ctx->opt_block_c[key[6]-'0'] = value;
     }
-    else if ( !strcmp(key,"block") )         { if ( value!=128 && value!=256 ) return MCB_EINVAL; ctx->opt_block = value; }
+    else if ( !strcmp(key,"block") )         { if ( value!=0 && value!=32 && value!=64 && value!=128 && value!=256 ) return MCB_EINVAL; ctx->opt_block = value; }
+    else if ( !strncmp(key,"tile_bytes_",11) && key[11]>='1' && key[11]<='5' && !key[12] ) ctx->opt_tile_bytes_c[key[11]-'0'] = value;
     else return MCB_EINVAL;
     return MCB_OK;
 }
@@ -310,17 +312,42 @@ extern "C" int mcb_selftest_div(mcb_ctx *ctx, int mode, uint64_t n, uint64_t see
 }
 
 /* ---- launch geometry -------------------------------------------------------------------------------- */
-static int class_block(const mcb_ctx *ctx, int nals) { return (int)(ctx->opt_block_c[nals] ? ctx->opt_block_c[nals] : ctx->opt_block); }
+/*  CTA size, tile size and ring size per allele-count class.  Explicit options win; the defaults below are the best
+ *  settings of the sweeps in profiles/ (measured at 2,504 samples) plus smaller CTAs for small sample counts, where a
+ *  128-thread CTA would have mostly idle lanes.                                                                    */
+static int class_block(const mcb_ctx *ctx, int nals)
+{
+    if ( ctx->opt_block_c[nals] ) return (int)ctx->opt_block_c[nals];
+    if ( ctx->opt_block ) return (int)ctx->opt_block;
+    const int S = ctx->p.nsmpl;
+    int b = S<=192 ? 32 : (S<=768 ? 64 : 128);
+    if ( nals==4 && b>64 ) b = 64;
+    return b;
+}
+static int64_t class_tile_bytes(const mcb_ctx *ctx, int nals)
+{
+    if ( ctx->opt_tile_bytes_c[nals] ) return ctx->opt_tile_bytes_c[nals];
+    if ( ctx->opt_tile_bytes ) return ctx->opt_tile_bytes;
+    return nals==3 ? 16384 : (nals==4 ? 8192 : 32768);
+}
+static int64_t class_ring_bytes(const mcb_ctx *ctx, int nals)
+{
+    if ( ctx->opt_ring_bytes_c[nals] ) return ctx->opt_ring_bytes_c[nals];
+    if ( ctx->opt_ring_bytes ) return ctx->opt_ring_bytes;
+    return (nals==3 || nals==4) ? 16384 : 65536;
+}
 
 static void tile_geometry(const mcb_ctx *ctx, int nals, int es, int *tile_smpl, int *nstage, size_t *ring_bytes)
 {
     int G = nals*(nals+1)/2, S = ctx->p.nsmpl;
-    int ts = (int)(ctx->opt_tile_bytes/(es*G));
+    const int64_t tile_target = class_tile_bytes(ctx, nals);
+    int ts = (int)(tile_target/(es*G));
     ts = std::max(256, ts/256*256);
     ts = std::min(ts, 32*class_block(ctx, nals));      /* the AC counters of phase 2 allow at most 63 samples per thread and tile */
+    ts = std::max(ts, class_block(ctx, nals));      /* the AC counters of phase 2 allow at most 63 samples per thread and tile */
     int ntiles = (S + ts - 1)/ts;
     size_t tile_bytes = (size_t)ts*G*es;
-    const int64_t ring_cap = ctx->opt_ring_bytes_c[nals] ? ctx->opt_ring_bytes_c[nals] : ctx->opt_ring_bytes;
+    const int64_t ring_cap = class_ring_bytes(ctx, nals);
     int cap = (int)std::max<int64_t>(2, ring_cap/(int64_t)tile_bytes);
     int ns = std::min(MAX_STAGE, std::min(ntiles, cap));
     if ( ns<1 ) ns = 1;

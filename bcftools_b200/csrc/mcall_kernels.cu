@@ -169,7 +169,8 @@ template<int NALS, int BLOCK> struct MinBlocks
 #ifndef MCB_MINB5
 #define MCB_MINB5 3
 #endif
-    static constexpr int value  = BLOCK==256 ? per256 : (NALS<=2 ? 2*MCB_MINB2 : (NALS==3 ? MCB_MINB3 : (NALS==4 ? MCB_MINB4 : MCB_MINB5)));
+    static constexpr int per128 = NALS<=2 ? 2*MCB_MINB2 : (NALS==3 ? MCB_MINB3 : (NALS==4 ? MCB_MINB4 : MCB_MINB5));
+    static constexpr int value  = BLOCK==256 ? per256 : (BLOCK==128 ? per128 : (BLOCK==64 ? (2*per128 > 32 ? 32 : 2*per128) : (4*per128 > 32 ? 32 : 4*per128)));
 };
 
 template<int NALS, bool PLOIDY, int BLOCK, typename PT>
@@ -1089,6 +1090,8 @@ static cudaError_t dispatch(bool ploidy, int block, int pl_es, const KArgs *a, i
 #define MCB_CASE(P,B,T) return nb ? occ_one<NALS,P,B,T>(ring_bytes, nb) : launch_one<NALS,P,B,T>(*a, grid, ring_bytes, st)
     if ( pl_es==4 )
     {
+        if ( block==32 )  { if ( ploidy ) MCB_CASE(true,32,int32_t);  MCB_CASE(false,32,int32_t); }
+        if ( block==64 )  { if ( ploidy ) MCB_CASE(true,64,int32_t);  MCB_CASE(false,64,int32_t); }
         if ( block==128 ) { if ( ploidy ) MCB_CASE(true,128,int32_t); MCB_CASE(false,128,int32_t); }
         if ( block==256 ) { if ( ploidy ) MCB_CASE(true,256,int32_t); MCB_CASE(false,256,int32_t); }
     }

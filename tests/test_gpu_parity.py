@@ -8,7 +8,7 @@ from tests import parity
 pytestmark = pytest.mark.gpu
 
 
-BLOCKS = (256, 128)
+BLOCKS = (0, 256, 128, 64, 32)      # 0 = the automatic per-class choice
 
 
 def _run(params, batch, tab, oracle_built, options=None, kind="port"):
