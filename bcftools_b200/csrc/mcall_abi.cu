@@ -48,7 +48,7 @@ struct mcb_ctx
     HostSlab slab[2];
     /* options */
     int64_t opt_tile_bytes = 0, opt_ring_bytes = 0, opt_blocks_per_sm = 0, opt_slab_bytes = 64ll<<20, opt_block = 0;     /* 0 = automatic */
-    int64_t opt_time_kernels = 0, opt_concurrent = 1;
+    int64_t opt_time_kernels = 0, opt_concurrent = 0;    /* concurrent class streams measured SLOWER than serial launches */
     int64_t opt_ring_bytes_c[NCLASS] = {0,0,0,0,0,0};   /* per allele-count class override of ring_bytes (0 = opt_ring_bytes) */
     int64_t opt_block_c[NCLASS] = {0,0,0,0,0,0};        /* per class override of the CTA size */
     int64_t opt_tile_bytes_c[NCLASS] = {0,0,0,0,0,0};   /* per class override of tile_bytes */

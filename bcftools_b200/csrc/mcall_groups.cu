@@ -82,7 +82,9 @@ __global__ void __launch_bounds__(GBLOCK) mcall_groups_kernel(const KArgs a, Gro
     __shared__ double s_pl2p[256];
     __shared__ double s_thr[130];
     __shared__ double s_p[GNW][16];
-    __shared__ int    s_pl[GNW][16];
+    __shared__ int    s_chunk[GNW][32][16];     /* PL rows of 32 samples of the group, fetched together: one global round trip per 32 samples */
+    __shared__ float  s_adc[GNW][32][5];        /* per-sample AD fractions of the chunk */
+    __shared__ unsigned char s_pld[GNW][32];
     __shared__ GSite  st;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -114,22 +116,41 @@ __global__ void __launch_bounds__(GBLOCK) mcall_groups_kernel(const KArgs a, Gro
             const int beg = a.grp_off[g], end = a.grp_off[g+1];
             /* ---- quality sums from FORMAT/AD: float32, sequential over the group's samples (mcall.c:1484-1501) */
             float qa = 0;
-            if ( lane<NALS && site_ad )
-                for (int i=beg; i<beg+(end-beg); i++)
+            if ( site_ad )
+                for (int base=beg; base<end; base+=32)
                 {
-                    const int32_t *ptr = site_ad + (size_t)a.grp_smpl[i]*nad;
-                    float sum = 0; int e = nad;
-                    for (int j=0; j<nad; j++)
+                    /* every lane: the fractions AD[a]/sum of ONE sample (independent per sample) ... */
+                    const int i = base + lane;
+                    float frac[5] = {0,0,0,0,0};
+                    if ( i<end )
                     {
-                        const int v = ptr[j];
-                        if ( v==I32_VEC_END ) { e = j; break; }
-                        if ( v!=I32_MISSING ) sum = __fadd_rn(sum, (float)v);
+                        const int32_t *ptr = site_ad + (size_t)a.grp_smpl[i]*nad;
+                        int adv[5]; float sum = 0; int e = nad<5 ? nad : 5;
+                        #pragma unroll
+                        for (int j=0; j<5; j++) adv[j] = j<nad ? ptr[j] : I32_VEC_END;
+                        #pragma unroll
+                        for (int j=0; j<5; j++)
+                        {
+                            if ( j>=e ) break;
+                            if ( adv[j]==I32_VEC_END ) { e = j; break; }
+                            if ( adv[j]!=I32_MISSING ) sum = __fadd_rn(sum, (float)adv[j]);
+                        }
+                        if ( sum!=0 )
+                        {
+                            #pragma unroll
+                            for (int j=0; j<5; j++) if ( j<e && adv[j]!=I32_MISSING ) frac[j] = __fdiv_rn((float)adv[j], sum);
+                        }
                     }
-                    if ( sum!=0 && lane<e )
+                    #pragma unroll
+                    for (int j=0; j<5; j++) s_adc[warp][lane][j] = frac[j];
+                    __syncwarp();
+                    /* ... lane a: the float32 running sum in group order (adding +0 for non-contributing samples is exact) */
+                    if ( lane<NALS )
                     {
-                        const int v = ptr[lane];
-                        if ( v!=I32_MISSING ) qa = __fadd_rn(qa, __fdiv_rn((float)v, sum));
+                        const int n = min(32, end-base);
+                        for (int k=0; k<n; k++) qa = __fadd_rn(qa, s_adc[warp][k][lane]);
                     }
+                    __syncwarp();
                 }
             float qf[NALS];
             #pragma unroll
@@ -219,54 +240,67 @@ __global__ void __launch_bounds__(GBLOCK) mcall_groups_kernel(const KArgs a, Gro
             /* ---- walk the group's samples; lane k accumulates prod val_s and prod sum_s of ITS set */
             double M = 1, MN = 1; int E = 0, EN = 0, cnt = 0, since = 0;
             uint32_t wflags = 0;
-            for (int i=beg; i<end; i++)
+            for (int base=beg; base<end; base+=32)
             {
-                const int s = a.grp_smpl[i];
-                int v = lane<G ? site_pl[(size_t)s*G + lane] : 0;
-                bool data = true;
-                if ( __any_sync(0xffffffffu, v<0) )
                 {
-                    if ( lane<G ) s_pl[warp][lane] = v;
-                    __syncwarp();
-                    int ok = 0;
-                    if ( lane==0 ) ok = fix_missing_local(s_pl[warp], NALS, unseen);
-                    ok = __shfl_sync(0xffffffffu, ok, 0);
-                    __syncwarp();
-                    if ( lane<G ) v = s_pl[warp][lane];
-                    data = ok && !__any_sync(0xffffffffu, v<0);
-                    __syncwarp();
+                    const int i = base + lane;
+                    if ( i<end )
+                    {
+                        const int s = a.grp_smpl[i];
+                        #pragma unroll
+                        for (int j=0; j<G; j++) s_chunk[warp][lane][j] = site_pl[(size_t)s*G + j];
+                        s_pld[warp][lane] = ploidy[s];
+                    }
                 }
-                if ( !__any_sync(0xffffffffu, v!=0) ) data = false;      /* PL=0,..,0: no data (mcall.c:529-537) */
-                if ( !data ) continue;
-                if ( lane<G ) s_p[warp][lane] = pl_to_p_dev(s_pl2p, a.tab, v, &wflags);
                 __syncwarp();
-                double sum = s_p[warp][0];
-                #pragma unroll
-                for (int j=1; j<G; j++) sum = __dadd_rn(sum, s_p[warp][j]);
-                const int pld = ploidy[s];
-                if ( live && lane<NSUB )
+                const int nchunk = min(32, end-base);
+                for (int k=0; k<nchunk; k++)
                 {
-                    double val = 0; bool use = false;
-                    if ( single ) { val = s_p[warp][tix[0]]; use = true; }     /* every sample, also ploidy 0 (mcall.c:607-611) */
-                    else if ( pld==2 )
+                    int *row = s_chunk[warp][k];
+                    int v = lane<G ? row[lane] : 0;
+                    bool data = true;
+                    if ( __any_sync(0xffffffffu, v<0) )
                     {
-                        val = cd[0]*s_p[warp][tix[0]];
-                        val = fma(cd[1], s_p[warp][tix[1]], val);
-                        if ( sc>=0 ) val = fma(cd[2], s_p[warp][tix[2]], val);
-                        val = fma(cd[3], s_p[warp][tix[3]], val);
-                        if ( sc>=0 ) { val = fma(cd[4], s_p[warp][tix[4]], val); val = fma(cd[5], s_p[warp][tix[5]], val); }
-                        use = true;
+                        int ok = 0;
+                        if ( lane==0 ) ok = fix_missing_local(row, NALS, unseen);
+                        ok = __shfl_sync(0xffffffffu, ok, 0);
+                        __syncwarp();
+                        if ( lane<G ) v = row[lane];
+                        data = ok && !__any_sync(0xffffffffu, v<0);
                     }
-                    else if ( pld==1 )
+                    if ( !__any_sync(0xffffffffu, v!=0) ) data = false;      /* PL=0,..,0: no data (mcall.c:529-537) */
+                    if ( !data ) continue;
+                    if ( lane<G ) s_p[warp][lane] = pl_to_p_dev(s_pl2p, a.tab, v, &wflags);
+                    __syncwarp();
+                    double sum = s_p[warp][0];
+                    #pragma unroll
+                    for (int j=1; j<G; j++) sum = __dadd_rn(sum, s_p[warp][j]);
+                    const int pld = s_pld[warp][k];
+                    if ( live && lane<NSUB )
                     {
-                        val = ch[0]*s_p[warp][tix[0]];
-                        val = fma(ch[1], s_p[warp][tix[1]], val);
-                        if ( sc>=0 ) val = fma(ch[2], s_p[warp][tix[2]], val);
-                        use = true;
+                        double val = 0; bool use = false;
+                        if ( single ) { val = s_p[warp][tix[0]]; use = true; }     /* every sample, also ploidy 0 (mcall.c:607-611) */
+                        else if ( pld==2 )
+                        {
+                            val = cd[0]*s_p[warp][tix[0]];
+                            val = fma(cd[1], s_p[warp][tix[1]], val);
+                            if ( sc>=0 ) val = fma(cd[2], s_p[warp][tix[2]], val);
+                            val = fma(cd[3], s_p[warp][tix[3]], val);
+                            if ( sc>=0 ) { val = fma(cd[4], s_p[warp][tix[4]], val); val = fma(cd[5], s_p[warp][tix[5]], val); }
+                            use = true;
+                        }
+                        else if ( pld==1 )
+                        {
+                            val = ch[0]*s_p[warp][tix[0]];
+                            val = fma(ch[1], s_p[warp][tix[1]], val);
+                            if ( sc>=0 ) val = fma(ch[2], s_p[warp][tix[2]], val);
+                            use = true;
+                        }
+                        if ( use && val!=0 ) { acc_mul(M, E, val); acc_mul(MN, EN, sum); cnt++; }
                     }
-                    if ( use && val!=0 ) { acc_mul(M, E, val); acc_mul(MN, EN, sum); cnt++; }
+                    if ( ++since >= 256 ) { acc_renorm(M, E); acc_renorm(MN, EN); since = 0; }
+                    __syncwarp();
                 }
-                if ( ++since >= 256 ) { acc_renorm(M, E); acc_renorm(MN, EN); since = 0; }
                 __syncwarp();
             }
             /* ---- set totals and the group's best set (same epilogue as the pooled kernel) */

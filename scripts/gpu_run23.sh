@@ -1,0 +1,7 @@
+set -x
+cd $GRAFT_REPO_ROOT
+mkdir -p gpurun_out; rm -f gpurun_out/quick23.log
+timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -5 | tee gpurun_out/pytest_gpu.log
+Q="python scripts/quick_bench.py --iters 5"
+$Q --config C5 --sites 2048 --rep 2 --groups 5 2>&1 | tail -1 | tee -a gpurun_out/quick23.log
+$Q --config C3 --sites 16384 --rep 4 2>&1 | tail -1 | tee -a gpurun_out/quick23.log

@@ -13,13 +13,14 @@ ap.add_argument("--iters", type=int, default=10)
 ap.add_argument("--opt", action="append", default=[])
 ap.add_argument("--tags", type=int, default=abi.CALL_FMT_GQ)
 ap.add_argument("--flag", type=int, default=0)
+ap.add_argument("--groups", type=int, default=0, help="-G groups (0 = pooled)")
 ap.add_argument("--check", action="store_true")
 ap.add_argument("--classes", action="store_true", help="also print the device ms per allele-count class (serialised)")
 ap.add_argument("--block", type=int, default=0)
 args = ap.parse_args()
 
 t0 = time.time()
-params, hb, tab = synth.make_batch(args.config, args.sites, flag=args.flag, output_tags=args.tags, with_groups=0)
+params, hb, tab = synth.make_batch(args.config, args.sites, flag=args.flag, output_tags=args.tags, with_groups=args.groups)
 print("generated", args.config, hb.nsites, "sites in %.1fs" % (time.time() - t0), flush=True)
 opts = {k: int(v) for k, v in (o.split("=") for o in args.opt)}
 if args.block: opts["block"] = args.block
