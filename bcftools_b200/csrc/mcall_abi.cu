@@ -42,6 +42,7 @@ struct mcb_ctx
     std::vector<uint8_t> h_ploidy;
     uint32_t *d_grp_off = nullptr, *d_grp_smpl = nullptr, *d_smpl2grp = nullptr;  int ngroups = 1;
     void *d_grp_scratch = nullptr;  size_t grp_scratch_bytes = 0;
+    void *d_gen_grp = nullptr, *d_gen_pl = nullptr, *d_gen_sum = nullptr;  int gen_grid = 0;    /* generic (6..32 allele) kernel scratch */
     /* device-path scratch */
     int32_t *d_lists = nullptr, *d_counts = nullptr;  int list_cap = 0;
     unsigned long long *d_cursor = nullptr;
@@ -239,7 +240,7 @@ extern "C" void mcb_destroy(mcb_ctx *ctx)
 {
     if ( !ctx ) return;
     cudaSetDevice(ctx->device);
-    cudaFree(ctx->d_tab); cudaFree(ctx->d_ploidy); cudaFree(ctx->d_grp_off); cudaFree(ctx->d_grp_smpl); cudaFree(ctx->d_smpl2grp); cudaFree(ctx->d_grp_scratch);
+    cudaFree(ctx->d_tab); cudaFree(ctx->d_ploidy); cudaFree(ctx->d_grp_off); cudaFree(ctx->d_grp_smpl); cudaFree(ctx->d_smpl2grp); cudaFree(ctx->d_grp_scratch); cudaFree(ctx->d_gen_grp); cudaFree(ctx->d_gen_pl); cudaFree(ctx->d_gen_sum);
     cudaFree(ctx->d_lists); cudaFree(ctx->d_counts); cudaFree(ctx->d_cursor);
     for (int i=0; i<2; i++)
     {
@@ -354,6 +355,30 @@ static void tile_geometry(const mcb_ctx *ctx, int nals, int es, int *tile_smpl, 
     *tile_smpl = ts; *nstage = ns; *ring_bytes = tile_bytes*ns;
 }
 
+/*  Sites with 0 or more than 5 alleles (class 0).  With max_nals <= 5 they cannot be legal input and are reported
+ *  unsupported; otherwise the generic kernel of mcall_generic.cu handles 6..32 alleles (int32 PLs).            */
+static int enqueue_class0(mcb_ctx *ctx, KArgs &a, const mcb_batch *b, const mcb_result *r, int32_t *lists, int32_t *counts, int pl_es, cudaStream_t st)
+{
+    if ( ctx->p.max_nals <= 5 || pl_es != 4 )
+    {
+        CK(launch_unsupported(lists, counts, r->ret, r->site_flags, b->nals, st));
+        return MCB_OK;
+    }
+    if ( !ctx->gen_grid )
+    {
+        size_t g1, g2, g3;
+        generic_scratch_bytes(1, ctx->ngroups, ctx->p.nsmpl, &g1, &g2, &g3);
+        int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ctx->nsm, (int64_t)(768ll<<20)/(int64_t)(g1+g2+g3)));
+        generic_scratch_bytes(grid, ctx->ngroups, ctx->p.nsmpl, &g1, &g2, &g3);
+        CK(cudaMalloc(&ctx->d_gen_grp, g1)); CK(cudaMalloc(&ctx->d_gen_pl, g2)); CK(cudaMalloc(&ctx->d_gen_sum, g3));
+        ctx->gen_grid = grid;
+    }
+    a.site_list = lists; a.site_count = counts;
+    a.grp_off = ctx->d_grp_off; a.grp_smpl = ctx->d_grp_smpl; a.smpl2grp = ctx->d_smpl2grp; a.ngroups = ctx->ngroups;
+    CK(launch_generic_kernel(a, ctx->d_gen_grp, ctx->d_gen_pl, ctx->d_gen_sum, std::min(ctx->gen_grid, std::max(1, b->nsites)), st));
+    return MCB_OK;
+}
+
 static int enqueue(mcb_ctx *ctx, const mcb_batch *b, const mcb_result *r, int32_t *lists, int32_t *counts, int list_stride, unsigned long long *cursor, cudaStream_t st)
 {
     CK(cudaMemsetAsync(counts, 0, sizeof(int32_t)*NCLASS, st));
@@ -396,7 +421,7 @@ static int enqueue(mcb_ctx *ctx, const mcb_batch *b, const mcb_result *r, int32_
             CK(launch_groups_kernel(nals, a, ctx->d_grp_scratch, grid, st));
             launches++;
         }
-        CK(launch_unsupported(lists, counts, r->ret, r->site_flags, b->nals, st));
+        { int rc0 = enqueue_class0(ctx, a, b, r, lists, counts, pl_es, st); if ( rc0 ) return rc0; }
         ctx->stats[0] += launches + 1;
         ctx->stats[1] += b->nsites;
         ctx->kev_valid = false;
@@ -452,7 +477,7 @@ static int enqueue(mcb_ctx *ctx, const mcb_batch *b, const mcb_result *r, int32_
         if ( timing ) { CK(cudaEventRecord(ctx->kev[nals], st)); nals = 6 - nals; }
     }
     ctx->kev_valid = timing;
-    CK(launch_unsupported(lists, counts, r->ret, r->site_flags, b->nals, st));
+    { int rc0 = enqueue_class0(ctx, a, b, r, lists, counts, pl_es, st); if ( rc0 ) return rc0; }
     launches++;
     ctx->stats[0] += launches;
     ctx->stats[1] += b->nsites;

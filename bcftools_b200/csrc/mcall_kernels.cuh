@@ -73,5 +73,7 @@ cudaError_t launch_unsupported(const int32_t *list, const int32_t *count, int32_
 cudaError_t site_kernel_occupancy(int nals, bool ploidy, int block, int pl_es, size_t ring_bytes, int *blocks_per_sm);
 size_t groups_scratch_bytes(int grid, int ngroups);
 cudaError_t launch_groups_kernel(int nals, const KArgs &a, void *scratch, int grid, cudaStream_t st);
+void generic_scratch_bytes(int grid, int ngroups, int nsmpl, size_t *grp, size_t *pl, size_t *sum);
+cudaError_t launch_generic_kernel(const KArgs &a, void *grp_scratch, void *pl_scratch, void *sum_scratch, int grid, cudaStream_t st);
 cudaError_t launch_selftest_div(const DevTables *tab, int mode, unsigned long long n, unsigned long long seed, unsigned long long *mismatch, cudaStream_t st);
 }

@@ -87,6 +87,24 @@ def test_sample_groups(S, maxA, mode, flag, oracle_built):
     assert st["compared"] > 0, st
 
 
+@pytest.mark.parametrize("S,maxA,groups,flag,tags", [(12, 8, None, 0, abi.CALL_FMT_GQ), (40, 7, None, abi.CALL_VARONLY, abi.CALL_FMT_GQ | abi.CALL_FMT_GP),
+                                                     (25, 9, 3, abi.CALL_KEEPALT, abi.CALL_FMT_GQ), (6, 32, None, 0, abi.CALL_FMT_GQ),
+                                                     (150, 6, None, 0, abi.CALL_FMT_GQ)])
+def test_more_than_five_alleles(S, maxA, groups, flag, tags, oracle_built):
+    """6..32 alleles (the reference accepts up to 32, mcall.c:1539-1543): the generic kernel of mcall_generic.cu,
+    mixed in one batch with sites of 1..5 alleles that go through the templated kernels."""
+    rng = np.random.default_rng([S, maxA, 3])
+    batch = parity.random_batch(rng, 40 if maxA > 16 else 90, S, maxA, zq=not (tags & abi.CALL_FMT_GP))
+    g = None if groups is None else [list(range(k, S, groups)) for k in range(groups)]
+    tab = np.full((2, S), 2, np.uint8)
+    tab[1, ::3] = 1
+    tab[1, 1::7] = 0
+    batch.ploidy_id = rng.integers(0, 2, batch.nsites).astype(np.uint16)
+    params = abi.CallParams(S, maxA, flag=flag, output_tags=tags, groups=g)
+    st = _run(params, batch, tab, oracle_built)
+    assert st["compared"] > 0 and (batch.nals > 5).sum() > 0, st
+
+
 def test_streaming_ring_matches_resident(oracle_built):
     """Small tiles force the streaming (two TMA passes) path; results must not depend on the tiling."""
     params, batch, tab = synth.make_batch("C3", 64)
