@@ -19,6 +19,7 @@ namespace mcb {
 
 #define GBLOCK 128
 #define GNW    (GBLOCK/32)
+#define BIG_GROUP 64        /* groups of at least this many samples are reduced by the whole CTA, sample-parallel */
 
 struct GroupRec
 {
@@ -85,6 +86,15 @@ __global__ void __launch_bounds__(GBLOCK) mcall_groups_kernel(const KArgs a, Gro
     __shared__ int    s_chunk[GNW][32][16];     /* PL rows of 32 samples of the group, fetched together: one global round trip per 32 samples */
     __shared__ float  s_adc[GNW][32][5];        /* per-sample AD fractions of the chunk */
     __shared__ unsigned char s_pld[GNW][32];
+    /* block-wide path for big groups (>= BIG_GROUP samples): same data flow as phase 1 of the pooled kernel */
+    constexpr int NTRI = S::NTRI, NACC = S::NACC;
+    __shared__ float  s_qf[NALS];
+    __shared__ double s_cfp[(NPAIR ? NPAIR : 1)*5], s_cft[(NTRI ? NTRI : 1)*9];
+    __shared__ uint32_t s_live;
+    __shared__ double s_redM[GNW][NACC];
+    __shared__ int    s_redE[GNW][NACC];
+    __shared__ long long s_redP[GNW][NALS];
+    __shared__ int    s_redC[GNW][2];
     __shared__ GSite  st;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -114,6 +124,7 @@ __global__ void __launch_bounds__(GBLOCK) mcall_groups_kernel(const KArgs a, Gro
         for (int g=warp; g<ngrp; g+=GNW)
         {
             const int beg = a.grp_off[g], end = a.grp_off[g+1];
+            if ( end-beg >= BIG_GROUP ) continue;       /* handled by the whole CTA below */
             /* ---- quality sums from FORMAT/AD: float32, sequential over the group's samples (mcall.c:1484-1501) */
             float qa = 0;
             if ( site_ad )
@@ -350,6 +361,364 @@ __global__ void __launch_bounds__(GBLOCK) mcall_groups_kernel(const KArgs a, Gro
         }
         __threadfence_block();
         __syncthreads();
+        /* =========================== phase A, big groups: the whole CTA, one lane per SAMPLE =========== */
+        for (int g=0; g<ngrp; g++)
+        {
+            const int beg = a.grp_off[g], end = a.grp_off[g+1], ng = end-beg;
+            if ( ng < BIG_GROUP ) continue;
+            if ( warp==0 )
+            {
+                /* quality sums (float32, group order), -F prior, normalisation: as in the warp path above */
+                float qa = 0;
+                if ( site_ad )
+                    for (int base=beg; base<end; base+=32)
+                    {
+                        const int i = base + lane;
+                        float frac[5] = {0,0,0,0,0};
+                        if ( i<end )
+                        {
+                            const int32_t *ptr = site_ad + (size_t)a.grp_smpl[i]*nad;
+                            int adv[5]; float sum = 0; int e = nad<5 ? nad : 5;
+                            #pragma unroll
+                            for (int j=0; j<5; j++) adv[j] = j<nad ? ptr[j] : I32_VEC_END;
+                            #pragma unroll
+                            for (int j=0; j<5; j++)
+                            {
+                                if ( j>=e ) break;
+                                if ( adv[j]==I32_VEC_END ) { e = j; break; }
+                                if ( adv[j]!=I32_MISSING ) sum = __fadd_rn(sum, (float)adv[j]);
+                            }
+                            if ( sum!=0 )
+                            {
+                                #pragma unroll
+                                for (int j=0; j<5; j++) if ( j<e && adv[j]!=I32_MISSING ) frac[j] = __fdiv_rn((float)adv[j], sum);
+                            }
+                        }
+                        #pragma unroll
+                        for (int j=0; j<5; j++) s_adc[0][lane][j] = frac[j];
+                        __syncwarp();
+                        if ( lane<NALS )
+                        {
+                            const int n = min(32, end-base);
+                            for (int k=0; k<n; k++) qa = __fadd_rn(qa, s_adc[0][k][lane]);
+                        }
+                        __syncwarp();
+                    }
+                float qf[NALS];
+                #pragma unroll
+                for (int j=0; j<NALS; j++) qf[j] = __shfl_sync(0xffffffffu, qa, j);
+                if ( a.use_prior && a.prior_an && a.prior_ac )
+                {
+                    const int an = a.prior_an[site];
+                    if ( an!=I32_MISSING && an>0 )
+                    {
+                        const int32_t *pac = a.prior_ac + (size_t)site*a.max_nals;
+                        const double den = __dadd_rn((double)(uint32_t)ng, __dmul_rn(0.5,(double)an));
+                        int ac0 = an;
+                        for (int j=0; j<NALS-1; j++)
+                        {
+                            if ( pac[j]==I32_VEC_END ) break;
+                            if ( pac[j]==I32_MISSING ) continue;
+                            ac0 -= pac[j];
+                            qf[j+1] = (float)__ddiv_rn(__dadd_rn((double)qf[j+1], __dmul_rn(0.5,(double)pac[j])), den);
+                        }
+                        if ( ac0<0 && lane==0 ) atomicOr(&st.flags, MCB_SITE_BAD_PRIOR);
+                        qf[0] = (float)__ddiv_rn(__dadd_rn((double)qf[0], __dmul_rn(0.5,(double)ac0)), den);
+                    }
+                }
+                {
+                    float qs = 0;
+                    #pragma unroll
+                    for (int j=0; j<NALS; j++) qs = __fadd_rn(qs, qf[j]);
+                    if ( qs!=0 )
+                    {
+                        #pragma unroll
+                        for (int j=0; j<NALS; j++) qf[j] = __fdiv_rn(qf[j], qs);
+                    }
+                }
+                if ( lane==0 )
+                {
+                    #pragma unroll
+                    for (int j=0; j<NALS; j++) { s_qf[j] = qf[j]; grec[g].q[j] = (double)qf[j]; }
+                }
+                __syncwarp();
+                /* allele-set coefficients, one lane per set (mcall.c:629-633, 671-677) */
+                uint32_t live = 0;
+                if ( lane < NPAIR )
+                {
+                    int aa = 1; while ( aa*(aa+1)/2 <= lane ) aa++;
+                    int bb = lane - aa*(aa-1)/2;
+                    float fqa = s_qf[aa], fqb = s_qf[bb];
+                    double *cf = s_cfp + lane*5;
+                    if ( fqa!=0 && fqb!=0 )
+                    {
+                        float den = __fadd_rn(fqa,fqb);
+                        double fa = (double)__fdiv_rn(fqa,den), fb = (double)__fdiv_rn(fqb,den);
+                        cf[0] = __dmul_rn(fa,fa); cf[1] = __dmul_rn(fb,fb); cf[2] = __dmul_rn(__dmul_rn(2.0,fa),fb);
+                        cf[3] = fa; cf[4] = fb;
+                        live = 1u<<lane;
+                    }
+                    else { cf[0] = cf[1] = cf[2] = cf[3] = cf[4] = 0; }
+                }
+                else if ( lane-NPAIR < NTRI )
+                {
+                    int k = lane-NPAIR;
+                    int aa = 2; while ( (aa+1)*aa*(aa-1)/6 <= k ) aa++;
+                    int r = k - aa*(aa-1)*(aa-2)/6;
+                    int bb = 1; while ( bb*(bb+1)/2 <= r ) bb++;
+                    int cc = r - bb*(bb-1)/2;
+                    float fqa = s_qf[aa], fqb = s_qf[bb], fqc = s_qf[cc];
+                    double *cf = s_cft + k*9;
+                    if ( fqa!=0 && fqb!=0 && fqc!=0 )
+                    {
+                        float den = __fadd_rn(__fadd_rn(fqa,fqb),fqc);
+                        double fa = (double)__fdiv_rn(fqa,den), fb = (double)__fdiv_rn(fqb,den), fc = (double)__fdiv_rn(fqc,den);
+                        cf[0] = __dmul_rn(fa,fa); cf[1] = __dmul_rn(fb,fb); cf[2] = __dmul_rn(fc,fc);
+                        cf[3] = __dmul_rn(__dmul_rn(2.0,fa),fb); cf[4] = __dmul_rn(__dmul_rn(2.0,fa),fc); cf[5] = __dmul_rn(__dmul_rn(2.0,fb),fc);
+                        cf[6] = fa; cf[7] = fb; cf[8] = fc;
+                        live = 1u<<lane;
+                    }
+                    else { for (int j=0; j<9; j++) cf[j] = 0; }
+                }
+                #pragma unroll
+                for (int off=16; off; off>>=1) live |= __shfl_xor_sync(0xffffffffu, live, off);
+                if ( lane==0 ) s_live = live;
+            }
+            __syncthreads();
+            const uint32_t live = s_live;
+            /* ---- sample-parallel accumulation (pooled kernel, phase 1) over the group's sample list */
+            double accM[NACC]; int accE[NACC]; long long plsum[NALS];
+            int cnt_all = 0, cnt_called = 0, since = 0;
+            uint32_t bflags = 0;
+            #pragma unroll
+            for (int k=0; k<NACC; k++) { accM[k] = 1.0; accE[k] = 0; }
+            #pragma unroll
+            for (int k=0; k<NALS; k++) plsum[k] = 0;
+            for (int i=tid; i<ng; i+=GBLOCK)
+            {
+                const int smp = a.grp_smpl[beg+i];
+                int pl[G]; double p[G];
+                int orv = 0;
+                #pragma unroll
+                for (int j=0; j<G; j++) { pl[j] = site_pl[(size_t)smp*G + j]; orv |= pl[j]; }
+                if ( orv<0 )
+                {
+                    int tmp[16];
+                    #pragma unroll
+                    for (int j=0; j<G; j++) tmp[j] = pl[j];
+                    const int ok = fix_missing_local(tmp, NALS, unseen);
+                    orv = 0;
+                    #pragma unroll
+                    for (int j=0; j<G; j++) { if ( ok ) pl[j] = tmp[j]; orv |= pl[j]; }
+                    if ( !ok || orv<0 ) continue;
+                }
+                if ( orv==0 ) continue;
+                #pragma unroll
+                for (int j=0; j<G; j++) p[j] = pl_to_p_dev(s_pl2p, a.tab, pl[j], &bflags);
+                double sum = p[0];
+                #pragma unroll
+                for (int j=1; j<G; j++) sum = __dadd_rn(sum, p[j]);
+                const int pld = ploidy[smp];
+                #pragma unroll
+                for (int k=0; k<NALS; k++) plsum[k] += pl[hom_idx(k)];
+                cnt_all++;
+                acc_mul(accM[NACC-2], accE[NACC-2], sum);
+                if ( pld==0 ) continue;
+                cnt_called++;
+                acc_mul(accM[NACC-1], accE[NACC-1], sum);
+                if ( pld==2 )
+                {
+                    #pragma unroll
+                    for (int x=1; x<NALS; x++)
+                        #pragma unroll
+                        for (int y=0; y<x; y++)
+                        {
+                            const int k = pair_idx(x,y);
+                            if ( live & (1u<<k) )
+                            {
+                                const double *cf = s_cfp + k*5;
+                                double val = fma(cf[2], p[gt_idx(x,y)], fma(cf[1], p[hom_idx(y)], cf[0]*p[hom_idx(x)]));
+                                acc_mul(accM[k], accE[k], val);
+                            }
+                        }
+                    #pragma unroll
+                    for (int x=2; x<NALS; x++)
+                        #pragma unroll
+                        for (int y=1; y<x; y++)
+                            #pragma unroll
+                            for (int z=0; z<y; z++)
+                            {
+                                const int k = tri_idx(x,y,z);
+                                if ( live & (1u<<(NPAIR+k)) )
+                                {
+                                    const double *cf = s_cft + k*9;
+                                    double val = fma(cf[5], p[gt_idx(y,z)], fma(cf[4], p[gt_idx(x,z)], fma(cf[3], p[gt_idx(x,y)],
+                                                 fma(cf[2], p[hom_idx(z)], fma(cf[1], p[hom_idx(y)], cf[0]*p[hom_idx(x)])))));
+                                    acc_mul(accM[NPAIR+k], accE[NPAIR+k], val);
+                                }
+                            }
+                }
+                else
+                {
+                    #pragma unroll
+                    for (int x=1; x<NALS; x++)
+                        #pragma unroll
+                        for (int y=0; y<x; y++)
+                        {
+                            const int k = pair_idx(x,y);
+                            if ( live & (1u<<k) )
+                            {
+                                const double *cf = s_cfp + k*5;
+                                double val = fma(cf[4], p[hom_idx(y)], cf[3]*p[hom_idx(x)]);
+                                acc_mul(accM[k], accE[k], val);
+                            }
+                        }
+                    #pragma unroll
+                    for (int x=2; x<NALS; x++)
+                        #pragma unroll
+                        for (int y=1; y<x; y++)
+                            #pragma unroll
+                            for (int z=0; z<y; z++)
+                            {
+                                const int k = tri_idx(x,y,z);
+                                if ( live & (1u<<(NPAIR+k)) )
+                                {
+                                    const double *cf = s_cft + k*9;
+                                    double val = fma(cf[8], p[hom_idx(z)], fma(cf[7], p[hom_idx(y)], cf[6]*p[hom_idx(x)]));
+                                    acc_mul(accM[NPAIR+k], accE[NPAIR+k], val);
+                                }
+                            }
+                }
+                if ( ++since >= 256 )
+                {
+                    #pragma unroll
+                    for (int k=0; k<NACC; k++) acc_renorm(accM[k], accE[k]);
+                    since = 0;
+                }
+            }
+            /* ---- CTA reduction (mantissa multiply, exponent add) */
+            #pragma unroll
+            for (int k=0; k<NACC; k++)
+            {
+                acc_renorm(accM[k], accE[k]);
+                #pragma unroll
+                for (int off=16; off; off>>=1)
+                {
+                    accM[k] = __dmul_rn(accM[k], __shfl_xor_sync(0xffffffffu, accM[k], off));
+                    accE[k] += __shfl_xor_sync(0xffffffffu, accE[k], off);
+                }
+                acc_renorm(accM[k], accE[k]);
+            }
+            #pragma unroll
+            for (int k=0; k<NALS; k++)
+                #pragma unroll
+                for (int off=16; off; off>>=1) plsum[k] += __shfl_xor_sync(0xffffffffu, plsum[k], off);
+            #pragma unroll
+            for (int off=16; off; off>>=1)
+            {
+                cnt_all    += __shfl_xor_sync(0xffffffffu, cnt_all, off);
+                cnt_called += __shfl_xor_sync(0xffffffffu, cnt_called, off);
+                bflags     |= __shfl_xor_sync(0xffffffffu, bflags, off);
+            }
+            if ( lane==0 )
+            {
+                #pragma unroll
+                for (int k=0; k<NACC; k++) { s_redM[warp][k] = accM[k]; s_redE[warp][k] = accE[k]; }
+                #pragma unroll
+                for (int k=0; k<NALS; k++) s_redP[warp][k] = plsum[k];
+                s_redC[warp][0] = cnt_all; s_redC[warp][1] = cnt_called;
+                if ( bflags ) atomicOr(&st.flags, bflags);
+            }
+            __syncthreads();
+            /* ---- set totals and the group's best set: lane k <-> allele set k */
+            if ( warp==0 )
+            {
+                constexpr double LN10_10 = 0.2302585092994045684017991454684;
+                int n_all = 0, n_called = 0;
+                #pragma unroll
+                for (int w=0; w<GNW; w++) { n_all += s_redC[w][0]; n_called += s_redC[w][1]; }
+                auto total_log = [&](int k, int n) -> double
+                {
+                    double M = 1.0; int E = 0;
+                    #pragma unroll
+                    for (int w=0; w<GNW; w++) { M = __dmul_rn(M, s_redM[w][k]); E += s_redE[w][k]; }
+                    return log(M) + (double)(E - 1023*n)*LN2;
+                };
+                const double lnN_all = n_all ? total_log(NACC-2, n_all) : 0.0;
+                const double lnN_called = n_called ? total_log(NACC-1, n_called) : 0.0;
+                double lk = 0; bool cand = false, in_sum = false; uint32_t mask = 0;
+                if ( lane < NALS )
+                {
+                    long long ps = 0;
+                    #pragma unroll
+                    for (int w=0; w<GNW; w++) ps += s_redP[w][lane];
+                    const bool set = n_all > 0;
+                    lk = set ? -LN10_10*(double)ps - lnN_all : 0.0;
+                    if ( lane>0 ) lk += a.theta;
+                    cand = set; in_sum = set && lane>0; mask = 1u<<lane;
+                }
+                else if ( lane < NSUB )
+                {
+                    const int k = lane - NALS;
+                    const bool lv = (live >> k) & 1u;
+                    const bool set = lv && n_called > 0;
+                    int nonref = 0;
+                    if ( k < NPAIR )
+                    {
+                        int aa = 1; while ( aa*(aa+1)/2 <= k ) aa++;
+                        int bb = k - aa*(aa-1)/2;
+                        mask = 1u<<aa | 1u<<bb; nonref = (aa!=0) + (bb!=0);
+                    }
+                    else
+                    {
+                        int kk = k - NPAIR;
+                        int aa = 2; while ( (aa+1)*aa*(aa-1)/6 <= kk ) aa++;
+                        int r = kk - aa*(aa-1)*(aa-2)/6;
+                        int bb = 1; while ( bb*(bb+1)/2 <= r ) bb++;
+                        int cc = r - bb*(bb-1)/2;
+                        mask = 1u<<aa | 1u<<bb | 1u<<cc; nonref = (aa!=0) + (bb!=0) + (cc!=0);
+                    }
+                    lk = set ? total_log(k, n_called) - lnN_called : 0.0;
+                    for (int j=0; j<nonref; j++) lk += a.theta;
+                    cand = set; in_sum = set;
+                }
+                double best = cand ? lk : -CUDART_INF; int best_lane = cand ? lane : 64;
+                #pragma unroll
+                for (int off=16; off; off>>=1)
+                {
+                    double ob = __shfl_xor_sync(0xffffffffu, best, off);
+                    int    ol = __shfl_xor_sync(0xffffffffu, best_lane, off);
+                    if ( ob > best || (ob==best && ol < best_lane) ) { best = ob; best_lane = ol; }
+                }
+                double second = (cand && lane!=best_lane) ? lk : -CUDART_INF;
+                #pragma unroll
+                for (int off=16; off; off>>=1) second = fmax(second, __shfl_xor_sync(0xffffffffu, second, off));
+                double mx = in_sum ? lk : -CUDART_INF;
+                #pragma unroll
+                for (int off=16; off; off>>=1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+                double term = in_sum ? exp(lk - mx) : 0.0;
+                #pragma unroll
+                for (int off=16; off; off>>=1) term += __shfl_xor_sync(0xffffffffu, term, off);
+                const double g_lk_sum = mx > -CUDART_INF ? mx + log(term) : -CUDART_INF;
+                const double g_ref_lk = __shfl_sync(0xffffffffu, lk, 0);
+                const uint32_t g_als = __shfl_sync(0xffffffffu, mask, best_lane & 31);
+                if ( lane==0 )
+                {
+                    const bool any = best_lane < 64;
+                    GroupRec &r = grec[g];
+                    r.als = any ? g_als : 0;
+                    int n = 0;
+                    for (int j=0; j<NALS; j++) n += (r.als>>j)&1u;
+                    r.nals = n; r.has_max = any;
+                    r.ref_lk = g_ref_lk; r.lk_sum = g_lk_sum;
+                    r.qual = any ? -4.343*(g_ref_lk - logsumexp2_dev(g_lk_sum, g_ref_lk)) : -CUDART_INF;
+                    if ( any && best - second < a.tie_eps ) atomicOr(&st.flags, MCB_SITE_NEAR_TIE);
+                }
+            }
+            __syncthreads();
+        }
+        __threadfence_block();
+        __syncthreads();
 
         /* =========================== phase B: combine the groups (mcall.c:1546-1577) ============= */
         if ( tid==0 )
@@ -416,8 +785,21 @@ __global__ void __launch_bounds__(GBLOCK) mcall_groups_kernel(const KArgs a, Gro
             int2 *out_gt = a.gt ? reinterpret_cast<int2*>(a.gt) + (size_t)site*nsmpl : nullptr;
             int32_t *out_gq = want_gq ? a.gq + (size_t)site*nsmpl : nullptr;
             uint32_t tflags = 0;
-            for (int s=tid; s<nsmpl; s+=GBLOCK)
+            unsigned long long acc = 0;     /* AC: 12-bit counters per new allele, flushed by warp shuffles (as in the pooled kernel) */
+            int acc_n = 0;
+            for (int sb=0; sb<nsmpl; sb+=GBLOCK)
             {
+                if ( acc_n >= 60 )       /* uniform across the CTA */
+                {
+                    unsigned long long v = acc;
+                    #pragma unroll
+                    for (int off=16; off; off>>=1) v += __shfl_xor_sync(0xffffffffu, v, off);
+                    if ( lane==0 ) for (int j=0; j<5; j++) { int c = (int)((v >> (12*j)) & 0xfff); if ( c ) atomicAdd(&st.ac[j], c); }
+                    acc = 0; acc_n = 0;
+                }
+                acc_n++;
+                const int s = sb + tid;
+                if ( s>=nsmpl ) continue;
                 const GroupRec &r = grec[a.smpl2grp[s]];
                 int pl[G]; double p[G];
                 int orv = 0;
@@ -457,7 +839,7 @@ __global__ void __launch_bounds__(GBLOCK) mcall_groups_kernel(const KArgs a, Gro
                 else if ( ref_gt )
                 {
                     gt0 = MCB_GT_UNPHASED(0); gt1 = pld==2 ? MCB_GT_UNPHASED(0) : I32_VEC_END;
-                    atomicAdd(&st.ac[0], pld);
+                    acc += (unsigned long long)pld;
                 }
                 else
                 {
@@ -492,12 +874,12 @@ __global__ void __launch_bounds__(GBLOCK) mcall_groups_kernel(const KArgs a, Gro
                                 if ( best < lk ) { best = lk; g0 = st.als_map[y]; g1 = st.als_map[x]; }
                             }
                         gt0 = MCB_GT_UNPHASED(g0); gt1 = MCB_GT_UNPHASED(g1);
-                        atomicAdd(&st.ac[min(g0,7)], 1); atomicAdd(&st.ac[min(g1,7)], 1);
+                        acc += (1ull << (12*min(g0,4))) + (1ull << (12*min(g1,4)));
                     }
                     else
                     {
                         gt0 = MCB_GT_UNPHASED(g0); gt1 = I32_VEC_END;
-                        atomicAdd(&st.ac[min(g0,7)], 1);
+                        acc += 1ull << (12*min(g0,4));
                     }
                     if ( want_gq || want_gp )           /* mcall.c:843-878 */
                     {
@@ -561,6 +943,12 @@ __global__ void __launch_bounds__(GBLOCK) mcall_groups_kernel(const KArgs a, Gro
                             if ( k<ngt_new ) dst[k] = k<nmax ? (float)__ddiv_rn((double)gps[k], gsum) : __uint_as_float(MCB_FLOAT_VECTOR_END_BITS);
                     }
                 }
+            }
+            {
+                unsigned long long v = acc;
+                #pragma unroll
+                for (int off=16; off; off>>=1) v += __shfl_xor_sync(0xffffffffu, v, off);
+                if ( lane==0 ) for (int j=0; j<5; j++) { int c = (int)((v >> (12*j)) & 0xfff); if ( c ) atomicAdd(&st.ac[j], c); }
             }
             if ( tflags ) atomicOr(&st.flags, tflags);
         }

@@ -71,13 +71,21 @@ def test_mixed_ploidy(S, oracle_built):
     assert st["compared"] > 0, st
 
 
-@pytest.mark.parametrize("S,maxA,mode,flag", [(30, 5, 3, 0), (9, 4, "single", abi.CALL_VARONLY), (200, 5, 7, abi.CALL_KEEPALT), (64, 3, 2, 0)])
+@pytest.mark.parametrize("S,maxA,mode,flag", [(30, 5, 3, 0), (9, 4, "single", abi.CALL_VARONLY), (200, 5, 7, abi.CALL_KEEPALT), (64, 3, 2, 0),
+                                              (300, 5, "mixed", 0), (700, 4, 3, abi.CALL_VARONLY)])
 def test_sample_groups(S, maxA, mode, flag, oracle_built):
     """-G: per-group quality sums from FORMAT/AD (float32, group order), per-group allele sets, union of the sets,
     QUAL of the best group, per-sample genotypes with the sample's own group (mcall.c:1466-1504, 1546-1561, 1608-1614)."""
     rng = np.random.default_rng([S, maxA, 99])
     batch = parity.random_batch(rng, 80, S, maxA)
-    groups = [[s] for s in range(S)] if mode == "single" else [list(range(k, S, mode)) for k in range(mode)]
+    if mode == "single":
+        groups = [[s] for s in range(S)]
+    elif mode == "mixed":       # big groups (whole-CTA path) next to small ones (warp path), interleaved sample indices
+        perm = rng.permutation(S)
+        cuts = [0, 150, 250, 290, S]
+        groups = [sorted(perm[cuts[k]:cuts[k + 1]].tolist()) for k in range(4)]
+    else:
+        groups = [list(range(k, S, mode)) for k in range(mode)]
     tab = np.full((2, S), 2, np.uint8)
     tab[1, ::3] = 1
     tab[1, 1::7] = 0
