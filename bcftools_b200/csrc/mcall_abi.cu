@@ -21,10 +21,13 @@ using namespace mcb;
 #define NCLASS 6                /* allele-count classes 1..5 + class 0 = everything else */
 #define MAX_STAGE 16
 
-struct HostSlab                 /* one half of the host-path double buffer */
+#define NSLAB 3
+struct HostSlab                 /* one stage of the host-path ring (H2D of slab k+1 overlaps kernels and D2H of slab k) */
 {
     cudaStream_t stream = nullptr;
-    cudaEvent_t  done = nullptr;
+    cudaEvent_t  done = nullptr, cursor_ready = nullptr;
+    /* compaction tail still owed by the slab in flight on this stage */
+    bool pending = false;  int p_beg = 0;  size_t p_plout = 0, p_gp = 0;
     void  *dev = nullptr;  size_t dev_bytes = 0;    /* one arena, carved per slab */
     int32_t *lists = nullptr, *counts = nullptr;  int list_cap = 0;
     unsigned long long *cursor = nullptr;           /* device: compacted-PL allocation cursor (int32 units) */
@@ -46,7 +49,7 @@ struct mcb_ctx
     /* device-path scratch */
     int32_t *d_lists = nullptr, *d_counts = nullptr;  int list_cap = 0;
     unsigned long long *d_cursor = nullptr;
-    HostSlab slab[2];
+    HostSlab slab[NSLAB];
     /* options */
     int64_t opt_tile_bytes = 0, opt_ring_bytes = 0, opt_blocks_per_sm = 0, opt_slab_bytes = 64ll<<20, opt_block = 0;     /* 0 = automatic */
     int64_t opt_time_kernels = 0, opt_concurrent = 0;    /* concurrent class streams measured SLOWER than serial launches */
@@ -225,10 +228,11 @@ extern "C" int mcb_init(mcb_ctx **out, const mcb_params *params)
         CK(cudaMemcpy(ctx->d_grp_smpl, params->grp_smpl, sizeof(uint32_t)*S, cudaMemcpyHostToDevice));
         CK(cudaMemcpy(ctx->d_smpl2grp, s2g.data(), sizeof(uint32_t)*S, cudaMemcpyHostToDevice));
     }
-    for (int i=0; i<2; i++)
+    for (int i=0; i<NSLAB; i++)
     {
         CK(cudaStreamCreateWithFlags(&ctx->slab[i].stream, cudaStreamNonBlocking));
         CK(cudaEventCreateWithFlags(&ctx->slab[i].done, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ctx->slab[i].cursor_ready, cudaEventDisableTiming));
         CK(cudaMalloc(&ctx->slab[i].counts, sizeof(int32_t)*NCLASS));
         CK(cudaMalloc(&ctx->slab[i].cursor, sizeof(unsigned long long)));
         CK(cudaHostAlloc(&ctx->slab[i].h_cursor, sizeof(unsigned long long), cudaHostAllocDefault));
@@ -242,11 +246,11 @@ extern "C" void mcb_destroy(mcb_ctx *ctx)
     cudaSetDevice(ctx->device);
     cudaFree(ctx->d_tab); cudaFree(ctx->d_ploidy); cudaFree(ctx->d_grp_off); cudaFree(ctx->d_grp_smpl); cudaFree(ctx->d_smpl2grp); cudaFree(ctx->d_grp_scratch); cudaFree(ctx->d_gen_grp); cudaFree(ctx->d_gen_pl); cudaFree(ctx->d_gen_sum);
     cudaFree(ctx->d_lists); cudaFree(ctx->d_counts); cudaFree(ctx->d_cursor);
-    for (int i=0; i<2; i++)
+    for (int i=0; i<NSLAB; i++)
     {
         if ( ctx->slab[i].stream ) cudaStreamDestroy(ctx->slab[i].stream);
         if ( ctx->slab[i].done ) cudaEventDestroy(ctx->slab[i].done);
-        
+        if ( ctx->slab[i].cursor_ready ) cudaEventDestroy(ctx->slab[i].cursor_ready);
         cudaFree(ctx->slab[i].dev); cudaFree(ctx->slab[i].lists); cudaFree(ctx->slab[i].counts); cudaFree(ctx->slab[i].cursor);
         if ( ctx->slab[i].h_cursor ) cudaFreeHost(ctx->slab[i].h_cursor);
     }
@@ -537,6 +541,24 @@ extern "C" int mcb_call_host(mcb_ctx *ctx, const mcb_batch *b, const mcb_result 
     int64_t out_total = 0;                              /* int32 units already placed in r->pl */
     std::vector<std::pair<int,int64_t>> slab_base;      /* (first site, base) per slab, applied to pl_off_out at the end */
 
+    /* Compacted output: the PL/GP extent of a slab is known only after its kernels ran.  The host reads the cursor of
+       slab k-1 AFTER it has queued the uploads and kernels of slab k, so the copy engines never wait for the host. */
+    auto finish = [&](HostSlab &sl) -> int
+    {
+        if ( !sl.pending ) return MCB_OK;
+        sl.pending = false;
+        CK(cudaEventSynchronize(sl.cursor_ready));
+        const int64_t used = (int64_t)*sl.h_cursor;
+        char *base = (char*) sl.dev;
+        if ( want_pl && used ) CK(cudaMemcpyAsync(r->pl + out_total, base + sl.p_plout, (size_t)used*4, cudaMemcpyDeviceToHost, sl.stream));
+        if ( want_gp && used ) CK(cudaMemcpyAsync(r->gp + out_total, base + sl.p_gp, (size_t)used*4, cudaMemcpyDeviceToHost, sl.stream));
+        slab_base.push_back(std::make_pair(sl.p_beg, out_total));
+        out_total += used;
+        CK(cudaEventRecord(sl.done, sl.stream));
+        return MCB_OK;
+    };
+    for (int i=0; i<NSLAB; i++) ctx->slab[i].pending = false;
+
     int beg = 0, islab = 0;
     while ( beg < R )
     {
@@ -544,8 +566,9 @@ extern "C" int mcb_call_host(mcb_ctx *ctx, const mcb_batch *b, const mcb_result 
         int end = beg; int64_t pl_ints = 0;
         while ( end < R && (end==beg || (pl_ints + ext[end])*es <= ctx->opt_slab_bytes) ) { pl_ints = b->pl_off[end] + ext[end] - b->pl_off[beg]; end++; }
         const int n = end - beg;
-        HostSlab &sl = ctx->slab[islab & 1];
-        CK(cudaEventSynchronize(sl.done));      /* previous use of this half finished (event starts signalled) */
+        HostSlab &sl = ctx->slab[islab % NSLAB];
+        { int frc = finish(sl); if ( frc ) return frc; }
+        CK(cudaEventSynchronize(sl.done));      /* previous use of this stage finished (event starts signalled) */
 
         /* carve the arena */
         size_t off = 0;
@@ -636,31 +659,31 @@ extern "C" int mcb_call_host(mcb_ctx *ctx, const mcb_batch *b, const mcb_result 
         if ( r->an ) D2H(r->an + beg, o_an, 4*(size_t)n);
         if ( r->site_flags ) D2H(r->site_flags + beg, o_fl, 4*(size_t)n);
         if ( r->diag ) D2H(r->diag + (size_t)beg*4, o_diag, 32*(size_t)n);
+        if ( compact )
+        {
+            CK(cudaMemcpyAsync(sl.h_cursor, sl.cursor, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+            D2H(r->pl_off_out + beg, o_ploo, sizeof(int64_t)*n);
+            CK(cudaEventRecord(sl.cursor_ready, st));
+        }
         if ( want_gt ) D2H(r->gt + (size_t)beg*S*2, o_gt, 8*(size_t)n*S);
         if ( want_gq ) D2H(r->gq + (size_t)beg*S, o_gq, 4*(size_t)n*S);
         if ( !compact )
         {
             if ( want_pl ) D2H(r->pl + pl0, o_plout, (size_t)pl_ints*4);
             if ( want_gp ) D2H(r->gp + pl0, o_gp, (size_t)pl_ints*4);
+            CK(cudaEventRecord(sl.done, st));
         }
         else
         {
-            /* the number of used int32 is only known once the kernels of this slab have run */
-            CK(cudaMemcpyAsync(sl.h_cursor, sl.cursor, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-            D2H(r->pl_off_out + beg, o_ploo, sizeof(int64_t)*n);
-            CK(cudaStreamSynchronize(st));
-            const int64_t used = (int64_t)*sl.h_cursor;
-            if ( want_pl && used ) D2H(r->pl + out_total, o_plout, (size_t)used*4);
-            if ( want_gp && used ) D2H(r->gp + out_total, o_gp, (size_t)used*4);
-            slab_base.push_back(std::make_pair(beg, out_total));
-            out_total += used;
+            sl.pending = true; sl.p_beg = beg; sl.p_plout = o_plout; sl.p_gp = o_gp;
+            /* the tail of the PREVIOUS slab: its kernels have had the whole upload of this one to finish */
+            if ( islab ) { int frc = finish(ctx->slab[(islab-1) % NSLAB]); if ( frc ) return frc; }
         }
 #undef D2H
-        CK(cudaEventRecord(sl.done, st));
         beg = end; islab++;
     }
-    CK(cudaStreamSynchronize(ctx->slab[0].stream));
-    CK(cudaStreamSynchronize(ctx->slab[1].stream));
+    for (int k=0; k<NSLAB; k++) { int frc = finish(ctx->slab[(islab + k) % NSLAB]); if ( frc ) return frc; }   /* oldest first */
+    for (int k=0; k<NSLAB; k++) CK(cudaStreamSynchronize(ctx->slab[k].stream));
     for (size_t k=0; k<slab_base.size(); k++)           /* slab-local offsets -> offsets into r->pl */
     {
         const int first = slab_base[k].first, last = k+1<slab_base.size() ? slab_base[k+1].first : R;

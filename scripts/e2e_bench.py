@@ -8,7 +8,7 @@ params, hb, tab = synth.make_batch("C3", sites, with_groups=0)
 for slab_mb in (256, 128, 64, 32, 16):
     mc = mcall.MCaller(params, ploidy_tab=tab, options={"slab_bytes": slab_mb << 20})
     sub = mcall.pin_batch(hb.subset(range(sites)))
-    res = mcall.pin_result(abi.HostResult(sub))
+    res = mcall.pin_result(abi.HostResult(sub, compact=True))
     for _ in range(2):
         mc.call_host(sub, res)
     t0 = time.perf_counter()
