@@ -37,7 +37,7 @@ struct HostSlab                 /* one stage of the host-path ring (H2D of slab 
 struct mcb_ctx
 {
     mcb_params p;
-    int device = 0, nsm = 0;
+    int device = 0, nsm = 0;  size_t smem_per_sm = 0;
     double theta_log = 0;
     double pl2p[256];
     DevTables *d_tab = nullptr;
@@ -52,6 +52,7 @@ struct mcb_ctx
     HostSlab slab[NSLAB];
     /* options */
     int64_t opt_tile_bytes = 0, opt_ring_bytes = 0, opt_blocks_per_sm = 0, opt_slab_bytes = 64ll<<20, opt_block = 0;     /* 0 = automatic */
+    int64_t opt_warp2 = -1;              /* biallelic warp-per-site kernel: -1 automatic, 0 off, n = force n warps per CTA */
     int64_t opt_time_kernels = 0, opt_concurrent = 0;    /* concurrent class streams measured SLOWER than serial launches */
     int64_t opt_ring_bytes_c[NCLASS] = {0,0,0,0,0,0};   /* per allele-count class override of ring_bytes (0 = opt_ring_bytes) */
     int64_t opt_block_c[NCLASS] = {0,0,0,0,0,0};        /* per class override of the CTA size */
@@ -148,6 +149,7 @@ extern "C" int mcb_set_option(mcb_ctx *ctx, const char *key, int64_t value)
     else if ( !strcmp(key,"slab_bytes") )    ctx->opt_slab_bytes = value;
     else if ( !strcmp(key,"time_kernels") )  ctx->opt_time_kernels = value;
     else if ( !strcmp(key,"concurrent") )    ctx->opt_concurrent = value;
+    else if ( !strcmp(key,"warp2") )         { if ( value<-1 || value>biallelic_max_warps() ) return MCB_EINVAL; ctx->opt_warp2 = value; }
     else if ( !strncmp(key,"ring_bytes_",11) && key[11]>='1' && key[11]<='5' && !key[12] ) ctx->opt_ring_bytes_c[key[11]-'0'] = value;
     else if ( !strncmp(key,"block_",6) && key[6]>='1' && key[6]<='5' && !key[7] )
     {
@@ -192,6 +194,7 @@ extern "C" int mcb_init(mcb_ctx **out, const mcb_params *params)
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, ctx->device));
     ctx->nsm = prop.multiProcessorCount;
+    ctx->smem_per_sm = prop.sharedMemPerMultiprocessor;
     ctx->theta_log = init_theta(params->theta, params->init_ploidy, params->nsmpl);
 
     DevTables *t = new DevTables();
@@ -459,6 +462,37 @@ static int enqueue(mcb_ctx *ctx, const mcb_batch *b, const mcb_result *r, int32_
         size_t ring; tile_geometry(ctx, nals, pl_es, &a.tile_smpl, &a.nstage, &ring);
         const int block = pl_es==2 ? 128 : class_block(ctx, nals);
         a.site_list = lists + (size_t)nals*list_stride; a.site_count = counts + nals;
+        /* two alleles, everything diploid, int32 PLs, no GP: one warp per site over a byte-packed shared-memory copy */
+        int bw_warps = 0;
+        if ( nals==2 && !ploidy && pl_es==4 && !(a.gp && (a.output_tags & MCB_CALL_FMT_GP)) && ctx->opt_warp2!=0 && a.nsmpl<=8192 )
+        {
+            const int ncta = biallelic_ctas_per_sm();
+            const size_t per_cta = (size_t)(ctx->smem_per_sm/ncta) - 1024;  /* the kernel is compiled for ncta CTAs per SM */
+            int w = biallelic_max_warps();
+            while ( w>0 && biallelic_smem_bytes(a.nsmpl, w) > per_cta ) w--;
+            if ( ctx->opt_warp2>0 ) w = std::min<int>(w, (int)ctx->opt_warp2);
+            const bool tiled_forced = ctx->opt_block || ctx->opt_block_c[2];  /* an explicit CTA size asks for the tiled kernel */
+            if ( ctx->opt_warp2>0 ? w>0 : (w*ncta>=16 && !tiled_forced) ) bw_warps = w;   /* few resident warps: the tiled kernel wins */
+        }
+        if ( bw_warps )
+        {
+            int grid = (int)std::min<int64_t>(((int64_t)b->nsites + bw_warps - 1)/bw_warps, (int64_t)ctx->nsm*biallelic_ctas_per_sm());
+            if ( ctx->opt_blocks_per_sm>0 ) grid = std::min<int>(grid, ctx->nsm*(int)std::min<int64_t>(biallelic_ctas_per_sm(), ctx->opt_blocks_per_sm));
+            cudaStream_t cs = fork ? ctx->cstream[nals] : st;
+            if ( fork ) CK(cudaStreamWaitEvent(cs, ctx->cev_fork, 0));
+            cudaError_t le = launch_biallelic_warp_kernel(a, grid, bw_warps, cs);
+            if ( le==cudaSuccess && getenv("MCB_DEBUG_SYNC") ) le = cudaStreamSynchronize(cs);
+            if ( le!=cudaSuccess )
+            {
+                char what[160];
+                snprintf(what, sizeof what, "biallelic warp kernel warps=%d grid=%d smem=%zu", bw_warps, grid, biallelic_smem_bytes(a.nsmpl, bw_warps));
+                return cuda_fail(ctx, le, what);
+            }
+            launches++;
+            if ( fork ) { CK(cudaEventRecord(ctx->cev_join[nals], cs)); CK(cudaStreamWaitEvent(st, ctx->cev_join[nals], 0)); }
+            if ( timing ) { CK(cudaEventRecord(ctx->kev[nals], st)); nals = 6 - nals; }
+            continue;
+        }
         int nb = 1;
         CK(site_kernel_occupancy(nals, ploidy, block, pl_es, ring, &nb));
         if ( nb<1 ) return cuda_fail(ctx, cudaErrorLaunchOutOfResources, "site kernel does not fit on an SM");

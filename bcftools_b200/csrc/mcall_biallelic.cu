@@ -1,0 +1,706 @@
+/*  mcall_biallelic.cu -- warp-per-site kernel for the dominant shape of `call -m`: two alleles (REF + one ALT),
+ *  every sample diploid, int32 PLs, one sample group, no FORMAT/GP.
+ *
+ *  Same algorithm and reference line map as the general site kernel (mcall_kernels.cu); what differs is the mapping:
+ *
+ *    - ONE WARP owns one site, so there is no block barrier, no cross-warp reduction and no idle warps while a
+ *      single lane evaluates the allele sets: warps of a CTA only share the read-only tables.
+ *    - phase 1 reads the site's PL block straight from global memory, 4 samples (12 int32 = 3 x 128 bit) per lane and
+ *      iteration, and leaves a byte-packed copy (3 bytes per sample: PL <= 255 in the common case) in the warp's
+ *      private shared-memory buffer.  A 2504-sample site takes 7.5 KB instead of the 30 KB int32 tile, so ~28 warps
+ *      stay resident per SM and HBM still sees every PL byte once.
+ *    - phase 2 reads the packed copy, calls the 4 genotypes and writes GT / GQ / trimmed PL with 128-bit stores.
+ *    - a sample with a value outside 0..255 (missing, vector_end, PL >= 256) is packed as the escape triple
+ *      (255,255,255); both phases send such samples through the general per-sample code on the original int32
+ *      values (phase 2 re-reads them; they are rare and hit L2).  A genuine (255,255,255) takes that path too.
+ *
+ *  Phase 2 arithmetic is the literal one of mcall_kernels.cu (mcall.c:787-878), so GT / GQ / PL / AC / AN are
+ *  bit-exact; phase 1 uses the same exponent-tracked products (QUAL within 1e-6 relative).
+ */
+
+#include "mcall_device.cuh"
+
+namespace mcb {
+
+#ifndef BW_ROLL1
+#define BW_ROLL1     0                  /* 1: phase-1 sample loop rolled (smaller code) */
+#endif
+#ifndef BW_UNROLL2
+#define BW_UNROLL2   1                  /* unroll factor of the phase-2 sample loop */
+#endif
+#ifndef BW_MAXWARP
+#define BW_MAXWARP   12                 /* warps per CTA the kernel is compiled for (2 CTAs per SM => 85 registers, no spills; 14 => 72 with spills measured 2 % slower) */
+#endif
+#ifndef BW_MINCTA
+#define BW_MINCTA    2
+#endif
+#define BW_ESC_CAP   64                 /* escaped samples per site handled lane-parallel after the main loops */
+#ifndef BW_PF_DIST
+#define BW_PF_DIST   4                  /* L2 prefetch distance of phase 1, in 128-sample iterations */
+#endif
+#define BW_REC_BYTES 384                /* per-warp site record in shared memory */
+
+constexpr int kBwUnroll2 = BW_UNROLL2;
+
+struct BWRec                            /* written by lane 0 after phase 1, read by the whole warp */
+{
+    int4   slot_out[3];                 /* diploid call of slot k: {gt0, gt1, AC[0] increment, AC[1] increment} */
+    double q[2];                        /* (double)qsum of the selected alleles, mcall.c:797, 820 */
+    double max_qual, lk_sum, ref_lk, gap;
+    float  qf[2];
+    uint32_t flags, als_new;
+    int    nsel, jgt0, inc_dip, nals_new, ret_early, pl_dropped, ref_gt;
+    int    als_map[2];
+    long long out_off;
+    int    nesc;                        /* samples that need the general path (escape list below; > BW_ESC_CAP: overflowed) */
+    unsigned short esc[BW_ESC_CAP];     /* their sample indices */
+};
+static_assert(sizeof(BWRec) <= BW_REC_BYTES, "BWRec grew past its slot");
+
+struct BWTables
+{
+    double pl2p[256];
+    double gq_thr[130];
+};
+
+/*  set_pdg's missing-value fill (mcall.c:495-527) on the 3 PLs of a biallelic sample; returns 0 for "no data"  */
+__device__ __noinline__ int fix_missing3(int *pl, int unseen)
+{
+    int j;
+    for (j=0; j<3; j++)
+    {
+        if ( pl[j]==I32_VEC_END ) return 0;         /* not diploid-shaped: all missing, mcall.c:465-470 */
+        if ( pl[j]==I32_MISSING ) break;
+    }
+    if ( j==0 || j==3 ) return 0;                   /* first value missing (mcall.c:476-481) / no sentinel at all */
+    j = 0;
+    for (int ia=0; ia<2; ia++)
+        for (int ib=0; ib<=ia; ib++)
+        {
+            if ( pl[j]==I32_MISSING )
+            {
+                int k = gt_idx(ia,unseen);
+                if ( pl[k]==I32_MISSING ) k = gt_idx(ib,unseen);
+                if ( pl[k]==I32_MISSING ) k = gt_idx(unseen,unseen);
+                pl[j] = pl[k]==I32_MISSING ? 255 : pl[k];
+            }
+            else if ( pl[j] < 0 ) return 0;
+            j++;
+        }
+    return 1;
+}
+
+__device__ __noinline__ double bw_big_pl_to_p(const DevTables *tab, int v, uint32_t *flags)
+{
+    if ( v > 2500 ) *flags |= MCB_SITE_PL_RANGE;
+    return (unsigned)v < (unsigned)MCB_PL2P_BIG ? tab->pl2p_big[v] : 0.0;
+}
+
+/*  general per-sample load: fills pl[] (missing values filled), p[], sum; returns "sample carries data"  */
+__device__ __forceinline__ bool bw_slow_sample(int (&pl)[3], double (&p)[3], double &sum, int unseen, uint32_t pl2p_s,
+                                               const DevTables *tab, uint32_t &flags)
+{
+    int orv = pl[0] | pl[1] | pl[2];
+    bool data = orv != 0;
+    if ( orv < 0 )
+    {
+        data = fix_missing3(pl, unseen);
+        if ( data ) { orv = pl[0] | pl[1] | pl[2]; data = orv > 0; }
+    }
+    #pragma unroll
+    for (int j=0; j<3; j++)
+        p[j] = !data ? 1.0 : ((unsigned)pl[j] < 256u ? lds64(pl2p_s + 8u*(uint32_t)pl[j]) : bw_big_pl_to_p(tab, pl[j], &flags));
+    sum = __dadd_rn(__dadd_rn(p[0], p[1]), p[2]);
+    return data;
+}
+
+/*  libdevice log/exp are ~200 instructions each when inlined; every warp walks the per-site code on its own schedule,
+ *  so one shared copy keeps the instruction cache warm  */
+__device__ __noinline__ double bw_log(double x) { return log(x); }
+__device__ __noinline__ double bw_exp(double x) { return exp(x); }
+__device__ __forceinline__ double bw_logsumexp2(double a, double b)       /* mcall.c:573-579 */
+{
+    const double hi = a>b ? a : b, lo = a>b ? b : a;
+    return bw_log(1 + bw_exp(lo - hi)) + hi;
+}
+
+struct BWSlow { int pl[3]; double p[3]; double sum; };
+__device__ __noinline__ bool bw_slow_sample_ni(BWSlow *w, int unseen, uint32_t pl2p_s, const DevTables *tab, uint32_t *flags)
+{
+    uint32_t f = 0;
+    const bool data = bw_slow_sample(w->pl, w->p, w->sum, unseen, pl2p_s, tab, f);
+    if ( f ) *flags |= f;
+    return data;
+}
+
+/*  per-site constants of phase 2, in registers  */
+struct BWConsts
+{
+    double q0, q1;
+    uint32_t slot_s, thr_s;
+    int nsel, jgt0, inc_dip;
+    bool want_gq;
+};
+
+/*  mcall_call_genotypes for one diploid sample of a biallelic site (mcall.c:787-878): literal arithmetic.
+ *  p0,p1,p2 = pl2p[PL], sum in index order.  Returns {gt0, gt1, AC0 inc, AC1 inc}; gq by reference.  */
+template<bool FAST>
+__device__ __forceinline__ int4 bw_call_sample(double p0, double p1, double p2, double sum, const BWConsts &c, int &gq)
+{
+    const double r = FAST ? rcp_shared(sum) : 0.0;
+    auto dv = [&](double x) -> double { return FAST ? div_shared(x, sum, r) : __ddiv_rn(x, sum); };
+    double best = 0; int bk = 0; bool any_best = false;     /* default 0/0 when every lk is 0 (mcall.c:787-789) */
+    double gv0, gv1 = 0, gv2 = 0;
+    {
+        const double pdg = dv(c.jgt0 ? p2 : p0);
+        gv0 = __dmul_rn(__dmul_rn(pdg, c.q0), c.q0);
+        if ( best < gv0 ) { best = gv0; bk = 0; any_best = true; }
+    }
+    if ( c.nsel>1 )
+    {
+        const double pdg = dv(p2);
+        gv2 = __dmul_rn(__dmul_rn(pdg, c.q1), c.q1);
+        if ( best < gv2 ) { best = gv2; bk = 2; any_best = true; }
+        gv1 = __dmul_rn(__dmul_rn(__dmul_rn(2.0, dv(p1)), c.q1), c.q0);
+        if ( best < gv1 ) { best = gv1; bk = 1; any_best = true; }
+    }
+    /* nothing beat 0: the reference keeps its 0/0 default, i.e. NEW allele 0 (mcall.c:788) */
+    const int4 outc = any_best ? lds128(c.slot_s + 16u*(uint32_t)bk) : make_int4(MCB_GT_UNPHASED(0), MCB_GT_UNPHASED(0), 2, 0);
+    gq = 0;
+    if ( c.want_gq )            /* mcall.c:843-878: max and sum over the float32 gps[0..nmax) in index order */
+    {
+        double gmax, gsum;
+        gv0 = (double)__double2float_rn(gv0); gv1 = (double)__double2float_rn(gv1); gv2 = (double)__double2float_rn(gv2);
+        const uint32_t full = c.nsel>1 ? 7u : 1u;
+        if ( ((uint32_t)c.inc_dip & full)==full )
+        {
+            gmax = (double)__double2float_rn(best);     /* float rounding is monotone */
+            gsum = __dadd_rn(__dadd_rn(gv0, gv1), gv2); /* absent slots hold +0 */
+        }
+        else
+        {
+            gmax = 0; gsum = 0;
+            if ( c.inc_dip & 1 ) { if ( gmax < gv0 ) gmax = gv0; gsum = __dadd_rn(gsum, gv0); }
+            if ( c.inc_dip & 2 ) { if ( gmax < gv1 ) gmax = gv1; gsum = __dadd_rn(gsum, gv1); }
+            if ( c.inc_dip & 4 ) { if ( gmax < gv2 ) gmax = gv2; gsum = __dadd_rn(gsum, gv2); }
+        }
+        const double xx = __dadd_rn(1.0, -__ddiv_rn(gmax, gsum));
+        if ( !(xx==xx) ) gq = 127;      /* NaN (0/0): `max<=INT8_MAX` is false => INT8_MAX */
+        else
+        {
+            /* (int)(-4.34294*log(x)) from host-libm thresholds: float estimate, exact fix-up */
+            int k = __float2int_rz(-3.0102999f*lg2_approx((float)xx));
+            k = max(0, min(127, k));
+            if ( xx <= lds64c(c.thr_s + 8u*(uint32_t)(k+1)) ) { k++; while ( xx <= lds64c(c.thr_s + 8u*(uint32_t)(k+1)) ) k++; }
+            else while ( xx > lds64c(c.thr_s + 8u*(uint32_t)k) ) k--;
+            gq = k;
+        }
+    }
+    return outc;
+}
+
+__device__ __forceinline__ int4 ldg128(const int4 *p) { return __ldg(p); }
+__device__ __forceinline__ void stg128(void *p, int x, int y, int z, int w)
+{
+    asm volatile("st.global.v4.s32 [%0], {%1,%2,%3,%4};" :: "l"(p), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ void stg64(void *p, int x, int y)
+{
+    asm volatile("st.global.v2.s32 [%0], {%1,%2};" :: "l"(p), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void stg32(void *p, int x)
+{
+    asm volatile("st.global.s32 [%0], %1;" :: "l"(p), "r"(x) : "memory");
+}
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t ldsu32(uint32_t a) { uint32_t v; asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
+__device__ __forceinline__ uint32_t byte_of(uint32_t w, int k) { return (w >> (8*k)) & 0xffu; }
+
+__global__ void __launch_bounds__(BW_MAXWARP*32, BW_MINCTA) mcall_biallelic_warp_kernel(const KArgs a, int warp_bytes)
+{
+    constexpr double LN2 = 0.693147180559945309417232121458, LN10_10 = 0.2302585092994045684017991454684;
+    BWTables &tb = *reinterpret_cast<BWTables*>(mcb_smem);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+    const uint32_t sbase = smem_base();
+    const uint32_t pl2p_s = sbase + (uint32_t)offsetof(BWTables, pl2p), thr_s = sbase + (uint32_t)offsetof(BWTables, gq_thr);
+    const uint32_t wbase_s = sbase + (uint32_t)align128(sizeof(BWTables)) + (uint32_t)warp*(uint32_t)warp_bytes;
+    const uint32_t buf_s = wbase_s + BW_REC_BYTES;
+    BWRec &rec = *reinterpret_cast<BWRec*>(mcb_smem + align128(sizeof(BWTables)) + (size_t)warp*warp_bytes);
+
+    for (int i=tid; i<256; i+=blockDim.x) tb.pl2p[i] = a.tab->pl2p[i];
+    for (int i=tid; i<130; i+=blockDim.x) tb.gq_thr[i] = i<128 ? a.tab->gq_thr[i] : -1.0;
+    __syncthreads();
+
+    const int S = a.nsmpl;
+    const int ngrp4 = (S + 3) >> 2, niter = (ngrp4 + 31) >> 5;
+    const int nsites = *a.site_count;
+    const bool want_gq = a.gq && (a.output_tags & (MCB_CALL_FMT_GQ|MCB_CALL_FMT_GP));
+
+    for (int isite = blockIdx.x*nwarp + warp; isite < nsites; isite += gridDim.x*nwarp)
+    {
+        const int site = a.site_list[isite];
+        const int64_t site_off = a.pl_off[site];
+        const int32_t *site_pl = reinterpret_cast<const int32_t*>(a.pl) + site_off;
+        const int4 *site_pl4 = reinterpret_cast<const int4*>(site_pl);
+        const int unseen = a.unseen ? a.unseen[site] : 0;
+        const char *site_end = reinterpret_cast<const char*>(site_pl) + (size_t)S*12;
+        /* the first blocks of this warp's NEXT site are pulled into L2 while phase 2 of this one runs */
+        const char *next_pl = nullptr;
+        {
+            const int nx = isite + gridDim.x*nwarp;
+            if ( nx < nsites ) next_pl = reinterpret_cast<const char*>(reinterpret_cast<const int32_t*>(a.pl) + a.pl_off[a.site_list[nx]]);
+        }
+        if ( lane==0 ) rec.nesc = 0;
+        __syncwarp();
+
+        /* ---- site set-up, every lane redundantly: qsum (mcall.c:1454-1464), -F prior (1507-1527), normalisation (1530-1535) */
+        float qf0, qf1; uint32_t sflags;
+        {
+            int nqs = a.nqs ? a.nqs[site] : 2;
+            float q[2];
+            #pragma unroll
+            for (int j=0; j<2; j++) q[j] = (a.qs && j<nqs) ? a.qs[(size_t)site*a.max_nals + j] : 0.f;
+            sflags = (a.qs && nqs>0) ? 0 : MCB_SITE_NO_QS;
+            if ( a.use_prior && a.prior_an && a.prior_ac )
+            {
+                int an = a.prior_an[site];
+                if ( an!=I32_MISSING && an>0 )
+                {
+                    const int32_t *pac = a.prior_ac + (size_t)site*a.max_nals;
+                    int ac0 = an;
+                    if ( pac[0]!=I32_VEC_END && pac[0]!=I32_MISSING )
+                    {
+                        ac0 -= pac[0];
+                        q[1] = (float)( __ddiv_rn(__dadd_rn((double)q[1], __dmul_rn(0.5,(double)pac[0])),
+                                                  __dadd_rn((double)(uint32_t)S, __dmul_rn(0.5,(double)an))) );
+                    }
+                    if ( ac0<0 ) sflags |= MCB_SITE_BAD_PRIOR;
+                    q[0] = (float)( __ddiv_rn(__dadd_rn((double)q[0], __dmul_rn(0.5,(double)ac0)),
+                                              __dadd_rn((double)(uint32_t)S, __dmul_rn(0.5,(double)an))) );
+                }
+            }
+            float qsum = __fadd_rn(__fadd_rn(0.f, q[0]), q[1]);
+            if ( qsum != 0 ) { q[0] = __fdiv_rn(q[0], qsum); q[1] = __fdiv_rn(q[1], qsum); }
+            qf0 = q[0]; qf1 = q[1];
+        }
+        /* the pair {ALT,REF}: float32 expression then widened (mcall.c:629-630) */
+        const bool live = qf1!=0 && qf0!=0;
+        double cf0 = 0, cf1 = 0, cf2 = 0;      /* fa2 (ALT hom), fb2 (REF hom), 2 fa fb (het) */
+        if ( live )
+        {
+            const float den = __fadd_rn(qf1, qf0);
+            const double fa = (double)__fdiv_rn(qf1, den), fb = (double)__fdiv_rn(qf0, den);
+            cf0 = __dmul_rn(fa,fa); cf1 = __dmul_rn(fb,fb); cf2 = __dmul_rn(__dmul_rn(2.0,fa),fb);
+        }
+
+        /* =========================== phase 1: site reduction ==================================== */
+        double accP = 1.0, accN = 1.0; int eP = 0, eN = 0;          /* pair product, normaliser product */
+        int nmul = 0;                                               /* multiplications folded into each product */
+        long long ps0 = 0, ps1 = 0;                                 /* single-allele sets: integer PL sums (mcall.c:607-611) */
+        int ps0f = 0, ps1f = 0;                                     /* ... of the iterations with every PL <= 255 */
+        int cnt = 0;
+        uint32_t tflags = 0;
+
+        auto load_group = [&](int g, int4 &v0, int4 &v1, int4 &v2)
+        {
+            if ( 4*g + 3 < S ) { v0 = ldg128(site_pl4 + 3*g); v1 = ldg128(site_pl4 + 3*g + 1); v2 = ldg128(site_pl4 + 3*g + 2); }
+            else
+            {
+                int x[12];
+                #pragma unroll
+                for (int k=0; k<12; k++) x[k] = (4*g + k/3 < S) ? __ldg(site_pl + 12*g + k) : 0;   /* past the end: "no data" */
+                v0 = make_int4(x[0],x[1],x[2],x[3]); v1 = make_int4(x[4],x[5],x[6],x[7]); v2 = make_int4(x[8],x[9],x[10],x[11]);
+            }
+        };
+        #pragma unroll 1
+        for (int it=0; it<niter; it++)
+        {
+            const int g = it*32 + lane;
+            if ( lane < 12 )            /* 12 lines of 128 bytes = the 128 samples of iteration it+BW_PF_DIST */
+            {
+                const char *pf = reinterpret_cast<const char*>(site_pl) + (size_t)(it + BW_PF_DIST)*1536 + 128*lane;
+                if ( pf < site_end ) prefetch_l2(pf);
+            }
+            int4 v0, v1, v2;
+            load_group(g, v0, v1, v2);
+            int x[12] = { v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w };
+            uint32_t pk[3] = {0,0,0};
+#if BW_ROLL1
+            #pragma unroll 1
+            for (int j=0; j<4; j++)
+            {
+                const int pa = x[0], pb = x[1], pc = x[2];
+                #pragma unroll
+                for (int k=0; k<9; k++) x[k] = x[k+3];
+#else
+            #pragma unroll
+            for (int j=0; j<4; j++)
+            {
+                const int pa = x[3*j], pb = x[3*j+1], pc = x[3*j+2];
+#endif
+                const int orv = pa | pb | pc;
+                double sum = 1.0, val = 1.0; bool data = false;
+                uint32_t tri = 0xffffffu;                               /* escape: the general path goes back to the int32 values */
+                if ( (unsigned)orv <= 255u && (pa & pb & pc) != 255 )
+                {
+                    data = orv != 0;                                    /* PL=0,0,0: no data (mcall.c:529-537) */
+                    const double p0 = lds64c(pl2p_s + 8u*(uint32_t)pa), p1 = lds64c(pl2p_s + 8u*(uint32_t)pb), p2 = lds64c(pl2p_s + 8u*(uint32_t)pc);
+                    sum = __dadd_rn(__dadd_rn(p0, p1), p2);
+                    val = fma(cf2, p1, fma(cf1, p0, cf0*p2));
+                    ps0f += pa; ps1f += pc;
+                    tri = (uint32_t)pa | (uint32_t)pb<<8 | (uint32_t)pc<<16;
+                }
+                else
+                {
+                    const int pos = atomicAdd(&rec.nesc, 1);
+                    if ( pos < BW_ESC_CAP ) rec.esc[pos] = (unsigned short)(4*g + j);      /* deferred: one lane per escaped sample */
+                    else                                                                    /* list full: right here */
+                    {
+                        BWSlow w; w.pl[0] = pa; w.pl[1] = pb; w.pl[2] = pc;
+                        data = bw_slow_sample_ni(&w, unseen, pl2p_s, a.tab, &tflags);
+                        if ( data ) { ps0 += w.pl[0]; ps1 += w.pl[2]; }
+                        sum = w.sum;
+                        val = fma(cf2, w.p[1], fma(cf1, w.p[0], cf0*w.p[2]));
+                    }
+                }
+                cnt += data;
+                acc_mul(accN, eN, data ? sum : 1.0);
+                acc_mul(accP, eP, (data && live) ? val : 1.0);
+#if BW_ROLL1
+                /* 96-bit shift register: the new triple enters at the top */
+                pk[0] = __funnelshift_r(pk[0], pk[1], 24); pk[1] = __funnelshift_r(pk[1], pk[2], 24); pk[2] = (pk[2]>>24) | (tri<<8);
+#else
+                /* byte 3j+k of the 12-byte group */
+                if ( j==0 ) pk[0] |= tri;
+                if ( j==1 ) { pk[0] |= tri<<24; pk[1] |= tri>>8; }
+                if ( j==2 ) { pk[1] |= tri<<16; pk[2] |= tri>>16; }
+                if ( j==3 ) pk[2] |= tri<<8;
+#endif
+            }
+            if ( g < ngrp4 ) { sts32(buf_s + 12u*(uint32_t)g, pk[0]); sts32(buf_s + 12u*(uint32_t)g + 4u, pk[1]); sts32(buf_s + 12u*(uint32_t)g + 8u, pk[2]); }
+            nmul += 4;
+            if ( (nmul & 511)==0 ) { acc_renorm(accP, eP); acc_renorm(accN, eN); }
+        }
+        /* ---- the escaped samples, one per lane */
+        __syncwarp();
+        const int nesc = min(rec.nesc, BW_ESC_CAP);
+        const bool esc_overflow = rec.nesc > BW_ESC_CAP;
+        #pragma unroll 1
+        for (int base=0; base<nesc; base+=32)
+        {
+            double sum = 1.0, val = 1.0; bool data = false;
+            if ( base + lane < nesc )
+            {
+                const int s = rec.esc[base + lane];
+                BWSlow w; w.pl[0] = __ldg(site_pl + 3*s); w.pl[1] = __ldg(site_pl + 3*s + 1); w.pl[2] = __ldg(site_pl + 3*s + 2);
+                data = bw_slow_sample_ni(&w, unseen, pl2p_s, a.tab, &tflags);
+                if ( data ) { ps0 += w.pl[0]; ps1 += w.pl[2]; }
+                sum = w.sum;
+                val = fma(cf2, w.p[1], fma(cf1, w.p[0], cf0*w.p[2]));
+            }
+            cnt += data;
+            acc_mul(accN, eN, data ? sum : 1.0);
+            acc_mul(accP, eP, (data && live) ? val : 1.0);
+            nmul += 1;
+        }
+
+        /* ---- warp reduction (mantissa multiply, exponent add) */
+        ps0 += ps0f; ps1 += ps1f;
+        acc_renorm(accP, eP); acc_renorm(accN, eN);
+        #pragma unroll
+        for (int off=16; off; off>>=1)
+        {
+            accP = __dmul_rn(accP, __shfl_xor_sync(0xffffffffu, accP, off)); eP += __shfl_xor_sync(0xffffffffu, eP, off);
+            accN = __dmul_rn(accN, __shfl_xor_sync(0xffffffffu, accN, off)); eN += __shfl_xor_sync(0xffffffffu, eN, off);
+            ps0 += __shfl_xor_sync(0xffffffffu, ps0, off); ps1 += __shfl_xor_sync(0xffffffffu, ps1, off);
+            cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
+            tflags |= __shfl_xor_sync(0xffffffffu, tflags, off);
+        }
+        acc_renorm(accP, eP); acc_renorm(accN, eN);
+        /* every lane multiplied nmul values in (1.0 with biased exponent 1023 for absent samples); acc_renorm removed its own bias */
+        const int n_all = cnt, nm = 32*nmul;        /* nmul is warp-uniform */
+
+        /* ---- allele sets in the reference's enumeration order: lane 0 {REF}, lane 1 {ALT}, lane 2 {ALT,REF} ---- */
+        {
+            const double lnN = n_all ? bw_log(accN) + (double)(eN - 1023*nm)*LN2 : 0.0;
+            double lk = 0; bool cand = false, in_sum = false; uint32_t mask = 0;
+            if ( lane < 2 )
+            {
+                const bool set = n_all > 0;
+                lk = set ? -LN10_10*(double)(lane ? ps1 : ps0) - lnN : 0.0;
+                if ( lane>0 ) lk += a.theta;
+                cand = set; in_sum = set && lane>0; mask = 1u<<lane;
+            }
+            else if ( lane==2 )
+            {
+                const bool set = live && n_all > 0;
+                lk = set ? (bw_log(accP) + (double)(eP - 1023*nm)*LN2) - lnN : 0.0;
+                lk += a.theta;
+                cand = set; in_sum = set; mask = 3u;
+            }
+            /* first strict maximum in enumeration order (UPDATE_MAX_LKs, mcall.c:582-585) */
+            double best = cand ? lk : -CUDART_INF; int best_lane = cand ? lane : 64;
+            #pragma unroll
+            for (int off=16; off; off>>=1)
+            {
+                double ob = __shfl_xor_sync(0xffffffffu, best, off);
+                int    ol = __shfl_xor_sync(0xffffffffu, best_lane, off);
+                if ( ob > best || (ob==best && ol < best_lane) ) { best = ob; best_lane = ol; }
+            }
+            double second = (cand && lane!=best_lane) ? lk : -CUDART_INF;
+            #pragma unroll
+            for (int off=16; off; off>>=1) second = fmax(second, __shfl_xor_sync(0xffffffffu, second, off));
+            /* lk_sum = log sum exp over every evaluated set except {REF} (mcall.c:584, 614) */
+            double mx = in_sum ? lk : -CUDART_INF;
+            #pragma unroll
+            for (int off=16; off; off>>=1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+            double term = in_sum ? bw_exp(lk - mx) : 0.0;
+            #pragma unroll
+            for (int off=16; off; off>>=1) term += __shfl_xor_sync(0xffffffffu, term, off);
+            const double grp_lk_sum = mx > -CUDART_INF ? mx + bw_log(term) : -CUDART_INF;
+            const double grp_ref_lk = __shfl_sync(0xffffffffu, lk, 0);
+            const uint32_t grp_als = __shfl_sync(0xffffffffu, mask, best_lane & 31);
+
+            if ( lane==0 )
+            {
+                const bool any = best_lane < 64;
+                const uint32_t gals = any ? grp_als : 0;
+                uint32_t flags = sflags | tflags;
+                double max_qual = -CUDART_INF, lk_sum = -CUDART_INF, ref_lk = -CUDART_INF;
+                if ( any )          /* mcall.c:1553-1560 */
+                {
+                    max_qual = -4.343*(grp_ref_lk - bw_logsumexp2(grp_lk_sum, grp_ref_lk));
+                    lk_sum = grp_lk_sum; ref_lk = grp_ref_lk;
+                }
+                const double gap = any ? best - second : CUDART_INF;
+                if ( any && gap < a.tie_eps ) flags |= MCB_SITE_NEAR_TIE;
+                uint32_t als_new = gals | 1u;               /* mcall.c:1552, 1564 */
+                const int is_variant = als_new!=1;
+                const int ret_early = ((a.flag & MCB_CALL_VARONLY) && !is_variant) || (flags & MCB_SITE_NO_QS);
+                int nals_new = 1;                                                   /* mcall.c:1569-1575: the unseen allele is not counted */
+                if ( unseen!=1 )
+                {
+                    if ( a.flag & MCB_CALL_KEEPALT ) als_new |= 2u;
+                    if ( als_new & 2u ) nals_new++;
+                }
+                int amap[2];
+                amap[0] = 0; amap[1] = (als_new & 2u) ? 1 : -1;                    /* mcall.c:547-570 */
+                rec.als_map[0] = amap[0]; rec.als_map[1] = amap[1];
+                if ( unseen && (als_new & (1u<<unseen)) ) flags |= MCB_SITE_UNSEEN_SEL;
+                const int pl_dropped = als_new==1;
+                const int ref_gt = (als_new==1) || !is_variant;
+                long long off = site_off;
+                if ( a.pl_off_out )
+                {
+                    off = -1;
+                    if ( !pl_dropped && !ret_early )
+                        off = (long long)atomicAdd(a.pl_cursor, (unsigned long long)(((long long)S*(nals_new*(nals_new+1)/2) + 3) & ~3ll));
+                    a.pl_off_out[site] = off;
+                }
+                if ( pl_dropped ) flags |= MCB_SITE_PL_DROPPED;
+                if ( ref_gt ) flags |= MCB_SITE_REF_GT;
+                rec.out_off = off; rec.pl_dropped = pl_dropped; rec.ref_gt = ref_gt;
+                rec.als_new = als_new; rec.nals_new = nals_new; rec.ret_early = ret_early; rec.flags = flags;
+                rec.max_qual = max_qual; rec.lk_sum = lk_sum; rec.ref_lk = ref_lk; rec.gap = gap;
+                rec.qf[0] = qf0; rec.qf[1] = qf1;
+                /* phase-2 constants: selected alleles in ascending order and the <=3 genotypes they span */
+                const int ngt_new = nals_new*(nals_new+1)/2;
+                int sel[2] = {0,0}, ns = 0;
+                if ( gals & 1u ) sel[ns++] = 0;
+                if ( gals & 2u ) sel[ns++] = 1;
+                rec.nsel = ns; rec.jgt0 = ns>0 ? 4*gt_idx(sel[0], sel[0]) : 0;
+                int inc_dip = 0;
+                for (int xx=0; xx<2; xx++)
+                {
+                    rec.q[xx] = xx<ns ? (double)(sel[xx] ? qf1 : qf0) : 0.0;
+                    const int nx = xx<ns ? amap[sel[xx]] : 0;
+                    for (int y=0; y<=xx; y++)
+                    {
+                        const int k = xx*(xx+1)/2 + y;
+                        const int ny = y<ns ? amap[sel[y]] : 0;
+                        const int ig = gt_idx(nx, ny);
+                        if ( xx<ns && ig < ngt_new ) inc_dip |= 1<<k;
+                        /* gts[0] = smaller new allele, gts[1] = larger (mcall.c:830-831); AC: one count per allele */
+                        rec.slot_out[k] = make_int4(MCB_GT_UNPHASED(ny), MCB_GT_UNPHASED(nx), (ny==0) + (nx==0), (ny==1) + (nx==1));
+                    }
+                }
+                rec.inc_dip = inc_dip;
+            }
+        }
+        __syncwarp();
+
+        /* =========================== phase 2: per-sample genotypes ============================== */
+        if ( rec.ret_early )
+        {
+            if ( lane==0 )
+            {
+                a.ret[site] = 0;
+                if ( a.site_flags ) a.site_flags[site] = rec.flags;
+            }
+            __syncwarp();
+            continue;
+        }
+        int ac0 = 0, ac1 = 0;
+        uint32_t tflags2 = 0;
+        {
+            const bool ref_gt = rec.ref_gt, pl_dropped = rec.pl_dropped;
+            const bool pl3 = rec.nals_new==2;       /* both alleles kept: the PL vector is copied; else (unseen ALT selected) PL[0] only */
+            int32_t *out_pl = (a.out_pl && !pl_dropped) ? a.out_pl + rec.out_off : nullptr;
+            int32_t *out_gt = a.gt ? a.gt + 2*(size_t)site*S : nullptr;
+            int32_t *out_gq = want_gq ? a.gq + (size_t)site*S : nullptr;
+            BWConsts c;
+            c.q0 = rec.q[0]; c.q1 = rec.q[1]; c.slot_s = wbase_s + (uint32_t)offsetof(BWRec, slot_out); c.thr_s = thr_s;
+            c.nsel = rec.nsel; c.jgt0 = rec.jgt0; c.inc_dip = rec.inc_dip; c.want_gq = want_gq;
+
+            #pragma unroll 1
+            for (int it=0; it<niter; it++)
+            {
+                const int g = it*32 + lane;
+                if ( it < BW_PF_DIST && lane < 12 && next_pl && (it*1536 + 128*lane) < S*12 ) prefetch_l2(next_pl + it*1536 + 128*lane);
+                if ( g >= ngrp4 ) continue;
+                uint32_t u0 = ldsu32(buf_s + 12u*(uint32_t)g), u1 = ldsu32(buf_s + 12u*(uint32_t)g + 4u), u2 = ldsu32(buf_s + 12u*(uint32_t)g + 8u);
+                const int s4 = 4*g, nv = min(4, S - s4);
+                if ( out_pl )           /* mcall.c:1158-1194: both alleles kept, the PL vector is copied.  Escaped samples are */
+                {                       /* rewritten below by the same thread with their filled int32 values.                 */
+                    int32_t *d = out_pl + 3*(size_t)s4;
+                    if ( !pl3 )
+                    {
+                        #pragma unroll
+                        for (int j=0; j<4; j++)
+                            if ( j < nv ) stg32(out_pl + s4 + j, (int)byte_of(3*j<4 ? u0 : (3*j<8 ? u1 : u2), (3*j) & 3));
+                    }
+                    else if ( nv==4 )
+                    {
+                        stg128(d,     (int)byte_of(u0,0), (int)byte_of(u0,1), (int)byte_of(u0,2), (int)byte_of(u0,3));
+                        stg128(d + 4, (int)byte_of(u1,0), (int)byte_of(u1,1), (int)byte_of(u1,2), (int)byte_of(u1,3));
+                        stg128(d + 8, (int)byte_of(u2,0), (int)byte_of(u2,1), (int)byte_of(u2,2), (int)byte_of(u2,3));
+                    }
+                    else
+                    {
+                        #pragma unroll
+                        for (int k=0; k<12; k++)
+                            if ( k/3 < nv ) stg32(d + k, (int)byte_of(k<4 ? u0 : (k<8 ? u1 : u2), k & 3));
+                    }
+                }
+                #pragma unroll (kBwUnroll2)
+                for (int j=0; j<nv; j++)
+                {
+                    const int s = s4 + j;
+                    const uint32_t pa = u0 & 0xffu, pb = (u0>>8) & 0xffu, pc = (u0>>16) & 0xffu;
+                    u0 = __funnelshift_r(u0, u1, 24); u1 = __funnelshift_r(u1, u2, 24); u2 >>= 24;    /* next sample's triple */
+                    int4 outc; int q = 0;
+                    if ( (pa & pb & pc) != 255u )
+                    {
+                        if ( ref_gt ) outc = make_int4(MCB_GT_UNPHASED(0), MCB_GT_UNPHASED(0), 2, 0);         /* mcall.c:713-743 */
+                        else
+                        {
+                            const double p0 = lds64c(pl2p_s + 8u*pa), p1 = lds64c(pl2p_s + 8u*pb), p2 = lds64c(pl2p_s + 8u*pc);
+                            const double sum = __dadd_rn(__dadd_rn(p0, p1), p2);
+                            outc = bw_call_sample<true>(p0, p1, p2, sum, c, q);
+                        }
+                        if ( (pa | pb | pc)==0 ) { outc = make_int4(MCB_GT_MISSING, MCB_GT_MISSING, 0, 0); q = 0; }
+                    }
+                    else if ( !esc_overflow ) continue;     /* on the escape list: called after this loop */
+                    else                /* list overflowed: general path on the original values, right here */
+                    {
+                        BWSlow w; w.pl[0] = __ldg(site_pl + 3*s); w.pl[1] = __ldg(site_pl + 3*s + 1); w.pl[2] = __ldg(site_pl + 3*s + 2);
+                        const bool has = bw_slow_sample_ni(&w, unseen, pl2p_s, a.tab, &tflags2);
+                        outc = make_int4(MCB_GT_MISSING, MCB_GT_MISSING, 0, 0);
+                        if ( !has ) { }
+                        else if ( ref_gt ) outc = make_int4(MCB_GT_UNPHASED(0), MCB_GT_UNPHASED(0), 2, 0);
+                        else outc = bw_call_sample<false>(w.p[0], w.p[1], w.p[2], w.sum, c, q);
+                        if ( out_pl )
+                        {
+                            if ( pl3 ) { int32_t *d = out_pl + 3*(size_t)s; stg32(d, w.pl[0]); stg32(d+1, w.pl[1]); stg32(d+2, w.pl[2]); }
+                            else stg32(out_pl + s, w.pl[0]);
+                        }
+                    }
+                    ac0 += outc.z; ac1 += outc.w;
+                    if ( out_gt ) stg64(out_gt + 2*(size_t)s, outc.x, outc.y);
+                    if ( out_gq ) stg32(out_gq + s, q);
+                }
+            }
+            /* ---- the escaped samples, one per lane (their PL rows overwrite the 255s stored above: order the stores) */
+            __syncwarp();
+            if ( !esc_overflow )
+            {
+                #pragma unroll 1
+                for (int base=0; base<nesc; base+=32)
+                {
+                    if ( base + lane >= nesc ) continue;
+                    const int s = rec.esc[base + lane];
+                    BWSlow w; w.pl[0] = __ldg(site_pl + 3*s); w.pl[1] = __ldg(site_pl + 3*s + 1); w.pl[2] = __ldg(site_pl + 3*s + 2);
+                    const bool has = bw_slow_sample_ni(&w, unseen, pl2p_s, a.tab, &tflags2);
+                    int4 outc = make_int4(MCB_GT_MISSING, MCB_GT_MISSING, 0, 0); int q = 0;
+                    if ( !has ) { }
+                    else if ( ref_gt ) outc = make_int4(MCB_GT_UNPHASED(0), MCB_GT_UNPHASED(0), 2, 0);
+                    else outc = bw_call_sample<false>(w.p[0], w.p[1], w.p[2], w.sum, c, q);
+                    ac0 += outc.z; ac1 += outc.w;
+                    if ( out_gt ) stg64(out_gt + 2*(size_t)s, outc.x, outc.y);
+                    if ( out_gq ) stg32(out_gq + s, q);
+                    if ( out_pl )
+                    {
+                        if ( pl3 ) { int32_t *d = out_pl + 3*(size_t)s; stg32(d, w.pl[0]); stg32(d+1, w.pl[1]); stg32(d+2, w.pl[2]); }
+                        else stg32(out_pl + s, w.pl[0]);
+                    }
+                }
+            }
+        }
+        #pragma unroll
+        for (int off=16; off; off>>=1)
+        {
+            ac0 += __shfl_xor_sync(0xffffffffu, ac0, off); ac1 += __shfl_xor_sync(0xffffffffu, ac1, off);
+            tflags2 |= __shfl_xor_sync(0xffffffffu, tflags2, off);
+        }
+
+        /* ---- site record: QUAL (mcall.c:1631-1645), AC/AN (1648-1650) ---------------------------------- */
+        if ( lane==0 )
+        {
+            const int nals_new = rec.nals_new;
+            int nAC = 0;
+            if ( !rec.ref_gt && nals_new>1 ) nAC = ac1;
+            int ret = nals_new;
+            if ( !rec.ref_gt && !nAC && (a.flag & MCB_CALL_VARONLY) ) ret = 0;      /* mcall.c:1618 */
+            float qual;
+            if ( nAC ) qual = (float)rec.max_qual;
+            else if ( rec.lk_sum != -CUDART_INF ) qual = (float)(-4.343*(rec.lk_sum - bw_logsumexp2(rec.lk_sum, rec.ref_lk)));
+            else if ( ac0 ) qual = a.theta ? (float)(-4.343*a.theta) : 0.f;
+            else qual = __uint_as_float(MCB_FLOAT_MISSING_BITS);
+            a.ret[site] = ret;
+            if ( a.als_new ) a.als_new[site] = rec.als_new;
+            if ( a.als_map ) for (int j=0; j<a.max_nals; j++) a.als_map[(size_t)site*a.max_nals + j] = j<2 ? (int8_t)rec.als_map[j] : (int8_t)-1;
+            if ( a.qual ) a.qual[site] = qual;
+            if ( a.ac ) for (int j=0; j<a.max_nals; j++) a.ac[(size_t)site*a.max_nals + j] = j==0 ? ac0 : ((j==1 && nals_new>1) ? ac1 : 0);
+            if ( a.an ) a.an[site] = nAC + ac0;
+            if ( a.site_flags ) a.site_flags[site] = rec.flags | tflags2;
+            if ( a.diag ) { double *d = a.diag + (size_t)site*4; d[0] = rec.max_qual; d[1] = rec.lk_sum; d[2] = rec.ref_lk; d[3] = rec.gap; }
+        }
+        __syncwarp();
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ *  launcher
+ * ---------------------------------------------------------------------------------------------- */
+size_t biallelic_warp_bytes(int nsmpl)
+{
+    return BW_REC_BYTES + (((size_t)3*(((size_t)nsmpl + 3) & ~(size_t)3) + 15) & ~(size_t)15) ;
+}
+size_t biallelic_smem_bytes(int nsmpl, int nwarp)
+{
+    return align128(sizeof(BWTables)) + (size_t)nwarp*biallelic_warp_bytes(nsmpl);
+}
+int biallelic_max_warps() { return BW_MAXWARP; }
+int biallelic_ctas_per_sm() { return BW_MINCTA; }
+
+cudaError_t launch_biallelic_warp_kernel(const KArgs &a, int grid, int nwarp, cudaStream_t st)
+{
+    const size_t smem = biallelic_smem_bytes(a.nsmpl, nwarp);
+    cudaError_t e = cudaFuncSetAttribute(mcall_biallelic_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if ( e != cudaSuccess ) return e;
+    mcall_biallelic_warp_kernel<<<grid, nwarp*32, smem, st>>>(a, (int)biallelic_warp_bytes(a.nsmpl));
+    return cudaGetLastError();
+}
+
+}   // namespace mcb

@@ -204,6 +204,32 @@ def test_idle_warps_do_not_index_the_table_with_sentinels(int16, oracle_built):
     assert parity.compare(got, exp, pr)["compared"] > 0
 
 
+@pytest.mark.parametrize("flag", [0, abi.CALL_VARONLY, abi.CALL_KEEPALT])
+@pytest.mark.parametrize("S", [1, 3, 4, 37, 128, 131, 1001, 2504, 4000])
+def test_biallelic_warp_kernel(S, flag, oracle_built):
+    """The warp-per-site kernel of the two-allele class (mcall_biallelic.cu): sample counts around its 4-sample lane
+    groups and 128-sample iterations (odd totals take the unaligned store path), missing / vector_end / PL >= 256
+    values (general-path iterations), an unseen ALT (`<*>` selected: one PL per sample is kept), zero QS entries,
+    compacted and in-place PL output.  Forced on with warp2=<warps per CTA>; compared with the oracle and with the
+    tiled kernel."""
+    from bcftools_b200 import mcall
+    rng = np.random.default_rng([S, flag, 11])
+    R = 96 if S < 1000 else 40
+    batch = parity.random_batch(rng, R, S, 2, minA=2, pl_max=300 if S in (37, 131) else 256)
+    batch.unseen[rng.random(R) < 0.25] = 1
+    for i in range(0, R, 7):            # clean sites: every iteration on the packed fast path
+        blk = batch.site_pl(i)
+        blk[...] = rng.integers(0, 256, blk.shape)
+        blk[np.arange(S), rng.integers(0, 3, S)] = 0
+    params = abi.CallParams(S, 2, flag=flag, output_tags=abi.CALL_FMT_GQ)
+    exp, _ = oracle_built.call("port", params, batch, None)
+    for opts, compact in (({"warp2": 12}, False), ({"warp2": 3}, True), ({"warp2": 0}, False)):
+        with mcall.MCaller(params, options=opts) as mc:
+            got = mc.call_host(batch, compact=compact)
+        st = parity.compare(got, exp, params)
+        assert st["compared"] > 0, (opts, st)
+
+
 def test_compacted_pl_output(oracle_built):
     """mcb_result.pl_off_out: trimmed PL blocks packed at the front of the output buffer (what leaves the device in
     the host path); content must be identical to the in-place layout, several slabs per call."""
