@@ -22,6 +22,9 @@
 
 namespace mcb {
 
+#ifndef BW_P2_LANE_SAMPLES
+#define BW_P2_LANE_SAMPLES 1            /* phase 2: lanes take consecutive samples (coalesced stores) instead of 4-sample groups */
+#endif
 #ifndef BW_ROLL1
 #define BW_ROLL1     0                  /* 1: phase-1 sample loop rolled (smaller code) */
 #endif
@@ -35,6 +38,9 @@ namespace mcb {
 #define BW_MINCTA    2
 #endif
 #define BW_ESC_CAP   64                 /* escaped samples per site handled lane-parallel after the main loops */
+#ifndef BW_PF_NEXT
+#define BW_PF_NEXT   0                  /* 128-sample blocks of the warp's next site prefetched into L2 during phase 2 */
+#endif
 #ifndef BW_PF_DIST
 #define BW_PF_DIST   4                  /* L2 prefetch distance of phase 1, in 128-sample iterations */
 #endif
@@ -215,6 +221,7 @@ __device__ __forceinline__ void stg32(void *p, int x)
 __device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ uint32_t ldsu32(uint32_t a) { uint32_t v; asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
+__device__ __forceinline__ uint32_t ldsu8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ uint32_t byte_of(uint32_t w, int k) { return (w >> (8*k)) & 0xffu; }
 
 __global__ void __launch_bounds__(BW_MAXWARP*32, BW_MINCTA) mcall_biallelic_warp_kernel(const KArgs a, int warp_bytes)
@@ -553,11 +560,58 @@ __global__ void __launch_bounds__(BW_MAXWARP*32, BW_MINCTA) mcall_biallelic_warp
             c.q0 = rec.q[0]; c.q1 = rec.q[1]; c.slot_s = wbase_s + (uint32_t)offsetof(BWRec, slot_out); c.thr_s = thr_s;
             c.nsel = rec.nsel; c.jgt0 = rec.jgt0; c.inc_dip = rec.inc_dip; c.want_gq = want_gq;
 
+#if BW_P2_LANE_SAMPLES
+            /* lanes take consecutive samples: GT / GQ / PL rows of a warp are contiguous, every store instruction writes whole sectors */
+            const int nit2 = (S + 31) >> 5;
+            #pragma unroll 1
+            for (int it=0; it<nit2; it++)
+            {
+                if ( it < BW_PF_NEXT && lane < 12 && next_pl && (it*1536 + 128*lane) < S*12 ) prefetch_l2(next_pl + it*1536 + 128*lane);
+                const int s = it*32 + lane;
+                if ( s >= S ) continue;
+                const uint32_t pa = ldsu8(buf_s + 3u*(uint32_t)s), pb = ldsu8(buf_s + 3u*(uint32_t)s + 1u), pc = ldsu8(buf_s + 3u*(uint32_t)s + 2u);
+                if ( out_pl )           /* mcall.c:1158-1194: both alleles kept, the PL vector is copied.  Escaped samples */
+                {                       /* are rewritten after the loop with their filled int32 values.                    */
+                    if ( pl3 ) { int32_t *d = out_pl + 3*(size_t)s; stg32(d, (int)pa); stg32(d+1, (int)pb); stg32(d+2, (int)pc); }
+                    else stg32(out_pl + s, (int)pa);
+                }
+                int4 outc; int q = 0;
+                if ( (pa & pb & pc) != 255u )
+                {
+                    if ( ref_gt ) outc = make_int4(MCB_GT_UNPHASED(0), MCB_GT_UNPHASED(0), 2, 0);         /* mcall.c:713-743 */
+                    else
+                    {
+                        const double p0 = lds64c(pl2p_s + 8u*pa), p1 = lds64c(pl2p_s + 8u*pb), p2 = lds64c(pl2p_s + 8u*pc);
+                        const double sum = __dadd_rn(__dadd_rn(p0, p1), p2);
+                        outc = bw_call_sample<true>(p0, p1, p2, sum, c, q);
+                    }
+                    if ( (pa | pb | pc)==0 ) { outc = make_int4(MCB_GT_MISSING, MCB_GT_MISSING, 0, 0); q = 0; }
+                }
+                else if ( !esc_overflow ) continue;     /* on the escape list: called after this loop */
+                else                /* list overflowed: general path on the original values, right here */
+                {
+                    BWSlow w; w.pl[0] = __ldg(site_pl + 3*s); w.pl[1] = __ldg(site_pl + 3*s + 1); w.pl[2] = __ldg(site_pl + 3*s + 2);
+                    const bool has = bw_slow_sample_ni(&w, unseen, pl2p_s, a.tab, &tflags2);
+                    outc = make_int4(MCB_GT_MISSING, MCB_GT_MISSING, 0, 0);
+                    if ( !has ) { }
+                    else if ( ref_gt ) outc = make_int4(MCB_GT_UNPHASED(0), MCB_GT_UNPHASED(0), 2, 0);
+                    else outc = bw_call_sample<false>(w.p[0], w.p[1], w.p[2], w.sum, c, q);
+                    if ( out_pl )
+                    {
+                        if ( pl3 ) { int32_t *d = out_pl + 3*(size_t)s; stg32(d, w.pl[0]); stg32(d+1, w.pl[1]); stg32(d+2, w.pl[2]); }
+                        else stg32(out_pl + s, w.pl[0]);
+                    }
+                }
+                ac0 += outc.z; ac1 += outc.w;
+                if ( out_gt ) stg64(out_gt + 2*(size_t)s, outc.x, outc.y);
+                if ( out_gq ) stg32(out_gq + s, q);
+            }
+#else
             #pragma unroll 1
             for (int it=0; it<niter; it++)
             {
                 const int g = it*32 + lane;
-                if ( it < BW_PF_DIST && lane < 12 && next_pl && (it*1536 + 128*lane) < S*12 ) prefetch_l2(next_pl + it*1536 + 128*lane);
+                if ( it < BW_PF_NEXT && lane < 12 && next_pl && (it*1536 + 128*lane) < S*12 ) prefetch_l2(next_pl + it*1536 + 128*lane);
                 if ( g >= ngrp4 ) continue;
                 uint32_t u0 = ldsu32(buf_s + 12u*(uint32_t)g), u1 = ldsu32(buf_s + 12u*(uint32_t)g + 4u), u2 = ldsu32(buf_s + 12u*(uint32_t)g + 8u);
                 const int s4 = 4*g, nv = min(4, S - s4);
@@ -621,6 +675,7 @@ __global__ void __launch_bounds__(BW_MAXWARP*32, BW_MINCTA) mcall_biallelic_warp
                     if ( out_gq ) stg32(out_gq + s, q);
                 }
             }
+#endif
             /* ---- the escaped samples, one per lane (their PL rows overwrite the 255s stored above: order the stores) */
             __syncwarp();
             if ( !esc_overflow )

@@ -13,7 +13,7 @@ synthetic sites replicated x4 in HBM = 65,536 sites, 2.9 GB of PL; the 1M-site j
   value     device-resident throughput: inputs already in HBM, CUDA events on the launching stream, max over ranks
   e2e       the same metric through the C-ABI host entry point mcb_call_host with pinned HOST buffers:
             H2D of the PL slab + kernels + D2H of GT/GQ/PL/site records inside the timed region
-  roofline  dominant kernel (mcall_site_kernel<2 alleles>): algorithmic bytes of its sites / its own device time
+  roofline  dominant kernel (mcall_biallelic_warp_kernel, the two-allele class): algorithmic bytes of its sites / its own device time
   cpu_baseline  the CPU oracle on this box's host cores on a bounded sample of the same workload (rank 0, N=1)
 
 The reference arm times the reference's own CPU implementation of the path (oracle/_ref = the unmodified mcall.c
@@ -176,6 +176,38 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
+def bind_to_gpu_numa_node(gpu_index):
+    """Multi-GPU runs: keep this rank's threads (and therefore its first-touched pinned buffers) on the CPUs NVML reports
+    as local to the GPU, so that N ranks do not push their PCIe traffic through one socket.  Best effort."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return 0
+
+
+def ncu_traffic(sites_per_step):
+    """DRAM bytes (read + write) of one launch of the dominant kernel, from the committed `ncu --set full` capture of this
+    same command (profiles/r01_ncu_dominant_kernel.json); None when the capture was taken on another step size."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_ncu_dominant_kernel.json")
+    try:
+        d = json.load(open(path))
+    except (OSError, ValueError):
+        return None, "no ncu capture committed"
+    if d.get("sites_per_step") != sites_per_step:
+        return None, "ncu capture is for %s sites per step" % d.get("sites_per_step")
+    return int(d["dram_bytes_read"] + d["dram_bytes_write"]), d.get("source", path)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -206,6 +238,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    numa_cpus = bind_to_gpu_numa_node(local_rank) if world > 1 else 0
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -299,6 +332,7 @@ def main():
         d2h = sum(getattr(hres, k).nbytes for k in ("ret", "als_new", "als_map", "qual", "ac", "an", "site_flags", "diag", "gt", "gq", "pl_off_out")
                   if getattr(hres, k) is not None) + 4 * int(mc.stats()[2])        # + the used (compacted) part of the PL buffer
         e2e = dict(value=world * args.steps * ne * params.nsmpl / dt, unit=UNIT, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
+                   host_cpus_bound_per_rank=numa_cpus,
                    sites_per_step=ne, ms_per_step=1e3 * dt / args.steps, pl_transport="int32 (bcf_get_format_int32 layout)")
         # secondary: the same call with the PL slab shipped as BCF int16 typed vectors (mcb_batch.pl_type=2)
         sub16 = mcall.pin_batch(hb.subset(range(ne)).to_int16())
@@ -337,8 +371,10 @@ def main():
             rd2, wr2 = synth.algorithmic_bytes(sub2, res2, params.output_tags)
             bytes2 = (rd2 + wr2) * args.replicate
             ach = bytes2 / (ktimes[2] * 1e-3) / 1e9
-            roof = dict(bound="hbm", kernel="mcall_site_kernel<NALS=2> (70 % of the sites of a step)", achieved=ach, peak=peak, unit="GB/s",
-                        frac=ach / peak, traffic=None, peak_source=peak_src, algorithmic_bytes_per_launch=int(bytes2),
+            traffic, traffic_src = ncu_traffic(db.nsites)
+            roof = dict(bound="hbm", kernel="mcall_biallelic_warp_kernel (the two-allele class: 70 % of the sites of a step)", achieved=ach, peak=peak,
+                        unit="GB/s", frac=ach / peak, traffic=traffic, traffic_source=traffic_src, peak_source=peak_src,
+                        algorithmic_bytes_per_launch=int(bytes2),
                         kernel_ms=float(ktimes[2]), kernel_share_of_step=float(ktimes[2] / ktimes[0]),
                         all_kernels=dict(achieved=(rd_all + wr_all) * args.replicate / (ktimes[0] * 1e-3) / 1e9,
                                          ms_per_class={str(k): float(ktimes[k]) for k in range(1, 6)}))
