@@ -460,7 +460,8 @@ static int enqueue(mcb_ctx *ctx, const mcb_batch *b, const mcb_result *r, int32_
     {
         if ( timing ) nals = 6 - nals;      /* timing mode keeps the ascending order of the event list */
         size_t ring; tile_geometry(ctx, nals, pl_es, &a.tile_smpl, &a.nstage, &ring);
-        const int block = pl_es==2 ? 128 : class_block(ctx, nals);
+        const bool gpk = a.gp && (a.output_tags & MCB_CALL_FMT_GP);
+        const int block = (pl_es==2 || gpk) ? 128 : class_block(ctx, nals);
         a.site_list = lists + (size_t)nals*list_stride; a.site_count = counts + nals;
         /* two alleles, everything diploid, int32 PLs, no GP: one warp per site over a byte-packed shared-memory copy */
         int bw_warps = 0;
@@ -494,14 +495,14 @@ static int enqueue(mcb_ctx *ctx, const mcb_batch *b, const mcb_result *r, int32_
             continue;
         }
         int nb = 1;
-        CK(site_kernel_occupancy(nals, ploidy, block, pl_es, ring, &nb));
+        CK(site_kernel_occupancy(nals, ploidy, gpk, block, pl_es, ring, &nb));
         if ( nb<1 ) return cuda_fail(ctx, cudaErrorLaunchOutOfResources, "site kernel does not fit on an SM");
         if ( ctx->opt_blocks_per_sm>0 ) nb = std::min<int>(nb, (int)ctx->opt_blocks_per_sm);
         int grid = (int)std::min<int64_t>((int64_t)b->nsites, (int64_t)ctx->nsm*nb);
         cudaStream_t cs = fork ? ctx->cstream[nals] : st;
         if ( fork ) CK(cudaStreamWaitEvent(cs, ctx->cev_fork, 0));
         {
-            cudaError_t le = launch_site_kernel(nals, ploidy, block, pl_es, a, grid, ring, cs);
+            cudaError_t le = launch_site_kernel(nals, ploidy, gpk, block, pl_es, a, grid, ring, cs);
             if ( le==cudaSuccess && getenv("MCB_DEBUG_SYNC") ) le = cudaStreamSynchronize(cs);
             if ( le!=cudaSuccess )
             {

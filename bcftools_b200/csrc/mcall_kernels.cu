@@ -173,7 +173,7 @@ template<int NALS, int BLOCK> struct MinBlocks
     static constexpr int value  = BLOCK==256 ? per256 : (BLOCK==128 ? per128 : (BLOCK==64 ? (2*per128 > 32 ? 32 : 2*per128) : (4*per128 > 32 ? 32 : 4*per128)));
 };
 
-template<int NALS, bool PLOIDY, int BLOCK, typename PT>
+template<int NALS, bool PLOIDY, int BLOCK, typename PT, bool GPOUT>
 __global__ void __launch_bounds__(BLOCK, (MinBlocks<NALS,BLOCK>::value)) mcall_site_kernel(const KArgs a)
 {
     using PLT = PLType<PT>;
@@ -701,7 +701,8 @@ __global__ void __launch_bounds__(BLOCK, (MinBlocks<NALS,BLOCK>::value)) mcall_s
             const int nals_new = sh.nals_new, ngt_new = nals_new*(nals_new+1)/2, grp_nals = sh.grp_nals;
             const bool ref_gt = sh.ref_gt, pl_dropped = sh.pl_dropped;
             const bool want_gq = a.gq && (a.output_tags & (MCB_CALL_FMT_GQ|MCB_CALL_FMT_GP));
-            const bool want_gp = a.gp && (a.output_tags & MCB_CALL_FMT_GP) && !ref_gt;
+            /* FORMAT/GP is compiled into its own instances: its code in the sample loop costs the GP-less kernels 2-6 % */
+            const bool want_gp = GPOUT && a.gp && (a.output_tags & MCB_CALL_FMT_GP) && !ref_gt;
             const bool want_gqm = want_gq || want_gp;       /* the max/sum arithmetic is shared by GQ and GP */
             int32_t *out_pl = (a.out_pl && !pl_dropped) ? a.out_pl + sh.out_off : nullptr;
             float   *out_gp = want_gp ? a.gp + sh.out_off : nullptr;
@@ -1064,20 +1065,20 @@ __global__ void unsupported_sites_kernel(const int32_t *list, const int32_t *cou
     }
 }
 
-template<int NALS, bool PLOIDY, int BLOCK, typename PT>
+template<int NALS, bool PLOIDY, int BLOCK, typename PT, bool GPOUT>
 static cudaError_t launch_one(const KArgs &a, int grid, size_t ring_bytes, cudaStream_t st)
 {
-    auto kern = mcall_site_kernel<NALS,PLOIDY,BLOCK,PT>;
+    auto kern = mcall_site_kernel<NALS,PLOIDY,BLOCK,PT,GPOUT>;
     const size_t smem = align128(sizeof(Shared<NALS,BLOCK>)) + ring_bytes;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if ( e!=cudaSuccess ) return e;
     kern<<<grid, BLOCK, smem, st>>>(a);
     return cudaGetLastError();
 }
-template<int NALS, bool PLOIDY, int BLOCK, typename PT>
+template<int NALS, bool PLOIDY, int BLOCK, typename PT, bool GPOUT>
 static cudaError_t occ_one(size_t ring_bytes, int *nb)
 {
-    auto kern = mcall_site_kernel<NALS,PLOIDY,BLOCK,PT>;
+    auto kern = mcall_site_kernel<NALS,PLOIDY,BLOCK,PT,GPOUT>;
     const size_t smem = align128(sizeof(Shared<NALS,BLOCK>)) + ring_bytes;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if ( e!=cudaSuccess ) return e;
@@ -1085,42 +1086,48 @@ static cudaError_t occ_one(size_t ring_bytes, int *nb)
 }
 /*  one dispatcher for launch (nb==NULL) and occupancy query (nb!=NULL)  */
 template<int NALS>
-static cudaError_t dispatch(bool ploidy, int block, int pl_es, const KArgs *a, int grid, size_t ring_bytes, cudaStream_t st, int *nb)
+static cudaError_t dispatch(bool ploidy, bool gp, int block, int pl_es, const KArgs *a, int grid, size_t ring_bytes, cudaStream_t st, int *nb)
 {
-#define MCB_CASE(P,B,T) return nb ? occ_one<NALS,P,B,T>(ring_bytes, nb) : launch_one<NALS,P,B,T>(*a, grid, ring_bytes, st)
+#define MCB_CASE(P,B,T,GP) return nb ? occ_one<NALS,P,B,T,GP>(ring_bytes, nb) : launch_one<NALS,P,B,T,GP>(*a, grid, ring_bytes, st)
+    if ( gp )               /* FORMAT/GP: one instance per shape and element type (any ploidy, 128-thread CTAs) */
+    {
+        if ( pl_es==4 ) MCB_CASE(true,128,int32_t,true);
+        if ( pl_es==2 ) MCB_CASE(true,128,int16_t,true);
+        return cudaErrorInvalidValue;
+    }
     if ( pl_es==4 )
     {
-        if ( block==32 )  { if ( ploidy ) MCB_CASE(true,32,int32_t);  MCB_CASE(false,32,int32_t); }
-        if ( block==64 )  { if ( ploidy ) MCB_CASE(true,64,int32_t);  MCB_CASE(false,64,int32_t); }
-        if ( block==128 ) { if ( ploidy ) MCB_CASE(true,128,int32_t); MCB_CASE(false,128,int32_t); }
-        if ( block==256 ) { if ( ploidy ) MCB_CASE(true,256,int32_t); MCB_CASE(false,256,int32_t); }
+        if ( block==32 )  { if ( ploidy ) MCB_CASE(true,32,int32_t,false);  MCB_CASE(false,32,int32_t,false); }
+        if ( block==64 )  { if ( ploidy ) MCB_CASE(true,64,int32_t,false);  MCB_CASE(false,64,int32_t,false); }
+        if ( block==128 ) { if ( ploidy ) MCB_CASE(true,128,int32_t,false); MCB_CASE(false,128,int32_t,false); }
+        if ( block==256 ) { if ( ploidy ) MCB_CASE(true,256,int32_t,false); MCB_CASE(false,256,int32_t,false); }
     }
     if ( pl_es==2 )         /* BCF int16 typed vectors: 128-thread CTAs only */
     {
-        if ( ploidy ) MCB_CASE(true,128,int16_t); MCB_CASE(false,128,int16_t);
+        if ( ploidy ) MCB_CASE(true,128,int16_t,false); MCB_CASE(false,128,int16_t,false);
     }
 #undef MCB_CASE
     return cudaErrorInvalidValue;
 }
-static cudaError_t dispatch_nals(int nals, bool ploidy, int block, int pl_es, const KArgs *a, int grid, size_t ring_bytes, cudaStream_t st, int *nb)
+static cudaError_t dispatch_nals(int nals, bool ploidy, bool gp, int block, int pl_es, const KArgs *a, int grid, size_t ring_bytes, cudaStream_t st, int *nb)
 {
     switch ( nals )
     {
-        case 1: return dispatch<1>(ploidy, block, pl_es, a, grid, ring_bytes, st, nb);
-        case 2: return dispatch<2>(ploidy, block, pl_es, a, grid, ring_bytes, st, nb);
-        case 3: return dispatch<3>(ploidy, block, pl_es, a, grid, ring_bytes, st, nb);
-        case 4: return dispatch<4>(ploidy, block, pl_es, a, grid, ring_bytes, st, nb);
-        case 5: return dispatch<5>(ploidy, block, pl_es, a, grid, ring_bytes, st, nb);
+        case 1: return dispatch<1>(ploidy, gp, block, pl_es, a, grid, ring_bytes, st, nb);
+        case 2: return dispatch<2>(ploidy, gp, block, pl_es, a, grid, ring_bytes, st, nb);
+        case 3: return dispatch<3>(ploidy, gp, block, pl_es, a, grid, ring_bytes, st, nb);
+        case 4: return dispatch<4>(ploidy, gp, block, pl_es, a, grid, ring_bytes, st, nb);
+        case 5: return dispatch<5>(ploidy, gp, block, pl_es, a, grid, ring_bytes, st, nb);
     }
     return cudaErrorInvalidValue;
 }
-cudaError_t launch_site_kernel(int nals, bool ploidy, int block, int pl_es, const KArgs &a, int grid, size_t ring_bytes, cudaStream_t st)
+cudaError_t launch_site_kernel(int nals, bool ploidy, bool gp, int block, int pl_es, const KArgs &a, int grid, size_t ring_bytes, cudaStream_t st)
 {
-    return dispatch_nals(nals, ploidy, block, pl_es, &a, grid, ring_bytes, st, nullptr);
+    return dispatch_nals(nals, ploidy, gp, gp ? 128 : block, pl_es, &a, grid, ring_bytes, st, nullptr);
 }
-cudaError_t site_kernel_occupancy(int nals, bool ploidy, int block, int pl_es, size_t ring_bytes, int *nb)
+cudaError_t site_kernel_occupancy(int nals, bool ploidy, bool gp, int block, int pl_es, size_t ring_bytes, int *nb)
 {
-    return dispatch_nals(nals, ploidy, block, pl_es, nullptr, 0, ring_bytes, nullptr, nb);
+    return dispatch_nals(nals, ploidy, gp, gp ? 128 : block, pl_es, nullptr, 0, ring_bytes, nullptr, nb);
 }
 
 cudaError_t launch_classify(const uint8_t *nals, int nsites, int32_t *lists, int32_t *counts, int list_stride, cudaStream_t st)

@@ -67,10 +67,10 @@ struct KArgs
 
 namespace mcb {
 /*  launchers implemented in mcall_kernels.cu  */
-cudaError_t launch_site_kernel(int nals, bool ploidy, int block, int pl_es, const KArgs &a, int grid, size_t ring_bytes, cudaStream_t st);
+cudaError_t launch_site_kernel(int nals, bool ploidy, bool gp, int block, int pl_es, const KArgs &a, int grid, size_t ring_bytes, cudaStream_t st);
 cudaError_t launch_classify(const uint8_t *nals, int nsites, int32_t *lists, int32_t *counts, int list_stride, cudaStream_t st);
 cudaError_t launch_unsupported(const int32_t *list, const int32_t *count, int32_t *ret, uint32_t *site_flags, const uint8_t *nals, cudaStream_t st);
-cudaError_t site_kernel_occupancy(int nals, bool ploidy, int block, int pl_es, size_t ring_bytes, int *blocks_per_sm);
+cudaError_t site_kernel_occupancy(int nals, bool ploidy, bool gp, int block, int pl_es, size_t ring_bytes, int *blocks_per_sm);
 size_t groups_scratch_bytes(int grid, int ngroups);
 cudaError_t launch_groups_kernel(int nals, const KArgs &a, void *scratch, int grid, cudaStream_t st);
 void generic_scratch_bytes(int grid, int ngroups, int nsmpl, size_t *grp, size_t *pl, size_t *sum);
