@@ -86,7 +86,7 @@ void b200_mcall_init(b200_call_t *call)
     b->res.site_flags = (uint32_t*) pinned(4*(size_t)R);  b->res.diag = NULL;
     b->res.gt = (int32_t*) pinned(8*(size_t)R*S);
     b->res.gq = (p.output_tags & (CALL_FMT_GQ|CALL_FMT_GP)) ? (int32_t*) pinned(4*(size_t)R*S) : NULL;
-    b->res.gp = NULL;
+    b->res.gp = (p.output_tags & CALL_FMT_GP) ? (float*) pinned((size_t)b->pl_cap*4) : NULL;
     b->res.pl = (int32_t*) pinned((size_t)b->pl_cap*4);
     b->res.pl_off_out = (int64_t*) pinned(sizeof(int64_t)*R);
     b->last_ploidy = (uint8_t*) malloc(S);
@@ -182,6 +182,7 @@ int b200_mcall_result(b200_call_t *call, int i, b200_out_t *out)
     {
         out->PLs = b->res.pl + b->res.pl_off_out[i];
         out->nPLs = S*out->ret*(out->ret+1)/2;
+        if ( b->res.gp && !(out->site_flags & MCB_SITE_REF_GT) ) out->GPs = b->res.gp + b->res.pl_off_out[i];
     }
     return 0;
 }
@@ -196,7 +197,7 @@ void b200_mcall_destroy(b200_call_t *call)
     mcb_host_free(b->qs); mcb_host_free(b->prior_an); mcb_host_free(b->prior_ac);
     mcb_host_free(b->res.ret); mcb_host_free(b->res.als_new); mcb_host_free(b->res.als_map); mcb_host_free(b->res.qual);
     mcb_host_free(b->res.ac); mcb_host_free(b->res.an); mcb_host_free(b->res.site_flags); mcb_host_free(b->res.gt);
-    mcb_host_free(b->res.gq); mcb_host_free(b->res.pl); mcb_host_free(b->res.pl_off_out);
+    mcb_host_free(b->res.gq); mcb_host_free(b->res.gp); mcb_host_free(b->res.pl); mcb_host_free(b->res.pl_off_out);
     free(b->user); free(b->last_ploidy); free(b);
     call->batcher = NULL;
 }

@@ -24,7 +24,7 @@ class B200Out(C.Structure):
     _fields_ = [("ret", C.c_int), ("als_new", C.c_uint32), ("als_map", C.POINTER(C.c_int8)), ("qual", C.c_float),
                 ("ac", C.POINTER(C.c_int32)), ("an", C.c_int), ("site_flags", C.c_uint32),
                 ("gts", C.POINTER(C.c_int32)), ("GQs", C.POINTER(C.c_int32)), ("PLs", C.POINTER(C.c_int32)), ("nPLs", C.c_int),
-                ("user", C.c_void_p)]
+                ("GPs", C.POINTER(C.c_float)), ("user", C.c_void_p)]
 
 
 HOST_EXPORTS = ["b200_mcall_init", "b200_mcall", "b200_mcall_flush", "b200_mcall_result", "b200_mcall_destroy",
@@ -61,7 +61,7 @@ def replay(params, batch, ploidy_tab=None, max_records=64):
         call.grp_off, call.grp_smpl = params.grp_off.ctypes.data, params.grp_smpl.ctypes.data
     call.use_prior, call.max_records, call.max_nals, call.device = int(params.use_prior), max_records, params.max_nals, params.device
     L.b200_mcall_init(C.byref(call))
-    res = abi.HostResult(batch)
+    res = abi.HostResult(batch, want_gp=bool(params.output_tags & abi.CALL_FMT_GP))
     done = [0]
 
     def collect(n):
@@ -81,6 +81,8 @@ def replay(params, batch, ploidy_tab=None, max_records=64):
             if out.PLs:
                 o = batch.pl_off[i]
                 res.pl[o:o + out.nPLs] = np.ctypeslib.as_array(out.PLs, (out.nPLs,))
+                if out.GPs and res.gp is not None:
+                    res.gp[o:o + out.nPLs] = np.ctypeslib.as_array(out.GPs, (out.nPLs,))
         done[0] += n
 
     try:

@@ -70,6 +70,7 @@ typedef struct
     const int32_t *gts;         /* [nsmpl*2] call->gts */
     const int32_t *GQs;         /* [nsmpl] or NULL */
     const int32_t *PLs; int nPLs;   /* trimmed PLs: nsmpl*G' values, NULL when the tag is dropped (mcall.c:1583) */
+    const float   *GPs;             /* FORMAT/GP (-a GP, mcall.c:859-884, 1621): nPLs float32 values laid out like PLs, or NULL */
     void *user;
 }
 b200_out_t;

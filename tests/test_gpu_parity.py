@@ -278,8 +278,6 @@ def test_host_batcher_replays_reference_goldens(name):
     vcfcall.c:1089-1148 drives mcall(), small batches so that several flushes happen."""
     from bcftools_b200 import host_call
     params, batch, tab, case = golden_util.load_case(name)
-    if params.output_tags & abi.CALL_FMT_GP:
-        pytest.skip("the C batcher does not carry FORMAT/GP yet")
     if any(s.get("qs") is None for s in case["sites"]) and params.ngroups <= 1:
         pytest.skip("no QS")
     res = host_call.replay(params, batch, tab, max_records=16)
