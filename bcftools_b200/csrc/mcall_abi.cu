@@ -27,7 +27,10 @@ struct HostSlab                 /* one stage of the host-path ring (H2D of slab 
     cudaStream_t stream = nullptr;
     cudaEvent_t  done = nullptr, cursor_ready = nullptr;
     /* compaction tail still owed by the slab in flight on this stage */
-    bool pending = false;  int p_beg = 0;  size_t p_plout = 0, p_gp = 0;
+    bool pending = false;  int p_beg = 0, p_n = 0;  size_t p_plout = 0, p_gp = 0;
+    /* the small per-site arrays of a slab travel as ONE copy each way through pinned staging buffers */
+    char *h_in = nullptr, *h_out = nullptr;  size_t h_in_bytes = 0, h_out_bytes = 0;
+    size_t s_out_beg = 0, s_ret = 0, s_als = 0, s_map = 0, s_qual = 0, s_ac = 0, s_an = 0, s_fl = 0, s_diag = 0, s_ploo = 0;
     void  *dev = nullptr;  size_t dev_bytes = 0;    /* one arena, carved per slab */
     int32_t *lists = nullptr, *counts = nullptr;  int list_cap = 0;
     unsigned long long *cursor = nullptr;           /* device: compacted-PL allocation cursor (int32 units) */
@@ -51,7 +54,7 @@ struct mcb_ctx
     unsigned long long *d_cursor = nullptr;
     HostSlab slab[NSLAB];
     /* options */
-    int64_t opt_tile_bytes = 0, opt_ring_bytes = 0, opt_blocks_per_sm = 0, opt_slab_bytes = 64ll<<20, opt_block = 0;     /* 0 = automatic */
+    int64_t opt_tile_bytes = 0, opt_ring_bytes = 0, opt_blocks_per_sm = 0, opt_slab_bytes = 64ll<<20, opt_slab_min = 8ll<<20, opt_block = 0;     /* 0 = automatic */
     int64_t opt_warp2 = -1;              /* biallelic warp-per-site kernel: -1 automatic, 0 off, n = force n warps per CTA */
     int64_t opt_time_kernels = 0, opt_concurrent = 0;    /* concurrent class streams measured SLOWER than serial launches */
     int64_t opt_ring_bytes_c[NCLASS] = {0,0,0,0,0,0};   /* per allele-count class override of ring_bytes (0 = opt_ring_bytes) */
@@ -147,6 +150,7 @@ extern "C" int mcb_set_option(mcb_ctx *ctx, const char *key, int64_t value)
     else if ( !strcmp(key,"ring_bytes") )    ctx->opt_ring_bytes = value;
     else if ( !strcmp(key,"blocks_per_sm") ) ctx->opt_blocks_per_sm = value;
     else if ( !strcmp(key,"slab_bytes") )    ctx->opt_slab_bytes = value;
+    else if ( !strcmp(key,"slab_min") )      ctx->opt_slab_min = value;        /* 0 = uniform slabs of slab_bytes */
     else if ( !strcmp(key,"time_kernels") )  ctx->opt_time_kernels = value;
     else if ( !strcmp(key,"concurrent") )    ctx->opt_concurrent = value;
     else if ( !strcmp(key,"warp2") )         { if ( value<-1 || value>biallelic_max_warps() ) return MCB_EINVAL; ctx->opt_warp2 = value; }
@@ -256,6 +260,8 @@ extern "C" void mcb_destroy(mcb_ctx *ctx)
         if ( ctx->slab[i].cursor_ready ) cudaEventDestroy(ctx->slab[i].cursor_ready);
         cudaFree(ctx->slab[i].dev); cudaFree(ctx->slab[i].lists); cudaFree(ctx->slab[i].counts); cudaFree(ctx->slab[i].cursor);
         if ( ctx->slab[i].h_cursor ) cudaFreeHost(ctx->slab[i].h_cursor);
+        if ( ctx->slab[i].h_in ) cudaFreeHost(ctx->slab[i].h_in);
+        if ( ctx->slab[i].h_out ) cudaFreeHost(ctx->slab[i].h_out);
     }
     for (int i=0; i<=NCLASS; i++) if ( ctx->kev[i] ) cudaEventDestroy(ctx->kev[i]);
     for (int i=1; i<NCLASS; i++) { if ( ctx->cstream[i] ) cudaStreamDestroy(ctx->cstream[i]); if ( ctx->cev_join[i] ) cudaEventDestroy(ctx->cev_join[i]); }
@@ -582,7 +588,19 @@ extern "C" int mcb_call_host(mcb_ctx *ctx, const mcb_batch *b, const mcb_result 
     {
         if ( !sl.pending ) return MCB_OK;
         sl.pending = false;
-        CK(cudaEventSynchronize(sl.cursor_ready));
+        CK(cudaEventSynchronize(sl.cursor_ready));      /* kernels ran, the small outputs (and the cursor) are in h_out */
+        const int beg = sl.p_beg, n = sl.p_n;
+        const char *ho = sl.h_out - sl.s_out_beg;
+        memcpy(r->ret + beg, ho + sl.s_ret, 4*(size_t)n);
+        if ( r->als_new ) memcpy(r->als_new + beg, ho + sl.s_als, 4*(size_t)n);
+        if ( r->als_map ) memcpy(r->als_map + (size_t)beg*M, ho + sl.s_map, (size_t)n*M);
+        if ( r->qual ) memcpy(r->qual + beg, ho + sl.s_qual, 4*(size_t)n);
+        if ( r->ac ) memcpy(r->ac + (size_t)beg*M, ho + sl.s_ac, 4*(size_t)n*M);
+        if ( r->an ) memcpy(r->an + beg, ho + sl.s_an, 4*(size_t)n);
+        if ( r->site_flags ) memcpy(r->site_flags + beg, ho + sl.s_fl, 4*(size_t)n);
+        if ( r->diag ) memcpy(r->diag + (size_t)beg*4, ho + sl.s_diag, 32*(size_t)n);
+        if ( !compact ) return MCB_OK;
+        memcpy(r->pl_off_out + beg, ho + sl.s_ploo, sizeof(int64_t)*(size_t)n);
         const int64_t used = (int64_t)*sl.h_cursor;
         char *base = (char*) sl.dev;
         if ( want_pl && used ) CK(cudaMemcpyAsync(r->pl + out_total, base + sl.p_plout, (size_t)used*4, cudaMemcpyDeviceToHost, sl.stream));
@@ -597,9 +615,15 @@ extern "C" int mcb_call_host(mcb_ctx *ctx, const mcb_batch *b, const mcb_result 
     int beg = 0, islab = 0;
     while ( beg < R )
     {
-        /* slab = as many sites as fit opt_slab_bytes of PL */
+        /* slab = as many sites as fit the slab budget of PL bytes.  The budget ramps up geometrically from opt_slab_min
+           at the start of the call and down again towards its end: the first upload and the last download are the only
+           transfers that overlap nothing, so they are kept short; the slabs in between are large (few launches). */
+        const int64_t done_bytes = (b->pl_off[beg] - b->pl_off[0])*es;
+        const int64_t left_bytes = (b->pl_off[R-1] + ext[R-1] - b->pl_off[beg])*es;
+        int64_t budget = std::min<int64_t>(ctx->opt_slab_bytes, std::max<int64_t>(ctx->opt_slab_min, std::min<int64_t>(done_bytes, left_bytes/2)));
+        if ( ctx->opt_slab_min<=0 ) budget = ctx->opt_slab_bytes;
         int end = beg; int64_t pl_ints = 0;
-        while ( end < R && (end==beg || (pl_ints + ext[end])*es <= ctx->opt_slab_bytes) ) { pl_ints = b->pl_off[end] + ext[end] - b->pl_off[beg]; end++; }
+        while ( end < R && (end==beg || (pl_ints + ext[end])*es <= budget) ) { pl_ints = b->pl_off[end] + ext[end] - b->pl_off[beg]; end++; }
         const int n = end - beg;
         HostSlab &sl = ctx->slab[islab % NSLAB];
         { int frc = finish(sl); if ( frc ) return frc; }
@@ -610,15 +634,34 @@ extern "C" int mcb_call_host(mcb_ctx *ctx, const mcb_batch *b, const mcb_result 
         auto carve = [&](size_t bytes) { size_t o = off; off += pad256(bytes); return o; };
         size_t o_pl = carve((size_t)pl_ints*es), o_plout = want_pl ? carve((size_t)pl_ints*4) : 0;
         size_t o_gp = want_gp ? carve((size_t)pl_ints*4) : 0;
+        const int64_t ad0 = have_ad ? b->ad_off[beg] : 0, ad_ints = have_ad ? b->ad_off[end-1] + aext[end-1] - ad0 : 0;
+        size_t o_ad = have_ad ? carve((size_t)ad_ints*4) : 0;
+        size_t o_gt = want_gt ? carve(8*(size_t)n*S) : 0, o_gq = want_gq ? carve(4*(size_t)n*S) : 0;
+        /* small inputs, contiguous: one upload */
+        const size_t in_beg = off;
         size_t o_ploff = carve(sizeof(int64_t)*n), o_nals = carve(n), o_unseen = carve(n), o_pid = carve(2*(size_t)n);
         size_t o_qs = carve(sizeof(float)*(size_t)n*M), o_nqs = carve(n);
         size_t o_pan = carve(sizeof(int32_t)*n), o_pac = carve(sizeof(int32_t)*(size_t)n*M);
+        size_t o_adoff = have_ad ? carve(sizeof(int64_t)*n) : 0, o_nad = have_ad ? carve(n) : 0;
+        const size_t in_end = off;
+        /* small outputs, contiguous: one download */
+        const size_t out_beg = off;
         size_t o_ret = carve(4*(size_t)n), o_als = carve(4*(size_t)n), o_map = carve((size_t)n*M), o_qual = carve(4*(size_t)n);
         size_t o_ac = carve(4*(size_t)n*M), o_an = carve(4*(size_t)n), o_fl = carve(4*(size_t)n), o_diag = carve(32*(size_t)n);
-        size_t o_gt = want_gt ? carve(8*(size_t)n*S) : 0, o_gq = want_gq ? carve(4*(size_t)n*S) : 0;
         size_t o_ploo = compact ? carve(sizeof(int64_t)*n) : 0;
-        const int64_t ad0 = have_ad ? b->ad_off[beg] : 0, ad_ints = have_ad ? b->ad_off[end-1] + aext[end-1] - ad0 : 0;
-        size_t o_ad = have_ad ? carve((size_t)ad_ints*4) : 0, o_adoff = have_ad ? carve(sizeof(int64_t)*n) : 0, o_nad = have_ad ? carve(n) : 0;
+        const size_t out_end = off;
+        if ( in_end - in_beg > sl.h_in_bytes )
+        {
+            if ( sl.h_in ) CK(cudaFreeHost(sl.h_in));
+            sl.h_in_bytes = (in_end - in_beg) + (in_end - in_beg)/4;
+            CK(cudaHostAlloc(&sl.h_in, sl.h_in_bytes, cudaHostAllocDefault));
+        }
+        if ( out_end - out_beg > sl.h_out_bytes )
+        {
+            if ( sl.h_out ) CK(cudaFreeHost(sl.h_out));
+            sl.h_out_bytes = (out_end - out_beg) + (out_end - out_beg)/4;
+            CK(cudaHostAlloc(&sl.h_out, sl.h_out_bytes, cudaHostAllocDefault));
+        }
         if ( off > sl.dev_bytes )
         {
             if ( sl.dev ) CK(cudaFree(sl.dev));
@@ -636,19 +679,19 @@ extern "C" int mcb_call_host(mcb_ctx *ctx, const mcb_batch *b, const mcb_result 
         const int64_t pl0 = b->pl_off[beg];
 #define H2D(dst,src,bytes) CK(cudaMemcpyAsync(base+(dst), (src), (bytes), cudaMemcpyHostToDevice, st))
         H2D(o_pl, (const char*)b->pl + (size_t)pl0*es, (size_t)pl_ints*es);
-        H2D(o_ploff, b->pl_off + beg, sizeof(int64_t)*n);
-        H2D(o_nals, b->nals + beg, n);
-        if ( b->unseen ) H2D(o_unseen, b->unseen + beg, n);
-        if ( b->ploidy_id ) H2D(o_pid, b->ploidy_id + beg, 2*(size_t)n);
-        if ( b->qs ) H2D(o_qs, b->qs + (size_t)beg*M, sizeof(float)*(size_t)n*M);
-        if ( b->nqs ) H2D(o_nqs, b->nqs + beg, n);
-        if ( b->prior_an ) H2D(o_pan, b->prior_an + beg, sizeof(int32_t)*n);
-        if ( b->prior_ac ) H2D(o_pac, b->prior_ac + (size_t)beg*M, sizeof(int32_t)*(size_t)n*M);
-        if ( have_ad )
+        if ( have_ad ) H2D(o_ad, b->ad + ad0, (size_t)ad_ints*4);
         {
-            H2D(o_ad, b->ad + ad0, (size_t)ad_ints*4);
-            H2D(o_adoff, b->ad_off + beg, sizeof(int64_t)*n);
-            H2D(o_nad, b->nad + beg, n);
+            char *hi = sl.h_in - in_beg;
+            memcpy(hi + o_ploff, b->pl_off + beg, sizeof(int64_t)*n);
+            memcpy(hi + o_nals, b->nals + beg, n);
+            if ( b->unseen ) memcpy(hi + o_unseen, b->unseen + beg, n);
+            if ( b->ploidy_id ) memcpy(hi + o_pid, b->ploidy_id + beg, 2*(size_t)n);
+            if ( b->qs ) memcpy(hi + o_qs, b->qs + (size_t)beg*M, sizeof(float)*(size_t)n*M);
+            if ( b->nqs ) memcpy(hi + o_nqs, b->nqs + beg, n);
+            if ( b->prior_an ) memcpy(hi + o_pan, b->prior_an + beg, sizeof(int32_t)*n);
+            if ( b->prior_ac ) memcpy(hi + o_pac, b->prior_ac + (size_t)beg*M, sizeof(int32_t)*(size_t)n*M);
+            if ( have_ad ) { memcpy(hi + o_adoff, b->ad_off + beg, sizeof(int64_t)*n); memcpy(hi + o_nad, b->nad + beg, n); }
+            H2D(in_beg, sl.h_in, in_end - in_beg);
         }
 #undef H2D
         /* device views: pl pointers are biased by -pl0 so that the absolute pl_off[] stay valid */
@@ -686,20 +729,12 @@ extern "C" int mcb_call_host(mcb_ctx *ctx, const mcb_batch *b, const mcb_result 
         if ( rc ) return rc;
 
 #define D2H(dst,src,bytes) CK(cudaMemcpyAsync((dst), base+(src), (bytes), cudaMemcpyDeviceToHost, st))
-        D2H(r->ret + beg, o_ret, 4*(size_t)n);
-        if ( r->als_new ) D2H(r->als_new + beg, o_als, 4*(size_t)n);
-        if ( r->als_map ) D2H(r->als_map + (size_t)beg*M, o_map, (size_t)n*M);
-        if ( r->qual ) D2H(r->qual + beg, o_qual, 4*(size_t)n);
-        if ( r->ac ) D2H(r->ac + (size_t)beg*M, o_ac, 4*(size_t)n*M);
-        if ( r->an ) D2H(r->an + beg, o_an, 4*(size_t)n);
-        if ( r->site_flags ) D2H(r->site_flags + beg, o_fl, 4*(size_t)n);
-        if ( r->diag ) D2H(r->diag + (size_t)beg*4, o_diag, 32*(size_t)n);
-        if ( compact )
-        {
-            CK(cudaMemcpyAsync(sl.h_cursor, sl.cursor, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-            D2H(r->pl_off_out + beg, o_ploo, sizeof(int64_t)*n);
-            CK(cudaEventRecord(sl.cursor_ready, st));
-        }
+        if ( compact ) CK(cudaMemcpyAsync(sl.h_cursor, sl.cursor, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        D2H(sl.h_out, out_beg, out_end - out_beg);
+        CK(cudaEventRecord(sl.cursor_ready, st));
+        sl.s_out_beg = out_beg; sl.s_ret = o_ret; sl.s_als = o_als; sl.s_map = o_map; sl.s_qual = o_qual; sl.s_ac = o_ac;
+        sl.s_an = o_an; sl.s_fl = o_fl; sl.s_diag = o_diag; sl.s_ploo = o_ploo;
+        sl.pending = true; sl.p_beg = beg; sl.p_n = n; sl.p_plout = o_plout; sl.p_gp = o_gp;
         if ( want_gt ) D2H(r->gt + (size_t)beg*S*2, o_gt, 8*(size_t)n*S);
         if ( want_gq ) D2H(r->gq + (size_t)beg*S, o_gq, 4*(size_t)n*S);
         if ( !compact )
@@ -708,12 +743,9 @@ extern "C" int mcb_call_host(mcb_ctx *ctx, const mcb_batch *b, const mcb_result 
             if ( want_gp ) D2H(r->gp + pl0, o_gp, (size_t)pl_ints*4);
             CK(cudaEventRecord(sl.done, st));
         }
-        else
-        {
-            sl.pending = true; sl.p_beg = beg; sl.p_plout = o_plout; sl.p_gp = o_gp;
-            /* the tail of the PREVIOUS slab: its kernels have had the whole upload of this one to finish */
-            if ( islab ) { int frc = finish(ctx->slab[(islab-1) % NSLAB]); if ( frc ) return frc; }
-        }
+        /* the host-side tail of the PREVIOUS slab (scatter of its small outputs, compacted PL download): its kernels
+           have had the whole upload of this one to finish */
+        if ( islab ) { int frc = finish(ctx->slab[(islab-1) % NSLAB]); if ( frc ) return frc; }
 #undef D2H
         beg = end; islab++;
     }

@@ -5,8 +5,8 @@ import numpy as np
 from bcftools_b200 import abi, synth, mcall
 sites = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
 params, hb, tab = synth.make_batch("C3", sites, with_groups=0)
-for slab_mb in (256, 128, 64, 32, 16):
-    mc = mcall.MCaller(params, ploidy_tab=tab, options={"slab_bytes": slab_mb << 20})
+for slab_mb, min_mb in ((64, 0), (64, 16), (64, 8), (64, 4), (64, 2), (128, 8), (32, 4)):
+    mc = mcall.MCaller(params, ploidy_tab=tab, options={"slab_bytes": slab_mb << 20, "slab_min": min_mb << 20})
     sub = mcall.pin_batch(hb.subset(range(sites)))
     res = mcall.pin_result(abi.HostResult(sub, compact=True))
     for _ in range(2):
@@ -16,5 +16,5 @@ for slab_mb in (256, 128, 64, 32, 16):
     for _ in range(n):
         mc.call_host(sub, res)
     dt = (time.perf_counter() - t0) / n
-    print(json.dumps(dict(slab_mb=slab_mb, ms=dt * 1e3, calls_per_s=sites * params.nsmpl / dt)), flush=True)
+    print(json.dumps(dict(slab_mb=slab_mb, min_mb=min_mb, ms=dt * 1e3, calls_per_s=sites * params.nsmpl / dt)), flush=True)
     mc.close()
