@@ -32,7 +32,7 @@ namespace mcb {
 #define BW_UNROLL2   1                  /* unroll factor of the phase-2 sample loop */
 #endif
 #ifndef BW_MAXWARP
-#define BW_MAXWARP   12                 /* warps per CTA the kernel is compiled for (2 CTAs per SM => 85 registers, no spills; 14 => 72 with spills measured 2 % slower) */
+#define BW_MAXWARP   14                 /* warps per CTA the kernel is compiled for (2 CTAs per SM => 72 registers, no spills) */
 #endif
 #ifndef BW_MINCTA
 #define BW_MINCTA    2

@@ -223,7 +223,7 @@ def test_biallelic_warp_kernel(S, flag, oracle_built):
         blk[np.arange(S), rng.integers(0, 3, S)] = 0
     params = abi.CallParams(S, 2, flag=flag, output_tags=abi.CALL_FMT_GQ)
     exp, _ = oracle_built.call("port", params, batch, None)
-    for opts, compact in (({"warp2": 12}, False), ({"warp2": 3}, True), ({"warp2": 0}, False)):
+    for opts, compact in (({"warp2": 14}, False), ({"warp2": 3}, True), ({"warp2": 0}, False)):
         with mcall.MCaller(params, options=opts) as mc:
             got = mc.call_host(batch, compact=compact)
         st = parity.compare(got, exp, params)
