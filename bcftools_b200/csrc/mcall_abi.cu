@@ -56,6 +56,7 @@ struct mcb_ctx
     /* options */
     int64_t opt_tile_bytes = 0, opt_ring_bytes = 0, opt_blocks_per_sm = 0, opt_slab_bytes = 64ll<<20, opt_slab_min = 8ll<<20, opt_block = 0;     /* 0 = automatic */
     int64_t opt_warp2 = -1;              /* biallelic warp-per-site kernel: -1 automatic, 0 off, n = force n warps per CTA */
+    int64_t opt_order = 54321;           /* launch order of the allele-count classes */
     int64_t opt_time_kernels = 0, opt_concurrent = 0;    /* concurrent class streams measured SLOWER than serial launches */
     int64_t opt_ring_bytes_c[NCLASS] = {0,0,0,0,0,0};   /* per allele-count class override of ring_bytes (0 = opt_ring_bytes) */
     int64_t opt_block_c[NCLASS] = {0,0,0,0,0,0};        /* per class override of the CTA size */
@@ -153,6 +154,7 @@ extern "C" int mcb_set_option(mcb_ctx *ctx, const char *key, int64_t value)
     else if ( !strcmp(key,"slab_min") )      ctx->opt_slab_min = value;        /* 0 = uniform slabs of slab_bytes */
     else if ( !strcmp(key,"time_kernels") )  ctx->opt_time_kernels = value;
     else if ( !strcmp(key,"concurrent") )    ctx->opt_concurrent = value;
+    else if ( !strcmp(key,"order") )         ctx->opt_order = value;
     else if ( !strcmp(key,"warp2") )         { if ( value<-1 || value>biallelic_max_warps() ) return MCB_EINVAL; ctx->opt_warp2 = value; }
     else if ( !strncmp(key,"ring_bytes_",11) && key[11]>='1' && key[11]<='5' && !key[12] ) ctx->opt_ring_bytes_c[key[11]-'0'] = value;
     else if ( !strncmp(key,"block_",6) && key[6]>='1' && key[6]<='5' && !key[7] )
@@ -213,7 +215,7 @@ extern "C" int mcb_init(mcb_ctx **out, const mcb_params *params)
     ctx->nploidy = 1;
     int rc = upload_ploidy(ctx);
     if ( rc ) return rc;
-    CK(cudaMalloc(&ctx->d_counts, sizeof(int32_t)*NCLASS));
+    CK(cudaMalloc(&ctx->d_counts, sizeof(int32_t)*(NCLASS+8)));     /* + work counter of the warp-per-site kernel */
     CK(cudaMalloc(&ctx->d_cursor, sizeof(unsigned long long)));
     if ( params->ngroups > 1 )         /* smpl_grp_t.smpl lists (mcall.c:250-349): every sample in exactly one group */
     {
@@ -240,7 +242,7 @@ extern "C" int mcb_init(mcb_ctx **out, const mcb_params *params)
         CK(cudaStreamCreateWithFlags(&ctx->slab[i].stream, cudaStreamNonBlocking));
         CK(cudaEventCreateWithFlags(&ctx->slab[i].done, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&ctx->slab[i].cursor_ready, cudaEventDisableTiming));
-        CK(cudaMalloc(&ctx->slab[i].counts, sizeof(int32_t)*NCLASS));
+        CK(cudaMalloc(&ctx->slab[i].counts, sizeof(int32_t)*(NCLASS+8)));
         CK(cudaMalloc(&ctx->slab[i].cursor, sizeof(unsigned long long)));
         CK(cudaHostAlloc(&ctx->slab[i].h_cursor, sizeof(unsigned long long), cudaHostAllocDefault));
     }
@@ -394,7 +396,7 @@ static int enqueue_class0(mcb_ctx *ctx, KArgs &a, const mcb_batch *b, const mcb_
 
 static int enqueue(mcb_ctx *ctx, const mcb_batch *b, const mcb_result *r, int32_t *lists, int32_t *counts, int list_stride, unsigned long long *cursor, cudaStream_t st)
 {
-    CK(cudaMemsetAsync(counts, 0, sizeof(int32_t)*NCLASS, st));
+    CK(cudaMemsetAsync(counts, 0, sizeof(int32_t)*(NCLASS+8), st));
     if ( r->pl_off_out ) CK(cudaMemsetAsync(cursor, 0, sizeof(unsigned long long), st));
     CK(launch_classify(b->nals, b->nsites, lists, counts, list_stride, st));
     int launches = 1;
@@ -431,6 +433,7 @@ static int enqueue(mcb_ctx *ctx, const mcb_batch *b, const mcb_result *r, int32_
         for (int nals=1; nals<=5; nals++)
         {
             a.site_list = lists + (size_t)nals*list_stride; a.site_count = counts + nals;
+            a.work_counter = counts + NCLASS + nals;
             CK(launch_groups_kernel(nals, a, ctx->d_grp_scratch, grid, st));
             launches++;
         }
@@ -454,21 +457,38 @@ static int enqueue(mcb_ctx *ctx, const mcb_batch *b, const mcb_result *r, int32_
         if ( !ctx->cev_fork )
         {
             CK(cudaEventCreateWithFlags(&ctx->cev_fork, cudaEventDisableTiming));
+            /* concurrent=2: stream priorities in launch order (5 alleles first = highest), so that a later class only
+               fills the SMs the earlier one leaves idle in the tail of its persistent grid */
+            int plo = 0, phi = 0;
+            CK(cudaDeviceGetStreamPriorityRange(&plo, &phi));       /* numerically lower = higher priority */
             for (int i=1; i<NCLASS; i++)
             {
+                int pos = 0; { int64_t v = ctx->opt_order; int d[5] = {5,4,3,2,1}; for (int k=4; k>=0 && v>0; k--, v/=10) d[k] = (int)(v%10); for (int k=0; k<5; k++) if ( d[k]==i ) pos = k; }
+                int prio = std::min(plo, phi + pos);
+                if ( ctx->opt_concurrent>=2 ) CK(cudaStreamCreateWithPriority(&ctx->cstream[i], cudaStreamNonBlocking, prio));
+                else
                 CK(cudaStreamCreateWithFlags(&ctx->cstream[i], cudaStreamNonBlocking));
                 CK(cudaEventCreateWithFlags(&ctx->cev_join[i], cudaEventDisableTiming));
             }
         }
         CK(cudaEventRecord(ctx->cev_fork, st));
     }
-    for (int nals=5; nals>=1; nals--)       /* the heavy, low-occupancy classes first */
+    /* launch order of the allele-count classes: digits of opt_order, first digit first (timing mode: ascending) */
+    int order[5] = {5,4,3,2,1};
     {
-        if ( timing ) nals = 6 - nals;      /* timing mode keeps the ascending order of the event list */
+        int64_t v = ctx->opt_order; int seen = 0, tmp[5], k = 4;
+        for (; k>=0 && v>0; k--, v/=10) { tmp[k] = (int)(v%10); if ( tmp[k]>=1 && tmp[k]<=5 ) seen |= 1<<tmp[k]; }
+        if ( k<0 && v==0 && seen==0x3e ) for (int i=0; i<5; i++) order[i] = tmp[i];
+    }
+    for (int io=0; io<5; io++)
+    {
+        int nals = order[io];
+        if ( timing ) nals = io + 1;        /* timing mode keeps the ascending order of the event list */
         size_t ring; tile_geometry(ctx, nals, pl_es, &a.tile_smpl, &a.nstage, &ring);
         const bool gpk = a.gp && (a.output_tags & MCB_CALL_FMT_GP);
         const int block = (pl_es==2 || gpk) ? 128 : class_block(ctx, nals);
         a.site_list = lists + (size_t)nals*list_stride; a.site_count = counts + nals;
+        a.work_counter = counts + NCLASS + nals;    /* zeroed with the class counts: sites are claimed dynamically */
         /* two alleles, everything diploid, int32 PLs, no GP: one warp per site over a byte-packed shared-memory copy */
         int bw_warps = 0;
         if ( nals==2 && !ploidy && pl_es==4 && !(a.gp && (a.output_tags & MCB_CALL_FMT_GP)) && ctx->opt_warp2!=0 && a.nsmpl<=8192 )
@@ -497,7 +517,7 @@ static int enqueue(mcb_ctx *ctx, const mcb_batch *b, const mcb_result *r, int32_
             }
             launches++;
             if ( fork ) { CK(cudaEventRecord(ctx->cev_join[nals], cs)); CK(cudaStreamWaitEvent(st, ctx->cev_join[nals], 0)); }
-            if ( timing ) { CK(cudaEventRecord(ctx->kev[nals], st)); nals = 6 - nals; }
+            if ( timing ) CK(cudaEventRecord(ctx->kev[nals], st));
             continue;
         }
         int nb = 1;
@@ -519,7 +539,7 @@ static int enqueue(mcb_ctx *ctx, const mcb_batch *b, const mcb_result *r, int32_
         }
         launches++;
         if ( fork ) { CK(cudaEventRecord(ctx->cev_join[nals], cs)); CK(cudaStreamWaitEvent(st, ctx->cev_join[nals], 0)); }
-        if ( timing ) { CK(cudaEventRecord(ctx->kev[nals], st)); nals = 6 - nals; }
+        if ( timing ) CK(cudaEventRecord(ctx->kev[nals], st));
     }
     ctx->kev_valid = timing;
     { int rc0 = enqueue_class0(ctx, a, b, r, lists, counts, pl_es, st); if ( rc0 ) return rc0; }

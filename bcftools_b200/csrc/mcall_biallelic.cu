@@ -25,6 +25,9 @@ namespace mcb {
 #ifndef BW_P2_LANE_SAMPLES
 #define BW_P2_LANE_SAMPLES 1            /* phase 2: lanes take consecutive samples (coalesced stores) instead of 4-sample groups */
 #endif
+#ifndef BW_DYNAMIC
+#define BW_DYNAMIC   1                  /* sites claimed from a global counter instead of a static stride */
+#endif
 #ifndef BW_ROLL1
 #define BW_ROLL1     0                  /* 1: phase-1 sample loop rolled (smaller code) */
 #endif
@@ -178,8 +181,19 @@ __global__ void __launch_bounds__(BW_MAXWARP*32, BW_MINCTA) mcall_biallelic_warp
     const int nsites = *a.site_count;
     const bool want_gq = a.gq && (a.output_tags & (MCB_CALL_FMT_GQ|MCB_CALL_FMT_GP));
 
+#if BW_DYNAMIC
+    /* sites are claimed from a global counter: REF-only sites cost a fraction of a variant site, so a static
+       round-robin leaves most warps idle while the unlucky ones finish their last site */
+    for (;;)
+    {
+        int isite = 0;
+        if ( lane==0 ) isite = atomicAdd(a.work_counter, 1);
+        isite = __shfl_sync(0xffffffffu, isite, 0);
+        if ( isite >= nsites ) break;
+#else
     for (int isite = blockIdx.x*nwarp + warp; isite < nsites; isite += gridDim.x*nwarp)
     {
+#endif
         const int site = a.site_list[isite];
         const int64_t site_off = a.pl_off[site];
         const int32_t *site_pl = reinterpret_cast<const int32_t*>(a.pl) + site_off;
@@ -189,7 +203,7 @@ __global__ void __launch_bounds__(BW_MAXWARP*32, BW_MINCTA) mcall_biallelic_warp
         /* the first blocks of this warp's NEXT site are pulled into L2 while phase 2 of this one runs */
         const char *next_pl = nullptr;
         {
-            const int nx = isite + gridDim.x*nwarp;
+            const int nx = BW_DYNAMIC ? nsites : isite + gridDim.x*nwarp;
             if ( nx < nsites ) next_pl = reinterpret_cast<const char*>(reinterpret_cast<const int32_t*>(a.pl) + a.pl_off[a.site_list[nx]]);
         }
         if ( lane==0 ) rec.nesc = 0;

@@ -55,6 +55,7 @@ template<int NALS, int BLOCK> struct Shared
     int      als_map[NALS];
     int      pl_map[S::G];
     int      ac[8];
+    int      next_site;
     Phase2Consts p2;
 };
 
@@ -210,8 +211,20 @@ __global__ void __launch_bounds__(BLOCK, (MinBlocks<NALS,BLOCK>::value)) mcall_s
     uint32_t phase_bits = 0;
     const int nsites = *a.site_count;
 
+#ifndef MCB_DYNAMIC
+#define MCB_DYNAMIC 1       /* CTAs claim sites from a global counter (REF-only sites are cheap: a static stride leaves a long tail) */
+#endif
+#if MCB_DYNAMIC
+    for (;;)
+    {
+        if ( tid==0 ) sh.next_site = atomicAdd(a.work_counter, 1);
+        __syncthreads();
+        const int isite = sh.next_site;
+        if ( isite >= nsites ) break;
+#else
     for (int isite = blockIdx.x; isite < nsites; isite += gridDim.x)
     {
+#endif
         const int site = a.site_list[isite];
         const int64_t site_off = a.pl_off[site];
         const PT *site_pl = reinterpret_cast<const PT*>(a.pl) + site_off;

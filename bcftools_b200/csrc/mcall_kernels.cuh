@@ -56,6 +56,7 @@ struct KArgs
     const uint8_t *ploidy_tab;  int nploidy;
     const uint32_t *grp_off;  const uint32_t *grp_smpl;  const uint32_t *smpl2grp;  int ngroups;
     const int32_t *site_list;  const int32_t *site_count;      /* the sites of this allele-count class */
+    int32_t *work_counter;                                      /* next unclaimed entry of site_list (warp-per-site kernel) */
     int nsmpl, max_nals;
     uint32_t flag, output_tags;
     double theta, tie_eps;
