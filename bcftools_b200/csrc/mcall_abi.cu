@@ -57,7 +57,7 @@ struct mcb_ctx
     int64_t opt_tile_bytes = 0, opt_ring_bytes = 0, opt_blocks_per_sm = 0, opt_slab_bytes = 64ll<<20, opt_slab_min = 8ll<<20, opt_block = 0;     /* 0 = automatic */
     int64_t opt_warp2 = -1;              /* biallelic warp-per-site kernel: -1 automatic, 0 off, n = force n warps per CTA */
     int64_t opt_order = 54321;           /* launch order of the allele-count classes */
-    int64_t opt_time_kernels = 0, opt_concurrent = 0;    /* concurrent class streams measured SLOWER than serial launches */
+    int64_t opt_time_kernels = 0, opt_concurrent = 1;    /* class kernels on their own streams: a class fills the tail of the previous one (-3.5 % per C3 step) */
     int64_t opt_ring_bytes_c[NCLASS] = {0,0,0,0,0,0};   /* per allele-count class override of ring_bytes (0 = opt_ring_bytes) */
     int64_t opt_block_c[NCLASS] = {0,0,0,0,0,0};        /* per class override of the CTA size */
     int64_t opt_tile_bytes_c[NCLASS] = {0,0,0,0,0,0};   /* per class override of tile_bytes */

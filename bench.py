@@ -250,7 +250,7 @@ def main():
     # ---- workload: each rank owns a contiguous range of sites (its own seed offset): weak scaling, no collective
     params, hb, tab = synth.make_batch(WORKLOAD, args.sites, seed_offset=rank, with_groups=0)
     params.device = local_rank
-    mc = mcall.MCaller(params, ploidy_tab=tab, options={"time_kernels": 1})
+    mc = mcall.MCaller(params, ploidy_tab=tab)
     db = device.DeviceBatch(hb, device=f"cuda:{local_rank}", replicate=args.replicate)
     dr = device.DeviceResult(db)
     b, r = db.c_struct(), dr.c_struct()
@@ -272,7 +272,10 @@ def main():
     barrier()
     dev_s = e0.elapsed_time(e1) * 1e-3
     launches = int(mc.stats()[0]) * args.steps
-    # per-class kernel times of one more (untimed) step for the roofline of the dominant kernel
+    # per-class kernel times of untimed extra steps for the roofline of the dominant kernel: the library serialises the
+    # class kernels on the caller's stream and brackets each with events (in the timed region they run on their own
+    # streams and overlap at the tails of their persistent grids)
+    mc.set_option("time_kernels", 1)
     per_class = []
     for _ in range(5):
         mc.call_device(b, r, stream)
