@@ -337,14 +337,14 @@ static int class_block(const mcb_ctx *ctx, int nals)
     if ( ctx->opt_block ) return (int)ctx->opt_block;
     const int S = ctx->p.nsmpl;
     int b = S<=192 ? 32 : (S<=768 ? 64 : 128);
-    if ( nals==4 && b>64 ) b = 64;
+    if ( (nals==3 || nals==4) && b>64 ) b = 64;
     return b;
 }
 static int64_t class_tile_bytes(const mcb_ctx *ctx, int nals)
 {
     if ( ctx->opt_tile_bytes_c[nals] ) return ctx->opt_tile_bytes_c[nals];
     if ( ctx->opt_tile_bytes ) return ctx->opt_tile_bytes;
-    return nals==3 ? 16384 : (nals==4 ? 8192 : 32768);
+    return (nals==3 || nals==4) ? 8192 : 32768;
 }
 static int64_t class_ring_bytes(const mcb_ctx *ctx, int nals)
 {
