@@ -489,9 +489,9 @@ static int enqueue(mcb_ctx *ctx, const mcb_batch *b, const mcb_result *r, int32_
         const int block = (pl_es==2 || gpk) ? 128 : class_block(ctx, nals);
         a.site_list = lists + (size_t)nals*list_stride; a.site_count = counts + nals;
         a.work_counter = counts + NCLASS + nals;    /* zeroed with the class counts: sites are claimed dynamically */
-        /* two alleles, everything diploid, int32 PLs, no GP: one warp per site over a byte-packed shared-memory copy */
+        /* two alleles, int32 PLs, no GP: one warp per site over a byte-packed shared-memory copy */
         int bw_warps = 0;
-        if ( nals==2 && !ploidy && pl_es==4 && !(a.gp && (a.output_tags & MCB_CALL_FMT_GP)) && ctx->opt_warp2!=0 && a.nsmpl<=8192 )
+        if ( nals==2 && pl_es==4 && !(a.gp && (a.output_tags & MCB_CALL_FMT_GP)) && ctx->opt_warp2!=0 && a.nsmpl<=8192 )
         {
             const int ncta = biallelic_ctas_per_sm();
             const size_t per_cta = (size_t)(ctx->smem_per_sm/ncta) - 1024;  /* the kernel is compiled for ncta CTAs per SM */
@@ -507,7 +507,7 @@ static int enqueue(mcb_ctx *ctx, const mcb_batch *b, const mcb_result *r, int32_
             if ( ctx->opt_blocks_per_sm>0 ) grid = std::min<int>(grid, ctx->nsm*(int)std::min<int64_t>(biallelic_ctas_per_sm(), ctx->opt_blocks_per_sm));
             cudaStream_t cs = fork ? ctx->cstream[nals] : st;
             if ( fork ) CK(cudaStreamWaitEvent(cs, ctx->cev_fork, 0));
-            cudaError_t le = launch_biallelic_warp_kernel(a, grid, bw_warps, cs);
+            cudaError_t le = launch_biallelic_warp_kernel(a, ploidy, grid, bw_warps, cs);
             if ( le==cudaSuccess && getenv("MCB_DEBUG_SYNC") ) le = cudaStreamSynchronize(cs);
             if ( le!=cudaSuccess )
             {

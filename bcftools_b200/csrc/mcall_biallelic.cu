@@ -1,5 +1,5 @@
 /*  mcall_biallelic.cu -- warp-per-site kernel for the dominant shape of `call -m`: two alleles (REF + one ALT),
- *  every sample diploid, int32 PLs, one sample group, no FORMAT/GP.
+ *  int32 PLs, one sample group, no FORMAT/GP (two instances: every sample diploid / any ploidy vector).
  *
  *  Same algorithm and reference line map as the general site kernel (mcall_kernels.cu); what differs is the mapping:
  *
@@ -22,17 +22,11 @@
 
 namespace mcb {
 
-#ifndef BW_P2_LANE_SAMPLES
-#define BW_P2_LANE_SAMPLES 1            /* phase 2: lanes take consecutive samples (coalesced stores) instead of 4-sample groups */
-#endif
 #ifndef BW_DYNAMIC
 #define BW_DYNAMIC   1                  /* sites claimed from a global counter instead of a static stride */
 #endif
 #ifndef BW_ROLL1
 #define BW_ROLL1     0                  /* 1: phase-1 sample loop rolled (smaller code) */
-#endif
-#ifndef BW_UNROLL2
-#define BW_UNROLL2   1                  /* unroll factor of the phase-2 sample loop */
 #endif
 #ifndef BW_MAXWARP
 #define BW_MAXWARP   14                 /* warps per CTA the kernel is compiled for (2 CTAs per SM => 72 registers, no spills) */
@@ -49,16 +43,15 @@ namespace mcb {
 #endif
 #define BW_REC_BYTES 384                /* per-warp site record in shared memory */
 
-constexpr int kBwUnroll2 = BW_UNROLL2;
-
 struct BWRec                            /* written by lane 0 after phase 1, read by the whole warp */
 {
     int4   slot_out[3];                 /* diploid call of slot k: {gt0, gt1, AC[0] increment, AC[1] increment} */
+    int4   hap_out[2];                  /* haploid call of selected allele x: {gt0, vector_end, AC[0] increment, AC[1] increment} */
     double q[2];                        /* (double)qsum of the selected alleles, mcall.c:797, 820 */
     double max_qual, lk_sum, ref_lk, gap;
     float  qf[2];
     uint32_t flags, als_new;
-    int    nsel, jgt0, inc_dip, nals_new, ret_early, pl_dropped, ref_gt;
+    int    nsel, jgt0, inc_dip, inc_hap, nals_new, ret_early, pl_dropped, ref_gt;
     int    als_map[2];
     long long out_off;
     int    nesc;                        /* samples that need the general path (escape list below; > BW_ESC_CAP: overflowed) */
@@ -142,6 +135,56 @@ __device__ __noinline__ bool bw_slow_sample_ni(BWSlow *w, int unseen, uint32_t p
     return data;
 }
 
+/*  mcall_call_genotypes for one HAPLOID sample (mcall.c:793-808, 843-878): lk_x = pdg[s_x/s_x] * q_x over the selected
+ *  alleles, GQ over the alleles below grp->nals (inc_hap).  pA = pl2p[PL of s0/s0], pB = of s1/s1.  */
+template<bool FAST>
+__device__ __forceinline__ int4 bw_call_haploid(double pA, double pB, double sum, const BWConsts &c, uint32_t hap_s, int inc_hap, int &gq)
+{
+    const double r = FAST ? rcp_shared(sum) : 0.0;
+    auto dv = [&](double x) -> double { return FAST ? div_shared(x, sum, r) : __ddiv_rn(x, sum); };
+    double best = 0; int bx = 0; bool any_best = false;
+    double gv0 = __dmul_rn(dv(pA), c.q0), gv2 = 0;
+    if ( best < gv0 ) { best = gv0; bx = 0; any_best = true; }
+    if ( c.nsel>1 )
+    {
+        gv2 = __dmul_rn(dv(pB), c.q1);
+        if ( best < gv2 ) { best = gv2; bx = 1; any_best = true; }
+    }
+    const int4 outc = any_best ? lds128(hap_s + 16u*(uint32_t)bx) : make_int4(MCB_GT_UNPHASED(0), I32_VEC_END, 1, 0);
+    gq = 0;
+    if ( c.want_gq )
+    {
+        double gmax = 0, gsum = 0;
+        gv0 = (double)__double2float_rn(gv0); gv2 = (double)__double2float_rn(gv2);
+        if ( inc_hap & 1 ) { if ( gmax < gv0 ) gmax = gv0; gsum = __dadd_rn(gsum, gv0); }
+        if ( inc_hap & 2 ) { if ( gmax < gv2 ) gmax = gv2; gsum = __dadd_rn(gsum, gv2); }
+        const double xx = __dadd_rn(1.0, -__ddiv_rn(gmax, gsum));
+        if ( !(xx==xx) ) gq = 127;
+        else
+        {
+            int k = __float2int_rz(-3.0102999f*lg2_approx((float)xx));
+            k = max(0, min(127, k));
+            if ( xx <= lds64c(c.thr_s + 8u*(uint32_t)(k+1)) ) { k++; while ( xx <= lds64c(c.thr_s + 8u*(uint32_t)(k+1)) ) k++; }
+            else while ( xx > lds64c(c.thr_s + 8u*(uint32_t)k) ) k--;
+            gq = k;
+        }
+    }
+    return outc;
+}
+
+/*  the sample's call under its ploidy: GT pair + AC increments in the int4, GQ by reference.  `has` = sample carries data.  */
+template<bool FAST>
+__device__ __forceinline__ int4 bw_call_any(int pld, bool has, bool ref_gt, double p0, double p1, double p2, double sum,
+                                            const BWConsts &c, uint32_t hap_s, int inc_hap, int &gq)
+{
+    gq = 0;
+    const int second_missing = pld==2 ? MCB_GT_MISSING : I32_VEC_END;
+    if ( !pld || !has ) return make_int4(MCB_GT_MISSING, second_missing, 0, 0);
+    if ( ref_gt ) return make_int4(MCB_GT_UNPHASED(0), pld==2 ? MCB_GT_UNPHASED(0) : I32_VEC_END, pld, 0);     /* mcall.c:713-743 */
+    if ( pld==2 ) return bw_call_sample<FAST>(p0, p1, p2, sum, c, gq);
+    return bw_call_haploid<FAST>(c.jgt0 ? p2 : p0, p2, sum, c, hap_s, inc_hap, gq);
+}
+
 __device__ __forceinline__ int4 ldg128(const int4 *p) { return __ldg(p); }
 __device__ __forceinline__ void stg128(void *p, int x, int y, int z, int w)
 {
@@ -161,6 +204,17 @@ __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefe
 __device__ __forceinline__ uint32_t ldsu8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ uint32_t byte_of(uint32_t w, int k) { return (w >> (8*k)) & 0xffu; }
 
+/*  trimmed PL row of one sample (mcall.c:1158-1194) under its ploidy; pl3: both alleles kept  */
+__device__ __forceinline__ void bw_store_pl(int32_t *out_pl, bool pl3, int s, int pld, int a, int b, int c)
+{
+    int v0 = a, v1 = b, v2 = c;
+    if ( pld==1 ) { v1 = c; v2 = I32_VEC_END; }                    /* haploid: the homozygous genotypes, then vector_end */
+    else if ( pld==0 ) { v0 = I32_MISSING; v1 = v2 = I32_VEC_END; }
+    if ( pl3 ) { int32_t *d = out_pl + 3*(size_t)s; stg32(d, v0); stg32(d+1, v1); stg32(d+2, v2); }
+    else stg32(out_pl + s, v0);
+}
+
+template<bool PLOIDY>
 __global__ void __launch_bounds__(BW_MAXWARP*32, BW_MINCTA) mcall_biallelic_warp_kernel(const KArgs a, int warp_bytes)
 {
     constexpr double LN2 = 0.693147180559945309417232121458, LN10_10 = 0.2302585092994045684017991454684;
@@ -206,6 +260,13 @@ __global__ void __launch_bounds__(BW_MAXWARP*32, BW_MINCTA) mcall_biallelic_warp
             const int nx = BW_DYNAMIC ? nsites : isite + gridDim.x*nwarp;
             if ( nx < nsites ) next_pl = reinterpret_cast<const char*>(reinterpret_cast<const int32_t*>(a.pl) + a.pl_off[a.site_list[nx]]);
         }
+        const uint8_t *ploidy = nullptr;
+        if ( PLOIDY )
+        {
+            int pid = a.ploidy_id ? a.ploidy_id[site] : 0;
+            if ( pid >= a.nploidy ) pid = 0;
+            ploidy = a.ploidy_tab + (size_t)pid*S;
+        }
         if ( lane==0 ) rec.nesc = 0;
         __syncwarp();
 
@@ -242,15 +303,17 @@ __global__ void __launch_bounds__(BW_MAXWARP*32, BW_MINCTA) mcall_biallelic_warp
         /* the pair {ALT,REF}: float32 expression then widened (mcall.c:629-630) */
         const bool live = qf1!=0 && qf0!=0;
         double cf0 = 0, cf1 = 0, cf2 = 0;      /* fa2 (ALT hom), fb2 (REF hom), 2 fa fb (het) */
+        double fa = 0, fb = 0;                 /* haploid samples: fa (ALT), fb (REF), mcall.c:642-643 */
         if ( live )
         {
             const float den = __fadd_rn(qf1, qf0);
-            const double fa = (double)__fdiv_rn(qf1, den), fb = (double)__fdiv_rn(qf0, den);
+            fa = (double)__fdiv_rn(qf1, den); fb = (double)__fdiv_rn(qf0, den);
             cf0 = __dmul_rn(fa,fa); cf1 = __dmul_rn(fb,fb); cf2 = __dmul_rn(__dmul_rn(2.0,fa),fb);
         }
 
         /* =========================== phase 1: site reduction ==================================== */
         double accP = 1.0, accN = 1.0; int eP = 0, eN = 0;          /* pair product, normaliser product */
+        double accC = 1.0; int eC = 0, cnt_called = 0;              /* PLOIDY: normaliser product / count of the samples with ploidy > 0 */
         int nmul = 0;                                               /* multiplications folded into each product */
         long long ps0 = 0, ps1 = 0;                                 /* single-allele sets: integer PL sums (mcall.c:607-611) */
         int ps0f = 0, ps1f = 0;                                     /* ... of the iterations with every PL <= 255 */
@@ -296,13 +359,15 @@ __global__ void __launch_bounds__(BW_MAXWARP*32, BW_MINCTA) mcall_biallelic_warp
 #endif
                 const int orv = pa | pb | pc;
                 double sum = 1.0, val = 1.0; bool data = false;
+                int pld = 2;
+                if ( PLOIDY ) pld = (4*g + j < S) ? (int)__ldg(ploidy + 4*g + j) : 2;
                 uint32_t tri = 0xffffffu;                               /* escape: the general path goes back to the int32 values */
                 if ( (unsigned)orv <= 255u && (pa & pb & pc) != 255 )
                 {
                     data = orv != 0;                                    /* PL=0,0,0: no data (mcall.c:529-537) */
                     const double p0 = lds64c(pl2p_s + 8u*(uint32_t)pa), p1 = lds64c(pl2p_s + 8u*(uint32_t)pb), p2 = lds64c(pl2p_s + 8u*(uint32_t)pc);
                     sum = __dadd_rn(__dadd_rn(p0, p1), p2);
-                    val = fma(cf2, p1, fma(cf1, p0, cf0*p2));
+                    val = (!PLOIDY || pld==2) ? fma(cf2, p1, fma(cf1, p0, cf0*p2)) : fma(fb, p0, fa*p2);
                     ps0f += pa; ps1f += pc;
                     tri = (uint32_t)pa | (uint32_t)pb<<8 | (uint32_t)pc<<16;
                 }
@@ -316,12 +381,14 @@ __global__ void __launch_bounds__(BW_MAXWARP*32, BW_MINCTA) mcall_biallelic_warp
                         data = bw_slow_sample_ni(&w, unseen, pl2p_s, a.tab, &tflags);
                         if ( data ) { ps0 += w.pl[0]; ps1 += w.pl[2]; }
                         sum = w.sum;
-                        val = fma(cf2, w.p[1], fma(cf1, w.p[0], cf0*w.p[2]));
+                        val = (!PLOIDY || pld==2) ? fma(cf2, w.p[1], fma(cf1, w.p[0], cf0*w.p[2])) : fma(fb, w.p[0], fa*w.p[2]);
                     }
                 }
-                cnt += data;
+                cnt += data;                                            /* single-allele sets and N_all: every sample, also ploidy 0 (mcall.c:607-611) */
                 acc_mul(accN, eN, data ? sum : 1.0);
-                acc_mul(accP, eP, (data && live) ? val : 1.0);
+                const bool called = data && (!PLOIDY || pld!=0);        /* ploidy 0: val stays 0 (mcall.c:639-644) */
+                if ( PLOIDY ) { cnt_called += called; acc_mul(accC, eC, called ? sum : 1.0); }
+                acc_mul(accP, eP, (called && live) ? val : 1.0);
 #if BW_ROLL1
                 /* 96-bit shift register: the new triple enters at the top */
                 pk[0] = __funnelshift_r(pk[0], pk[1], 24); pk[1] = __funnelshift_r(pk[1], pk[2], 24); pk[2] = (pk[2]>>24) | (tri<<8);
@@ -335,7 +402,7 @@ __global__ void __launch_bounds__(BW_MAXWARP*32, BW_MINCTA) mcall_biallelic_warp
             }
             if ( g < ngrp4 ) { sts32(buf_s + 12u*(uint32_t)g, pk[0]); sts32(buf_s + 12u*(uint32_t)g + 4u, pk[1]); sts32(buf_s + 12u*(uint32_t)g + 8u, pk[2]); }
             nmul += 4;
-            if ( (nmul & 511)==0 ) { acc_renorm(accP, eP); acc_renorm(accN, eN); }
+            if ( (nmul & 511)==0 ) { acc_renorm(accP, eP); acc_renorm(accN, eN); if ( PLOIDY ) acc_renorm(accC, eC); }
         }
         /* ---- the escaped samples, one per lane */
         __syncwarp();
@@ -344,25 +411,28 @@ __global__ void __launch_bounds__(BW_MAXWARP*32, BW_MINCTA) mcall_biallelic_warp
         #pragma unroll 1
         for (int base=0; base<nesc; base+=32)
         {
-            double sum = 1.0, val = 1.0; bool data = false;
+            double sum = 1.0, val = 1.0; bool data = false; int pld = 2;
             if ( base + lane < nesc )
             {
                 const int s = rec.esc[base + lane];
+                if ( PLOIDY ) pld = __ldg(ploidy + s);
                 BWSlow w; w.pl[0] = __ldg(site_pl + 3*s); w.pl[1] = __ldg(site_pl + 3*s + 1); w.pl[2] = __ldg(site_pl + 3*s + 2);
                 data = bw_slow_sample_ni(&w, unseen, pl2p_s, a.tab, &tflags);
                 if ( data ) { ps0 += w.pl[0]; ps1 += w.pl[2]; }
                 sum = w.sum;
-                val = fma(cf2, w.p[1], fma(cf1, w.p[0], cf0*w.p[2]));
+                val = (!PLOIDY || pld==2) ? fma(cf2, w.p[1], fma(cf1, w.p[0], cf0*w.p[2])) : fma(fb, w.p[0], fa*w.p[2]);
             }
             cnt += data;
             acc_mul(accN, eN, data ? sum : 1.0);
-            acc_mul(accP, eP, (data && live) ? val : 1.0);
+            const bool called = data && (!PLOIDY || pld!=0);
+            if ( PLOIDY ) { cnt_called += called; acc_mul(accC, eC, called ? sum : 1.0); }
+            acc_mul(accP, eP, (called && live) ? val : 1.0);
             nmul += 1;
         }
 
         /* ---- warp reduction (mantissa multiply, exponent add) */
         ps0 += ps0f; ps1 += ps1f;
-        acc_renorm(accP, eP); acc_renorm(accN, eN);
+        acc_renorm(accP, eP); acc_renorm(accN, eN); if ( PLOIDY ) acc_renorm(accC, eC);
         #pragma unroll
         for (int off=16; off; off>>=1)
         {
@@ -371,14 +441,21 @@ __global__ void __launch_bounds__(BW_MAXWARP*32, BW_MINCTA) mcall_biallelic_warp
             ps0 += __shfl_xor_sync(0xffffffffu, ps0, off); ps1 += __shfl_xor_sync(0xffffffffu, ps1, off);
             cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
             tflags |= __shfl_xor_sync(0xffffffffu, tflags, off);
+            if ( PLOIDY )
+            {
+                accC = __dmul_rn(accC, __shfl_xor_sync(0xffffffffu, accC, off)); eC += __shfl_xor_sync(0xffffffffu, eC, off);
+                cnt_called += __shfl_xor_sync(0xffffffffu, cnt_called, off);
+            }
         }
-        acc_renorm(accP, eP); acc_renorm(accN, eN);
+        acc_renorm(accP, eP); acc_renorm(accN, eN); if ( PLOIDY ) acc_renorm(accC, eC);
         /* every lane multiplied nmul values in (1.0 with biased exponent 1023 for absent samples); acc_renorm removed its own bias */
         const int n_all = cnt, nm = 32*nmul;        /* nmul is warp-uniform */
 
         /* ---- allele sets in the reference's enumeration order: lane 0 {REF}, lane 1 {ALT}, lane 2 {ALT,REF} ---- */
         {
             const double lnN = n_all ? bw_log(accN) + (double)(eN - 1023*nm)*LN2 : 0.0;
+            const int n_called = PLOIDY ? cnt_called : n_all;
+            const double lnN_called = PLOIDY ? (n_called ? bw_log(accC) + (double)(eC - 1023*nm)*LN2 : 0.0) : lnN;
             double lk = 0; bool cand = false, in_sum = false; uint32_t mask = 0;
             if ( lane < 2 )
             {
@@ -389,8 +466,8 @@ __global__ void __launch_bounds__(BW_MAXWARP*32, BW_MINCTA) mcall_biallelic_warp
             }
             else if ( lane==2 )
             {
-                const bool set = live && n_all > 0;
-                lk = set ? (bw_log(accP) + (double)(eP - 1023*nm)*LN2) - lnN : 0.0;
+                const bool set = live && n_called > 0;
+                lk = set ? (bw_log(accP) + (double)(eP - 1023*nm)*LN2) - lnN_called : 0.0;
                 lk += a.theta;
                 cand = set; in_sum = set; mask = 3u;
             }
@@ -465,11 +542,14 @@ __global__ void __launch_bounds__(BW_MAXWARP*32, BW_MINCTA) mcall_biallelic_warp
                 if ( gals & 1u ) sel[ns++] = 0;
                 if ( gals & 2u ) sel[ns++] = 1;
                 rec.nsel = ns; rec.jgt0 = ns>0 ? 4*gt_idx(sel[0], sel[0]) : 0;
-                int inc_dip = 0;
+                int inc_dip = 0, inc_hap = 0;
+                const int gn = ns;                                          /* grp->nals: alleles of the selected set */
                 for (int xx=0; xx<2; xx++)
                 {
                     rec.q[xx] = xx<ns ? (double)(sel[xx] ? qf1 : qf0) : 0.0;
                     const int nx = xx<ns ? amap[sel[xx]] : 0;
+                    if ( xx<ns && nx < gn ) inc_hap |= 1<<xx;               /* mcall.c:853 */
+                    rec.hap_out[xx] = make_int4(MCB_GT_UNPHASED(nx), I32_VEC_END, nx==0, nx==1);
                     for (int y=0; y<=xx; y++)
                     {
                         const int k = xx*(xx+1)/2 + y;
@@ -480,7 +560,7 @@ __global__ void __launch_bounds__(BW_MAXWARP*32, BW_MINCTA) mcall_biallelic_warp
                         rec.slot_out[k] = make_int4(MCB_GT_UNPHASED(ny), MCB_GT_UNPHASED(nx), (ny==0) + (nx==0), (ny==1) + (nx==1));
                     }
                 }
-                rec.inc_dip = inc_dip;
+                rec.inc_dip = inc_dip; rec.inc_hap = inc_hap;
             }
         }
         __syncwarp();
@@ -507,8 +587,9 @@ __global__ void __launch_bounds__(BW_MAXWARP*32, BW_MINCTA) mcall_biallelic_warp
             BWConsts c;
             c.q0 = rec.q[0]; c.q1 = rec.q[1]; c.slot_s = wbase_s + (uint32_t)offsetof(BWRec, slot_out); c.thr_s = thr_s;
             c.nsel = rec.nsel; c.jgt0 = rec.jgt0; c.inc_dip = rec.inc_dip; c.want_gq = want_gq;
+            const uint32_t hap_s = wbase_s + (uint32_t)offsetof(BWRec, hap_out);
+            const int inc_hap = rec.inc_hap;
 
-#if BW_P2_LANE_SAMPLES
             /* lanes take consecutive samples: GT / GQ / PL rows of a warp are contiguous, every store instruction writes whole sectors */
             const int nit2 = (S + 31) >> 5;
             #pragma unroll 1
@@ -518,81 +599,15 @@ __global__ void __launch_bounds__(BW_MAXWARP*32, BW_MINCTA) mcall_biallelic_warp
                 const int s = it*32 + lane;
                 if ( s >= S ) continue;
                 const uint32_t pa = ldsu8(buf_s + 3u*(uint32_t)s), pb = ldsu8(buf_s + 3u*(uint32_t)s + 1u), pc = ldsu8(buf_s + 3u*(uint32_t)s + 2u);
-                if ( out_pl )           /* mcall.c:1158-1194: both alleles kept, the PL vector is copied.  Escaped samples */
-                {                       /* are rewritten after the loop with their filled int32 values.                    */
-                    if ( pl3 ) { int32_t *d = out_pl + 3*(size_t)s; stg32(d, (int)pa); stg32(d+1, (int)pb); stg32(d+2, (int)pc); }
-                    else stg32(out_pl + s, (int)pa);
-                }
+                const int pld = PLOIDY ? (int)__ldg(ploidy + s) : 2;
+                /* mcall.c:1158-1194: both alleles kept, the PL vector is copied.  Escaped samples are rewritten after the loop
+                   with their filled int32 values. */
+                if ( out_pl ) bw_store_pl(out_pl, pl3, s, pld, (int)pa, (int)pb, (int)pc);
                 int4 outc; int q = 0;
                 if ( (pa & pb & pc) != 255u )
                 {
-                    if ( ref_gt ) outc = make_int4(MCB_GT_UNPHASED(0), MCB_GT_UNPHASED(0), 2, 0);         /* mcall.c:713-743 */
-                    else
-                    {
-                        const double p0 = lds64c(pl2p_s + 8u*pa), p1 = lds64c(pl2p_s + 8u*pb), p2 = lds64c(pl2p_s + 8u*pc);
-                        const double sum = __dadd_rn(__dadd_rn(p0, p1), p2);
-                        outc = bw_call_sample<true>(p0, p1, p2, sum, c, q);
-                    }
-                    if ( (pa | pb | pc)==0 ) { outc = make_int4(MCB_GT_MISSING, MCB_GT_MISSING, 0, 0); q = 0; }
-                }
-                else if ( !esc_overflow ) continue;     /* on the escape list: called after this loop */
-                else                /* list overflowed: general path on the original values, right here */
-                {
-                    BWSlow w; w.pl[0] = __ldg(site_pl + 3*s); w.pl[1] = __ldg(site_pl + 3*s + 1); w.pl[2] = __ldg(site_pl + 3*s + 2);
-                    const bool has = bw_slow_sample_ni(&w, unseen, pl2p_s, a.tab, &tflags2);
-                    outc = make_int4(MCB_GT_MISSING, MCB_GT_MISSING, 0, 0);
-                    if ( !has ) { }
-                    else if ( ref_gt ) outc = make_int4(MCB_GT_UNPHASED(0), MCB_GT_UNPHASED(0), 2, 0);
-                    else outc = bw_call_sample<false>(w.p[0], w.p[1], w.p[2], w.sum, c, q);
-                    if ( out_pl )
-                    {
-                        if ( pl3 ) { int32_t *d = out_pl + 3*(size_t)s; stg32(d, w.pl[0]); stg32(d+1, w.pl[1]); stg32(d+2, w.pl[2]); }
-                        else stg32(out_pl + s, w.pl[0]);
-                    }
-                }
-                ac0 += outc.z; ac1 += outc.w;
-                if ( out_gt ) stg64(out_gt + 2*(size_t)s, outc.x, outc.y);
-                if ( out_gq ) stg32(out_gq + s, q);
-            }
-#else
-            #pragma unroll 1
-            for (int it=0; it<niter; it++)
-            {
-                const int g = it*32 + lane;
-                if ( it < BW_PF_NEXT && lane < 12 && next_pl && (it*1536 + 128*lane) < S*12 ) prefetch_l2(next_pl + it*1536 + 128*lane);
-                if ( g >= ngrp4 ) continue;
-                uint32_t u0 = ldsu32(buf_s + 12u*(uint32_t)g), u1 = ldsu32(buf_s + 12u*(uint32_t)g + 4u), u2 = ldsu32(buf_s + 12u*(uint32_t)g + 8u);
-                const int s4 = 4*g, nv = min(4, S - s4);
-                if ( out_pl )           /* mcall.c:1158-1194: both alleles kept, the PL vector is copied.  Escaped samples are */
-                {                       /* rewritten below by the same thread with their filled int32 values.                 */
-                    int32_t *d = out_pl + 3*(size_t)s4;
-                    if ( !pl3 )
-                    {
-                        #pragma unroll
-                        for (int j=0; j<4; j++)
-                            if ( j < nv ) stg32(out_pl + s4 + j, (int)byte_of(3*j<4 ? u0 : (3*j<8 ? u1 : u2), (3*j) & 3));
-                    }
-                    else if ( nv==4 )
-                    {
-                        stg128(d,     (int)byte_of(u0,0), (int)byte_of(u0,1), (int)byte_of(u0,2), (int)byte_of(u0,3));
-                        stg128(d + 4, (int)byte_of(u1,0), (int)byte_of(u1,1), (int)byte_of(u1,2), (int)byte_of(u1,3));
-                        stg128(d + 8, (int)byte_of(u2,0), (int)byte_of(u2,1), (int)byte_of(u2,2), (int)byte_of(u2,3));
-                    }
-                    else
-                    {
-                        #pragma unroll
-                        for (int k=0; k<12; k++)
-                            if ( k/3 < nv ) stg32(d + k, (int)byte_of(k<4 ? u0 : (k<8 ? u1 : u2), k & 3));
-                    }
-                }
-                #pragma unroll (kBwUnroll2)
-                for (int j=0; j<nv; j++)
-                {
-                    const int s = s4 + j;
-                    const uint32_t pa = u0 & 0xffu, pb = (u0>>8) & 0xffu, pc = (u0>>16) & 0xffu;
-                    u0 = __funnelshift_r(u0, u1, 24); u1 = __funnelshift_r(u1, u2, 24); u2 >>= 24;    /* next sample's triple */
-                    int4 outc; int q = 0;
-                    if ( (pa & pb & pc) != 255u )
+                    const bool has = (pa | pb | pc) != 0;
+                    if ( !PLOIDY )
                     {
                         if ( ref_gt ) outc = make_int4(MCB_GT_UNPHASED(0), MCB_GT_UNPHASED(0), 2, 0);         /* mcall.c:713-743 */
                         else
@@ -601,29 +616,27 @@ __global__ void __launch_bounds__(BW_MAXWARP*32, BW_MINCTA) mcall_biallelic_warp
                             const double sum = __dadd_rn(__dadd_rn(p0, p1), p2);
                             outc = bw_call_sample<true>(p0, p1, p2, sum, c, q);
                         }
-                        if ( (pa | pb | pc)==0 ) { outc = make_int4(MCB_GT_MISSING, MCB_GT_MISSING, 0, 0); q = 0; }
+                        if ( !has ) { outc = make_int4(MCB_GT_MISSING, MCB_GT_MISSING, 0, 0); q = 0; }
                     }
-                    else if ( !esc_overflow ) continue;     /* on the escape list: called after this loop */
-                    else                /* list overflowed: general path on the original values, right here */
+                    else
                     {
-                        BWSlow w; w.pl[0] = __ldg(site_pl + 3*s); w.pl[1] = __ldg(site_pl + 3*s + 1); w.pl[2] = __ldg(site_pl + 3*s + 2);
-                        const bool has = bw_slow_sample_ni(&w, unseen, pl2p_s, a.tab, &tflags2);
-                        outc = make_int4(MCB_GT_MISSING, MCB_GT_MISSING, 0, 0);
-                        if ( !has ) { }
-                        else if ( ref_gt ) outc = make_int4(MCB_GT_UNPHASED(0), MCB_GT_UNPHASED(0), 2, 0);
-                        else outc = bw_call_sample<false>(w.p[0], w.p[1], w.p[2], w.sum, c, q);
-                        if ( out_pl )
-                        {
-                            if ( pl3 ) { int32_t *d = out_pl + 3*(size_t)s; stg32(d, w.pl[0]); stg32(d+1, w.pl[1]); stg32(d+2, w.pl[2]); }
-                            else stg32(out_pl + s, w.pl[0]);
-                        }
+                        const double p0 = lds64c(pl2p_s + 8u*pa), p1 = lds64c(pl2p_s + 8u*pb), p2 = lds64c(pl2p_s + 8u*pc);
+                        const double sum = __dadd_rn(__dadd_rn(p0, p1), p2);
+                        outc = bw_call_any<true>(pld, has, ref_gt, p0, p1, p2, sum, c, hap_s, inc_hap, q);
                     }
-                    ac0 += outc.z; ac1 += outc.w;
-                    if ( out_gt ) stg64(out_gt + 2*(size_t)s, outc.x, outc.y);
-                    if ( out_gq ) stg32(out_gq + s, q);
                 }
+                else if ( !esc_overflow ) continue;     /* on the escape list: called after this loop */
+                else                /* list overflowed: general path on the original values, right here */
+                {
+                    BWSlow w; w.pl[0] = __ldg(site_pl + 3*s); w.pl[1] = __ldg(site_pl + 3*s + 1); w.pl[2] = __ldg(site_pl + 3*s + 2);
+                    const bool has = bw_slow_sample_ni(&w, unseen, pl2p_s, a.tab, &tflags2);
+                    outc = bw_call_any<false>(pld, has, ref_gt, w.p[0], w.p[1], w.p[2], w.sum, c, hap_s, inc_hap, q);
+                    if ( out_pl ) bw_store_pl(out_pl, pl3, s, pld, w.pl[0], w.pl[1], w.pl[2]);
+                }
+                ac0 += outc.z; ac1 += outc.w;
+                if ( out_gt ) stg64(out_gt + 2*(size_t)s, outc.x, outc.y);
+                if ( out_gq ) stg32(out_gq + s, q);
             }
-#endif
             /* ---- the escaped samples, one per lane (their PL rows overwrite the 255s stored above: order the stores) */
             __syncwarp();
             if ( !esc_overflow )
@@ -633,20 +646,15 @@ __global__ void __launch_bounds__(BW_MAXWARP*32, BW_MINCTA) mcall_biallelic_warp
                 {
                     if ( base + lane >= nesc ) continue;
                     const int s = rec.esc[base + lane];
+                    const int pld = PLOIDY ? (int)__ldg(ploidy + s) : 2;
                     BWSlow w; w.pl[0] = __ldg(site_pl + 3*s); w.pl[1] = __ldg(site_pl + 3*s + 1); w.pl[2] = __ldg(site_pl + 3*s + 2);
                     const bool has = bw_slow_sample_ni(&w, unseen, pl2p_s, a.tab, &tflags2);
-                    int4 outc = make_int4(MCB_GT_MISSING, MCB_GT_MISSING, 0, 0); int q = 0;
-                    if ( !has ) { }
-                    else if ( ref_gt ) outc = make_int4(MCB_GT_UNPHASED(0), MCB_GT_UNPHASED(0), 2, 0);
-                    else outc = bw_call_sample<false>(w.p[0], w.p[1], w.p[2], w.sum, c, q);
+                    int q = 0;
+                    const int4 outc = bw_call_any<false>(pld, has, ref_gt, w.p[0], w.p[1], w.p[2], w.sum, c, hap_s, inc_hap, q);
                     ac0 += outc.z; ac1 += outc.w;
                     if ( out_gt ) stg64(out_gt + 2*(size_t)s, outc.x, outc.y);
                     if ( out_gq ) stg32(out_gq + s, q);
-                    if ( out_pl )
-                    {
-                        if ( pl3 ) { int32_t *d = out_pl + 3*(size_t)s; stg32(d, w.pl[0]); stg32(d+1, w.pl[1]); stg32(d+2, w.pl[2]); }
-                        else stg32(out_pl + s, w.pl[0]);
-                    }
+                    if ( out_pl ) bw_store_pl(out_pl, pl3, s, pld, w.pl[0], w.pl[1], w.pl[2]);
                 }
             }
         }
@@ -697,12 +705,13 @@ size_t biallelic_smem_bytes(int nsmpl, int nwarp)
 int biallelic_max_warps() { return BW_MAXWARP; }
 int biallelic_ctas_per_sm() { return BW_MINCTA; }
 
-cudaError_t launch_biallelic_warp_kernel(const KArgs &a, int grid, int nwarp, cudaStream_t st)
+cudaError_t launch_biallelic_warp_kernel(const KArgs &a, bool ploidy, int grid, int nwarp, cudaStream_t st)
 {
     const size_t smem = biallelic_smem_bytes(a.nsmpl, nwarp);
-    cudaError_t e = cudaFuncSetAttribute(mcall_biallelic_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    auto kern = ploidy ? mcall_biallelic_warp_kernel<true> : mcall_biallelic_warp_kernel<false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if ( e != cudaSuccess ) return e;
-    mcall_biallelic_warp_kernel<<<grid, nwarp*32, smem, st>>>(a, (int)biallelic_warp_bytes(a.nsmpl));
+    kern<<<grid, nwarp*32, smem, st>>>(a, (int)biallelic_warp_bytes(a.nsmpl));
     return cudaGetLastError();
 }
 

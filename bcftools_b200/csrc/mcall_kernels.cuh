@@ -76,10 +76,10 @@ size_t groups_scratch_bytes(int grid, int ngroups);
 cudaError_t launch_groups_kernel(int nals, const KArgs &a, void *scratch, int grid, cudaStream_t st);
 void generic_scratch_bytes(int grid, int ngroups, int nsmpl, size_t *grp, size_t *pl, size_t *sum);
 cudaError_t launch_generic_kernel(const KArgs &a, void *grp_scratch, void *pl_scratch, void *sum_scratch, int grid, cudaStream_t st);
-/*  warp-per-site kernel for biallelic, all-diploid, int32, single-group, GP-less calls (mcall_biallelic.cu)  */
+/*  warp-per-site kernel for biallelic, int32, single-group, GP-less calls (mcall_biallelic.cu)  */
 size_t biallelic_smem_bytes(int nsmpl, int nwarp);
 int biallelic_max_warps();
 int biallelic_ctas_per_sm();
-cudaError_t launch_biallelic_warp_kernel(const KArgs &a, int grid, int nwarp, cudaStream_t st);
+cudaError_t launch_biallelic_warp_kernel(const KArgs &a, bool ploidy, int grid, int nwarp, cudaStream_t st);
 cudaError_t launch_selftest_div(const DevTables *tab, int mode, unsigned long long n, unsigned long long seed, unsigned long long *mismatch, cudaStream_t st);
 }

@@ -228,6 +228,18 @@ def test_biallelic_warp_kernel(S, flag, oracle_built):
             got = mc.call_host(batch, compact=compact)
         st = parity.compare(got, exp, params)
         assert st["compared"] > 0, (opts, st)
+    # the same sites under mixed ploidy vectors (haploid and ploidy-0 samples): the PLOIDY instance of the kernel
+    tab = np.full((3, S), 2, np.uint8)
+    tab[1, ::2] = 1
+    tab[2, ::3] = 1
+    tab[2, 1::5] = 0
+    batch.ploidy_id = rng.integers(0, 3, R).astype(np.uint16)
+    exp, _ = oracle_built.call("port", params, batch, tab)
+    for opts, compact in (({"warp2": 14}, True), ({"warp2": 0}, False)):
+        with mcall.MCaller(params, ploidy_tab=tab, options=opts) as mc:
+            got = mc.call_host(batch, compact=compact)
+        st = parity.compare(got, exp, params)
+        assert st["compared"] > 0, (opts, st)
 
 
 def test_compacted_pl_output(oracle_built):
