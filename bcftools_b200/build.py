@@ -23,31 +23,42 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build_variant(out_path, defines, verbose=False):
-    """Experimental builds with extra -D flags (scripts/ use this for register-cap sweeps)."""
+def _compile_link(out_path, extra, verbose=False):
+    """One nvcc per source in parallel (objects under lib/obj/<name of the library>/), then one link."""
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-D" + d for d in defines] + ["-shared", "-o", out_path] + [os.path.join(CSRC, s) for s in SOURCES]
-    r = subprocess.run(cmd, capture_output=True, text=True)
+    objdir = os.path.join(os.path.dirname(LIB), "obj", os.path.basename(out_path))
+    os.makedirs(objdir, exist_ok=True)
+    procs = []
+    for s in SOURCES:
+        obj = os.path.join(objdir, os.path.basename(s) + ".o")
+        cmd = [nvcc] + NVCC_FLAGS + extra + ["-c", "-o", obj, os.path.join(CSRC, s)]
+        procs.append((obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    failed = False
+    for obj, pr in procs:
+        out = pr.communicate()[0]
+        if verbose or pr.returncode:
+            sys.stderr.write(out)
+        failed |= pr.returncode != 0
+    if failed:
+        raise RuntimeError("nvcc failed building " + out_path)
+    r = subprocess.run([nvcc, "-shared", "-o", out_path] + [o for o, _ in procs], capture_output=True, text=True)
     if verbose or r.returncode:
         sys.stderr.write(r.stdout + r.stderr)
     if r.returncode:
-        raise RuntimeError("nvcc failed building " + out_path)
+        raise RuntimeError("nvcc failed linking " + out_path)
     return out_path
+
+
+def build_variant(out_path, defines, verbose=False):
+    """Experimental builds with extra -D flags (scripts/ use this for register-cap sweeps)."""
+    return _compile_link(out_path, ["-D" + d for d in defines], verbose)
 
 
 def build(force=False, verbose=False):
     if not force and not _stale():
         return LIB
-    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-shared", "-o", LIB] + \
-          [os.path.join(CSRC, s) for s in SOURCES]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if verbose or r.returncode:
-        sys.stderr.write(r.stdout + r.stderr)
-    if r.returncode:
-        raise RuntimeError("nvcc failed building " + LIB)
-    return LIB
+    return _compile_link(LIB, ["-Xptxas", "-v"] if verbose else [], verbose)
 
 
 if __name__ == "__main__":

@@ -61,6 +61,7 @@ struct mcb_ctx
     int64_t opt_ring_bytes_c[NCLASS] = {0,0,0,0,0,0};   /* per allele-count class override of ring_bytes (0 = opt_ring_bytes) */
     int64_t opt_block_c[NCLASS] = {0,0,0,0,0,0};        /* per class override of the CTA size */
     int64_t opt_tile_bytes_c[NCLASS] = {0,0,0,0,0,0};   /* per class override of tile_bytes */
+    int64_t opt_bps_c[NCLASS] = {0,0,0,0,0,0};          /* per class cap of resident CTAs per SM (0 = as many as fit): lets classes share an SM */
     cudaStream_t cstream[NCLASS] = {};   /* one stream per allele-count class: their persistent grids overlap */
     cudaEvent_t  cev_fork = nullptr, cev_join[NCLASS] = {};
     cudaEvent_t kev[NCLASS+1] = {};      /* events around the per-class launches (time_kernels=1) */
@@ -164,6 +165,7 @@ extern "C" int mcb_set_option(mcb_ctx *ctx, const char *key, int64_t value)
     }
     else if ( !strcmp(key,"block") )         { if ( value!=0 && value!=32 && value!=64 && value!=128 && value!=256 ) return MCB_EINVAL; ctx->opt_block = value; }
     else if ( !strncmp(key,"tile_bytes_",11) && key[11]>='1' && key[11]<='5' && !key[12] ) ctx->opt_tile_bytes_c[key[11]-'0'] = value;
+    else if ( !strncmp(key,"bps_",4) && key[4]>='1' && key[4]<='5' && !key[5] ) { if ( value<0 ) return MCB_EINVAL; ctx->opt_bps_c[key[4]-'0'] = value; }
     else return MCB_EINVAL;
     return MCB_OK;
 }
@@ -505,6 +507,7 @@ static int enqueue(mcb_ctx *ctx, const mcb_batch *b, const mcb_result *r, int32_
         {
             int grid = (int)std::min<int64_t>(((int64_t)b->nsites + bw_warps - 1)/bw_warps, (int64_t)ctx->nsm*biallelic_ctas_per_sm());
             if ( ctx->opt_blocks_per_sm>0 ) grid = std::min<int>(grid, ctx->nsm*(int)std::min<int64_t>(biallelic_ctas_per_sm(), ctx->opt_blocks_per_sm));
+            if ( ctx->opt_bps_c[2]>0 ) grid = std::min<int>(grid, ctx->nsm*(int)std::min<int64_t>(biallelic_ctas_per_sm(), ctx->opt_bps_c[2]));
             cudaStream_t cs = fork ? ctx->cstream[nals] : st;
             if ( fork ) CK(cudaStreamWaitEvent(cs, ctx->cev_fork, 0));
             cudaError_t le = launch_biallelic_warp_kernel(a, ploidy, grid, bw_warps, cs);
@@ -524,6 +527,7 @@ static int enqueue(mcb_ctx *ctx, const mcb_batch *b, const mcb_result *r, int32_
         CK(site_kernel_occupancy(nals, ploidy, gpk, block, pl_es, ring, &nb));
         if ( nb<1 ) return cuda_fail(ctx, cudaErrorLaunchOutOfResources, "site kernel does not fit on an SM");
         if ( ctx->opt_blocks_per_sm>0 ) nb = std::min<int>(nb, (int)ctx->opt_blocks_per_sm);
+        if ( ctx->opt_bps_c[nals]>0 ) nb = std::min<int>(nb, (int)ctx->opt_bps_c[nals]);
         int grid = (int)std::min<int64_t>((int64_t)b->nsites, (int64_t)ctx->nsm*nb);
         cudaStream_t cs = fork ? ctx->cstream[nals] : st;
         if ( fork ) CK(cudaStreamWaitEvent(cs, ctx->cev_fork, 0));

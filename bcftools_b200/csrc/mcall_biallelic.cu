@@ -45,7 +45,7 @@ namespace mcb {
 
 struct BWRec                            /* written by lane 0 after phase 1, read by the whole warp */
 {
-    int4   slot_out[3];                 /* diploid call of slot k: {gt0, gt1, AC[0] increment, AC[1] increment} */
+    int4   slot_out[4];                 /* diploid call of slot k: {gt0, gt1, AC[0] increment, AC[1] increment}; [3] = no call (./., no AC) */
     int4   hap_out[2];                  /* haploid call of selected allele x: {gt0, vector_end, AC[0] increment, AC[1] increment} */
     double q[2];                        /* (double)qsum of the selected alleles, mcall.c:797, 820 */
     double max_qual, lk_sum, ref_lk, gap;
@@ -170,6 +170,50 @@ __device__ __forceinline__ int4 bw_call_haploid(double pA, double pB, double sum
         }
     }
     return outc;
+}
+
+
+#ifndef BW_FAST2
+#define BW_FAST2     1                  /* 1: straight-line phase 2 for the common variant site, two adjacent samples per lane */
+#endif
+
+/*  mcall_call_genotypes + GQ (mcall.c:787-878) for one diploid sample of a site whose selected set is {REF, ALT} with both
+ *  alleles kept (nsel==2, new genotypes 0/0, 0/1, 1/1 all below ngt_new) -- the same literal arithmetic as
+ *  bw_call_sample<true>, written without branches so that two samples interleave in one instruction stream:
+ *    - q1x2 = 2*q1: (2*pdg)*q1 == pdg*(2*q1) bit for bit (scaling by 2 is exact, nothing here is subnormal);
+ *    - slot 0 of the site record equals the reference's 0/0 default, so "nothing beat 0" needs no special case;
+ *    - gmax/gsum: both are float32 values widened to double (or 0), far inside the range where the shared-reciprocal
+ *      sequence IS the compiler's own fast path of `/` (a >= 2^-969, normal quotient); 0/x = 0 and 0/0 = NaN come out
+ *      of the same instructions (MUFU.RCP64H(0) = inf -> NaN), which is what mcall.c:877 sees;
+ *    - GQ: the float estimate -3.0103*lg2(x) is within 0.01 of -4.34294*log(x), so its floor is off by at most one and
+ *      one compare against each neighbouring host-libm threshold settles it; NaN compares false and is mapped to 127.
+ *  Returns the slot index (0 = s0/s0, 1 = het, 2 = s1/s1) and GQ.                                                          */
+__device__ __forceinline__ void bw_fast_sample(uint32_t pa, uint32_t pb, uint32_t pc, double q0, double q1, double q1x2,
+                                               uint32_t pl2p_s, uint32_t thr_s, int &bk, int &gq)
+{
+    const double p0 = lds64c(pl2p_s + 8u*pa), p1 = lds64c(pl2p_s + 8u*pb), p2 = lds64c(pl2p_s + 8u*pc);
+    const double sum = __dadd_rn(__dadd_rn(p0, p1), p2);
+    const double r = rcp_shared(sum);
+    const double g0 = __dmul_rn(__dmul_rn(div_shared(p0, sum, r), q0), q0);
+    const double g2 = __dmul_rn(__dmul_rn(div_shared(p2, sum, r), q1), q1);
+    const double g1 = __dmul_rn(__dmul_rn(div_shared(p1, sum, r), q1x2), q0);
+    /* homs in ascending allele order, then the het, strict `<` (mcall.c:787-835) */
+    double best = 0.0 < g0 ? g0 : 0.0;
+    const bool b2 = best < g2; best = b2 ? g2 : best;
+    const bool b1 = best < g1; best = b1 ? g1 : best;
+    bk = b1 ? 1 : (b2 ? 2 : 0);
+    /* mcall.c:843-878: max and sum over the float32 gps[] in new-genotype order 0/0, 0/1, 1/1 */
+    const double f0 = (double)__double2float_rn(g0), f1 = (double)__double2float_rn(g1), f2 = (double)__double2float_rn(g2);
+    const double gmax = (double)__double2float_rn(best);         /* float rounding is monotone */
+    const double gsum = __dadd_rn(__dadd_rn(f0, f1), f2);
+    const double rs = rcp_shared(gsum);
+    const double xx = __dadd_rn(1.0, -div_shared(gmax, gsum, rs));
+    int k = __float2int_rz(-3.0102999f*lg2_approx((float)xx));
+    k = max(0, min(127, k));
+    const double t0 = lds64c(thr_s + 8u*(uint32_t)k), t1 = lds64c(thr_s + 8u*(uint32_t)k + 8u);
+    k += (xx <= t1) ? 1 : 0;
+    k -= (xx > t0) ? 1 : 0;
+    gq = (xx==xx) ? k : 127;            /* NaN (0/0): `max<=INT8_MAX` is false => INT8_MAX */
 }
 
 /*  the sample's call under its ploidy: GT pair + AC increments in the int4, GQ by reference.  `has` = sample carries data.  */
@@ -561,6 +605,7 @@ __global__ void __launch_bounds__(BW_MAXWARP*32, BW_MINCTA) mcall_biallelic_warp
                     }
                 }
                 rec.inc_dip = inc_dip; rec.inc_hap = inc_hap;
+                rec.slot_out[3] = make_int4(MCB_GT_MISSING, MCB_GT_MISSING, 0, 0);
             }
         }
         __syncwarp();
@@ -590,6 +635,49 @@ __global__ void __launch_bounds__(BW_MAXWARP*32, BW_MINCTA) mcall_biallelic_warp
             const uint32_t hap_s = wbase_s + (uint32_t)offsetof(BWRec, hap_out);
             const int inc_hap = rec.inc_hap;
 
+#if BW_FAST2
+            /*  The common variant site -- every sample diploid, {REF,ALT} selected and both kept, GT + GQ + PL all written,
+             *  no escape-list overflow, an even sample count (16-byte aligned GT pairs): straight-line code, each lane takes
+             *  TWO ADJACENT samples per iteration so that their dependency chains interleave and GT / GQ / PL of the pair
+             *  leave as one 128-bit, one 64-bit and three 64-bit stores (a warp still writes contiguous rows).  */
+            const bool fast2 = !PLOIDY && !ref_gt && c.nsel==2 && c.inc_dip==7 && want_gq && out_pl && pl3 && out_gt && out_gq
+                               && !esc_overflow && !(S & 1);
+            if ( fast2 )
+            {
+                const double q1x2 = __dmul_rn(2.0, c.q1);
+                const int npair = S >> 1;
+                #pragma unroll 1
+                for (int pr=lane; pr<npair; pr+=32)
+                {
+                    const uint32_t ad = buf_s + 6u*(uint32_t)pr;
+                    const uint32_t pa0 = ldsu8(ad), pb0 = ldsu8(ad + 1u), pc0 = ldsu8(ad + 2u);
+                    const uint32_t pa1 = ldsu8(ad + 3u), pb1 = ldsu8(ad + 4u), pc1 = ldsu8(ad + 5u);
+                    int32_t *dpl = out_pl + 6*(size_t)pr;       /* escaped samples: placeholders, rewritten after the loop */
+                    stg64(dpl, (int)pa0, (int)pb0); stg64(dpl + 2, (int)pc0, (int)pa1); stg64(dpl + 4, (int)pb1, (int)pc1);
+                    int k0, k1, q0, q1;
+                    bw_fast_sample(pa0, pb0, pc0, c.q0, c.q1, q1x2, pl2p_s, thr_s, k0, q0);
+                    bw_fast_sample(pa1, pb1, pc1, c.q0, c.q1, q1x2, pl2p_s, thr_s, k1, q1);
+                    const bool has0 = (pa0 | pb0 | pc0) != 0, has1 = (pa1 | pb1 | pc1) != 0;     /* PL=0,0,0: no data (mcall.c:529-537) */
+                    const bool esc0 = (pa0 & pb0 & pc0) == 255u, esc1 = (pa1 & pb1 & pc1) == 255u;
+                    const int4 o0 = lds128(c.slot_s + 16u*(uint32_t)((has0 && !esc0) ? k0 : 3));
+                    const int4 o1 = lds128(c.slot_s + 16u*(uint32_t)((has1 && !esc1) ? k1 : 3));
+                    ac0 += o0.z + o1.z; ac1 += o0.w + o1.w;
+                    q0 = has0 ? q0 : 0; q1 = has1 ? q1 : 0;
+                    if ( !(esc0 | esc1) )
+                    {
+                        stg128(out_gt + 4*(size_t)pr, o0.x, o0.y, o1.x, o1.y);
+                        stg64(out_gq + 2*(size_t)pr, q0, q1);
+                    }
+                    else            /* on the escape list: called after this loop */
+                    {
+                        if ( !esc0 ) { stg64(out_gt + 4*(size_t)pr, o0.x, o0.y); stg32(out_gq + 2*(size_t)pr, q0); }
+                        if ( !esc1 ) { stg64(out_gt + 4*(size_t)pr + 2, o1.x, o1.y); stg32(out_gq + 2*(size_t)pr + 1, q1); }
+                    }
+                }
+            }
+            else
+#endif
+            {
             /* lanes take consecutive samples: GT / GQ / PL rows of a warp are contiguous, every store instruction writes whole sectors */
             const int nit2 = (S + 31) >> 5;
             #pragma unroll 1
@@ -636,6 +724,7 @@ __global__ void __launch_bounds__(BW_MAXWARP*32, BW_MINCTA) mcall_biallelic_warp
                 ac0 += outc.z; ac1 += outc.w;
                 if ( out_gt ) stg64(out_gt + 2*(size_t)s, outc.x, outc.y);
                 if ( out_gq ) stg32(out_gq + s, q);
+            }
             }
             /* ---- the escaped samples, one per lane (their PL rows overwrite the 255s stored above: order the stores) */
             __syncwarp();
