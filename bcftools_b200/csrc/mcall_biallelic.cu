@@ -177,45 +177,6 @@ __device__ __forceinline__ int4 bw_call_haploid(double pA, double pB, double sum
 #define BW_FAST2     1                  /* 1: straight-line phase 2 for the common variant site, two adjacent samples per lane */
 #endif
 
-/*  mcall_call_genotypes + GQ (mcall.c:787-878) for one diploid sample of a site whose selected set is {REF, ALT} with both
- *  alleles kept (nsel==2, new genotypes 0/0, 0/1, 1/1 all below ngt_new) -- the same literal arithmetic as
- *  bw_call_sample<true>, written without branches so that two samples interleave in one instruction stream:
- *    - q1x2 = 2*q1: (2*pdg)*q1 == pdg*(2*q1) bit for bit (scaling by 2 is exact, nothing here is subnormal);
- *    - slot 0 of the site record equals the reference's 0/0 default, so "nothing beat 0" needs no special case;
- *    - gmax/gsum: both are float32 values widened to double (or 0), far inside the range where the shared-reciprocal
- *      sequence IS the compiler's own fast path of `/` (a >= 2^-969, normal quotient); 0/x = 0 and 0/0 = NaN come out
- *      of the same instructions (MUFU.RCP64H(0) = inf -> NaN), which is what mcall.c:877 sees;
- *    - GQ: the float estimate -3.0103*lg2(x) is within 0.01 of -4.34294*log(x), so its floor is off by at most one and
- *      one compare against each neighbouring host-libm threshold settles it; NaN compares false and is mapped to 127.
- *  Returns the slot index (0 = s0/s0, 1 = het, 2 = s1/s1) and GQ.                                                          */
-__device__ __forceinline__ void bw_fast_sample(uint32_t pa, uint32_t pb, uint32_t pc, double q0, double q1, double q1x2,
-                                               uint32_t pl2p_s, uint32_t thr_s, int &bk, int &gq)
-{
-    const double p0 = lds64c(pl2p_s + 8u*pa), p1 = lds64c(pl2p_s + 8u*pb), p2 = lds64c(pl2p_s + 8u*pc);
-    const double sum = __dadd_rn(__dadd_rn(p0, p1), p2);
-    const double r = rcp_shared(sum);
-    const double g0 = __dmul_rn(__dmul_rn(div_shared(p0, sum, r), q0), q0);
-    const double g2 = __dmul_rn(__dmul_rn(div_shared(p2, sum, r), q1), q1);
-    const double g1 = __dmul_rn(__dmul_rn(div_shared(p1, sum, r), q1x2), q0);
-    /* homs in ascending allele order, then the het, strict `<` (mcall.c:787-835) */
-    double best = 0.0 < g0 ? g0 : 0.0;
-    const bool b2 = best < g2; best = b2 ? g2 : best;
-    const bool b1 = best < g1; best = b1 ? g1 : best;
-    bk = b1 ? 1 : (b2 ? 2 : 0);
-    /* mcall.c:843-878: max and sum over the float32 gps[] in new-genotype order 0/0, 0/1, 1/1 */
-    const double f0 = (double)__double2float_rn(g0), f1 = (double)__double2float_rn(g1), f2 = (double)__double2float_rn(g2);
-    const double gmax = (double)__double2float_rn(best);         /* float rounding is monotone */
-    const double gsum = __dadd_rn(__dadd_rn(f0, f1), f2);
-    const double rs = rcp_shared(gsum);
-    const double xx = __dadd_rn(1.0, -div_shared(gmax, gsum, rs));
-    int k = __float2int_rz(-3.0102999f*lg2_approx((float)xx));
-    k = max(0, min(127, k));
-    const double t0 = lds64c(thr_s + 8u*(uint32_t)k), t1 = lds64c(thr_s + 8u*(uint32_t)k + 8u);
-    k += (xx <= t1) ? 1 : 0;
-    k -= (xx > t0) ? 1 : 0;
-    gq = (xx==xx) ? k : 127;            /* NaN (0/0): `max<=INT8_MAX` is false => INT8_MAX */
-}
-
 /*  the sample's call under its ploidy: GT pair + AC increments in the int4, GQ by reference.  `has` = sample carries data.  */
 template<bool FAST>
 __device__ __forceinline__ int4 bw_call_any(int pld, bool has, bool ref_gt, double p0, double p1, double p2, double sum,
@@ -358,7 +319,7 @@ __global__ void __launch_bounds__(BW_MAXWARP*32, BW_MINCTA) mcall_biallelic_warp
         /* =========================== phase 1: site reduction ==================================== */
         double accP = 1.0, accN = 1.0; int eP = 0, eN = 0;          /* pair product, normaliser product */
         double accC = 1.0; int eC = 0, cnt_called = 0;              /* PLOIDY: normaliser product / count of the samples with ploidy > 0 */
-        int nmul = 0;                                               /* multiplications folded into each product */
+        int nmul = 0, nslow = 0;                                    /* multiplications folded into each product (warp-uniform) / of this lane's overflow samples */
         long long ps0 = 0, ps1 = 0;                                 /* single-allele sets: integer PL sums (mcall.c:607-611) */
         int ps0f = 0, ps1f = 0;                                     /* ... of the iterations with every PL <= 255 */
         int cnt = 0;
@@ -375,32 +336,26 @@ __global__ void __launch_bounds__(BW_MAXWARP*32, BW_MINCTA) mcall_biallelic_warp
                 v0 = make_int4(x[0],x[1],x[2],x[3]); v1 = make_int4(x[4],x[5],x[6],x[7]); v2 = make_int4(x[8],x[9],x[10],x[11]);
             }
         };
+        /*  The 4 samples of an iteration are multiplied together as plain doubles (each factor is in [1e-26, 3]) and enter the
+         *  exponent-tracked products once per iteration.  (Measured dead end: packing the 12 raw int32 to bytes first and
+         *  issuing the loads of the NEXT iteration before the arithmetic of this one -- the byte extraction and the longer
+         *  register lives cost more than the hidden L2 latency gains: class 0.95 -> 1.07 ms.)  */
+        const char *pf = reinterpret_cast<const char*>(site_pl) + (size_t)BW_PF_DIST*1536 + 128*lane;
         #pragma unroll 1
         for (int it=0; it<niter; it++)
         {
             const int g = it*32 + lane;
-            if ( lane < 12 )            /* 12 lines of 128 bytes = the 128 samples of iteration it+BW_PF_DIST */
-            {
-                const char *pf = reinterpret_cast<const char*>(site_pl) + (size_t)(it + BW_PF_DIST)*1536 + 128*lane;
-                if ( pf < site_end ) prefetch_l2(pf);
-            }
+            if ( lane < 12 && pf < site_end ) prefetch_l2(pf);      /* 12 lines of 128 bytes = the 128 samples of iteration it+BW_PF_DIST */
+            pf += 1536;
             int4 v0, v1, v2;
             load_group(g, v0, v1, v2);
-            int x[12] = { v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w };
+            const int x[12] = { v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w };
             uint32_t pk[3] = {0,0,0};
-#if BW_ROLL1
-            #pragma unroll 1
-            for (int j=0; j<4; j++)
-            {
-                const int pa = x[0], pb = x[1], pc = x[2];
-                #pragma unroll
-                for (int k=0; k<9; k++) x[k] = x[k+3];
-#else
+            double lN = 1.0, lP = 1.0, lC = 1.0;
             #pragma unroll
             for (int j=0; j<4; j++)
             {
                 const int pa = x[3*j], pb = x[3*j+1], pc = x[3*j+2];
-#endif
                 const int orv = pa | pb | pc;
                 double sum = 1.0, val = 1.0; bool data = false;
                 int pld = 2;
@@ -422,31 +377,42 @@ __global__ void __launch_bounds__(BW_MAXWARP*32, BW_MINCTA) mcall_biallelic_warp
                     else                                                                    /* list full: right here */
                     {
                         BWSlow w; w.pl[0] = pa; w.pl[1] = pb; w.pl[2] = pc;
-                        data = bw_slow_sample_ni(&w, unseen, pl2p_s, a.tab, &tflags);
-                        if ( data ) { ps0 += w.pl[0]; ps1 += w.pl[2]; }
-                        sum = w.sum;
-                        val = (!PLOIDY || pld==2) ? fma(cf2, w.p[1], fma(cf1, w.p[0], cf0*w.p[2])) : fma(fb, w.p[0], fa*w.p[2]);
+                        const bool sdata = bw_slow_sample_ni(&w, unseen, pl2p_s, a.tab, &tflags);
+                        if ( sdata ) { ps0 += w.pl[0]; ps1 += w.pl[2]; }
+                        const double sval = (!PLOIDY || pld==2) ? fma(cf2, w.p[1], fma(cf1, w.p[0], cf0*w.p[2])) : fma(fb, w.p[0], fa*w.p[2]);
+                        /* values of the big-PL table can be tiny: straight into the exponent-tracked products */
+                        cnt += sdata;
+                        const bool scalled = sdata && (!PLOIDY || pld!=0);
+                        acc_mul(accN, eN, sdata ? w.sum : 1.0);
+                        if ( PLOIDY ) { cnt_called += scalled; acc_mul(accC, eC, scalled ? w.sum : 1.0); }
+                        acc_mul(accP, eP, (scalled && live) ? sval : 1.0);
+                        nslow++;
                     }
                 }
                 cnt += data;                                            /* single-allele sets and N_all: every sample, also ploidy 0 (mcall.c:607-611) */
-                acc_mul(accN, eN, data ? sum : 1.0);
                 const bool called = data && (!PLOIDY || pld!=0);        /* ploidy 0: val stays 0 (mcall.c:639-644) */
-                if ( PLOIDY ) { cnt_called += called; acc_mul(accC, eC, called ? sum : 1.0); }
-                acc_mul(accP, eP, (called && live) ? val : 1.0);
-#if BW_ROLL1
-                /* 96-bit shift register: the new triple enters at the top */
-                pk[0] = __funnelshift_r(pk[0], pk[1], 24); pk[1] = __funnelshift_r(pk[1], pk[2], 24); pk[2] = (pk[2]>>24) | (tri<<8);
-#else
+                const double fN = data ? sum : 1.0, fP = (called && live) ? val : 1.0, fC = called ? sum : 1.0;
+                lN = j ? __dmul_rn(lN, fN) : fN; lP = j ? __dmul_rn(lP, fP) : fP;
+                if ( PLOIDY ) { cnt_called += called; lC = j ? __dmul_rn(lC, fC) : fC; }
                 /* byte 3j+k of the 12-byte group */
                 if ( j==0 ) pk[0] |= tri;
                 if ( j==1 ) { pk[0] |= tri<<24; pk[1] |= tri>>8; }
                 if ( j==2 ) { pk[1] |= tri<<16; pk[2] |= tri>>16; }
                 if ( j==3 ) pk[2] |= tri<<8;
-#endif
             }
             if ( g < ngrp4 ) { sts32(buf_s + 12u*(uint32_t)g, pk[0]); sts32(buf_s + 12u*(uint32_t)g + 4u, pk[1]); sts32(buf_s + 12u*(uint32_t)g + 8u, pk[2]); }
-            nmul += 4;
-            if ( (nmul & 511)==0 ) { acc_renorm(accP, eP); acc_renorm(accN, eN); if ( PLOIDY ) acc_renorm(accC, eC); }
+            acc_mul(accN, eN, lN); acc_mul(accP, eP, lP); if ( PLOIDY ) acc_mul(accC, eC, lC);
+            nmul += 1;
+            if ( (nmul & 255)==0 ) { acc_renorm(accP, eP); acc_renorm(accN, eN); if ( PLOIDY ) acc_renorm(accC, eC); }
+        }
+        /*  acc_mul calls made outside the warp-uniform count (escape-list overflow, a handful of samples at most): level
+            every lane to the warp's maximum with multiplications by 1.0 so that the exponent bias stays 1023 per call  */
+        {
+            int mx = nslow;
+            #pragma unroll
+            for (int off=16; off; off>>=1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+            for (int k=nslow; k<mx; k++) { acc_mul(accN, eN, 1.0); acc_mul(accP, eP, 1.0); if ( PLOIDY ) acc_mul(accC, eC, 1.0); }
+            nmul += mx;
         }
         /* ---- the escaped samples, one per lane */
         __syncwarp();
@@ -655,8 +621,14 @@ __global__ void __launch_bounds__(BW_MAXWARP*32, BW_MINCTA) mcall_biallelic_warp
                     int32_t *dpl = out_pl + 6*(size_t)pr;       /* escaped samples: placeholders, rewritten after the loop */
                     stg64(dpl, (int)pa0, (int)pb0); stg64(dpl + 2, (int)pc0, (int)pa1); stg64(dpl + 4, (int)pb1, (int)pc1);
                     int k0, k1, q0, q1;
-                    bw_fast_sample(pa0, pb0, pc0, c.q0, c.q1, q1x2, pl2p_s, thr_s, k0, q0);
-                    bw_fast_sample(pa1, pb1, pc1, c.q0, c.q1, q1x2, pl2p_s, thr_s, k1, q1);
+                    {
+                        const double p0 = lds64c(pl2p_s + 8u*pa0), p1 = lds64c(pl2p_s + 8u*pb0), p2 = lds64c(pl2p_s + 8u*pc0);
+                        fast2_call(p0, p1, p2, __dadd_rn(__dadd_rn(p0, p1), p2), c.q0, c.q1, q1x2, thr_s, k0, q0);
+                    }
+                    {
+                        const double p0 = lds64c(pl2p_s + 8u*pa1), p1 = lds64c(pl2p_s + 8u*pb1), p2 = lds64c(pl2p_s + 8u*pc1);
+                        fast2_call(p0, p1, p2, __dadd_rn(__dadd_rn(p0, p1), p2), c.q0, c.q1, q1x2, thr_s, k1, q1);
+                    }
                     const bool has0 = (pa0 | pb0 | pc0) != 0, has1 = (pa1 | pb1 | pc1) != 0;     /* PL=0,0,0: no data (mcall.c:529-537) */
                     const bool esc0 = (pa0 & pb0 & pc0) == 255u, esc1 = (pa1 & pb1 & pc1) == 255u;
                     const int4 o0 = lds128(c.slot_s + 16u*(uint32_t)((has0 && !esc0) ? k0 : 3));

@@ -10,6 +10,9 @@
 #ifndef MCB_UNROLL2
 #define MCB_UNROLL2 1       /* unroll factor of the phase-2 sample loop */
 #endif
+#ifndef MCB_FAST2
+#define MCB_FAST2 1         /* straight-line phase 2 for sites whose selected set is a pair (two adjacent samples per lane) */
+#endif
 
 namespace mcb {
 
@@ -735,6 +738,16 @@ __global__ void __launch_bounds__(BLOCK, (MinBlocks<NALS,BLOCK>::value)) mcall_s
             #pragma unroll
             for (int k=0; k<NPLM; k++) plm4[k] = ES*sh.pl_map[k];
             const uint32_t oflags = (out_gt ? 1u : 0u) | (out_gq ? 2u : 0u) | (out_pl ? 4u : 0u) | (out_gp ? 8u : 0u);
+            /*  fast2: every sample diploid, the selected set is a pair s0<s1 whose alleles are exactly the kept ones (new alleles
+             *  0 and 1, all three new genotypes below ngt_new), GT + GQ + PL all written, int32 PLs, an even sample count
+             *  and 16-byte aligned outputs (pairs of samples leave in vector stores).  CTA-uniform.  */
+            constexpr bool FAST2 = MCB_FAST2 && !PLOIDY && !GPOUT && ES==4 && NALS>=2;
+            const bool fast2 = FAST2 && !ref_gt && nsel==2 && (inc_dip & 7u)==7u && nals_new==2 && sh.als_new==sh.grp_als && want_gq
+                               && oflags==7u && !(nsmpl & 1) && !(TS & 1)
+                               && !((reinterpret_cast<uintptr_t>(out_gt) & 15) | (reinterpret_cast<uintptr_t>(out_gq) & 7) | (reinterpret_cast<uintptr_t>(out_pl) & 7));
+            const double fq0 = q0, fq1 = q1, fq1x2 = __dmul_rn(2.0, q1);
+            const int fj0 = jgt4[0], fj1 = jgt4[NSLOT>1 ? 1 : 0], fj2 = jgt4[NSLOT>2 ? 2 : 0];
+            int f_alt = 0, f_called = 0;
             unsigned long long acc = 0;     /* AC: 12-bit counters, new allele j at bits [12j,12j+12) */
             int acc_n = 0;
             uint32_t tflags2 = 0;
@@ -765,13 +778,80 @@ __global__ void __launch_bounds__(BLOCK, (MinBlocks<NALS,BLOCK>::value)) mcall_s
                 }
                 const uint32_t tile_s = ring_s + (uint32_t)(ES*stage*tile_ints);
                 const int s0 = t*TS, n = min(TS, nsmpl - s0);
-                if ( acc_n + (TS + BLOCK - 1)/BLOCK > 63 ) flush_ac();     /* uniform across the block: safe to shuffle */
-                acc_n += (TS + BLOCK - 1)/BLOCK;
-                #pragma unroll (kUnroll2)
-                for (int sb=0; sb<n; sb+=BLOCK)         /* uniform trip count: the loader votes across the warp */
+                const int per_tile = 2*((TS + 2*BLOCK - 1)/(2*BLOCK));     /* samples of a tile per thread */
+                if ( acc_n + per_tile > 63 ) flush_ac();                    /* uniform across the block: safe to shuffle */
+                acc_n += per_tile;
+                #pragma unroll 1
+                for (int sb=0; sb<n; sb+=2*BLOCK)       /* uniform trip count: the loaders vote across the warp */
                 {
-                    const int s = min(sb + tid, n-1);
-                    const bool valid = sb + tid < n;
+                const int wb = sb + 64*warp;            /* a warp owns 64 consecutive samples per iteration */
+                bool done = false;
+                if constexpr ( FAST2 ) if ( fast2 )
+                {
+                    /*  The common variant site (see fast2 above): each lane takes TWO ADJACENT samples, straight-line code
+                     *  (fast2_call), GT / GQ / PL of the pair leave as one 128-bit and four 64-bit stores.  A warp whose 64
+                     *  samples hold a missing value or a PL >= 256 votes itself onto the general path below.  */
+                    const int sp = wb + 2*lane;
+                    const bool valid = sp < n;
+                    const uint32_t row_s = tile_s + (uint32_t)((valid ? sp : 0)*G*4);
+                    int pl2[2*G];
+                    if constexpr ( (G & 1)==0 )
+                    {
+                        #pragma unroll
+                        for (int j=0; j<2*G; j+=4) { const int4 v = lds128(row_s + 4u*j); pl2[j] = v.x; pl2[j+1] = v.y; pl2[j+2] = v.z; pl2[j+3] = v.w; }
+                    }
+                    else
+                    {
+                        #pragma unroll
+                        for (int j=0; j<2*G; j+=2) { pl2[j] = lds32(row_s + 4u*j); pl2[j+1] = lds32(row_s + 4u*j + 4u); }
+                    }
+                    int orv0 = 0, orv1 = 0;
+                    #pragma unroll
+                    for (int j=0; j<G; j++) { orv0 |= pl2[j]; orv1 |= pl2[G+j]; }
+                    if ( !__any_sync(0xffffffffu, (unsigned)(orv0 | orv1) > 255u) )
+                    {
+                        done = true;
+                        if ( valid )
+                        {
+                            int k0, k1, g0, g1;
+                            const int a0 = lds32(row_s + (uint32_t)fj0), b0 = lds32(row_s + (uint32_t)fj1), c0 = lds32(row_s + (uint32_t)fj2);
+                            const int a1 = lds32(row_s + (uint32_t)(4*G) + (uint32_t)fj0), b1 = lds32(row_s + (uint32_t)(4*G) + (uint32_t)fj1), c1 = lds32(row_s + (uint32_t)(4*G) + (uint32_t)fj2);
+                            {
+                                double sum = lds64c(pl2p_s + 8u*(uint32_t)pl2[0]);
+                                #pragma unroll
+                                for (int j=1; j<G; j++) sum = __dadd_rn(sum, lds64c(pl2p_s + 8u*(uint32_t)pl2[j]));
+                                fast2_call(lds64c(pl2p_s + 8u*(uint32_t)a0), lds64c(pl2p_s + 8u*(uint32_t)b0), lds64c(pl2p_s + 8u*(uint32_t)c0),
+                                           sum, fq0, fq1, fq1x2, thr_s, k0, g0);
+                            }
+                            {
+                                double sum = lds64c(pl2p_s + 8u*(uint32_t)pl2[G]);
+                                #pragma unroll
+                                for (int j=1; j<G; j++) sum = __dadd_rn(sum, lds64c(pl2p_s + 8u*(uint32_t)pl2[G+j]));
+                                fast2_call(lds64c(pl2p_s + 8u*(uint32_t)a1), lds64c(pl2p_s + 8u*(uint32_t)b1), lds64c(pl2p_s + 8u*(uint32_t)c1),
+                                           sum, fq0, fq1, fq1x2, thr_s, k1, g1);
+                            }
+                            const bool has0 = orv0 != 0, has1 = orv1 != 0;      /* PL=0,..,0: no data (mcall.c:529-537) */
+                            /* new alleles 0 and 1: GT codes 2 and 4, slot index = copies of allele 1; no data: ./. and GQ 0 */
+                            const int x0 = has0 ? (k0==2 ? 4 : 2) : 0, y0 = has0 ? (k0 ? 4 : 2) : 0;
+                            const int x1 = has1 ? (k1==2 ? 4 : 2) : 0, y1 = has1 ? (k1 ? 4 : 2) : 0;
+                            f_alt += (has0 ? k0 : 0) + (has1 ? k1 : 0); f_called += (int)has0 + (int)has1;
+                            const size_t sg = (size_t)(s0 + sp);
+                            asm volatile("st.global.v4.s32 [%0], {%1,%2,%3,%4};" :: "l"(out_gt + sg), "r"(x0), "r"(y0), "r"(x1), "r"(y1) : "memory");
+                            asm volatile("st.global.v2.s32 [%0], {%1,%2};" :: "l"(out_gq + sg), "r"(has0 ? g0 : 0), "r"(has1 ? g1 : 0) : "memory");
+                            const int32_t *dst = out_pl + 3*sg;             /* mcall.c:1158-1194: the kept genotypes are the three slots */
+                            asm volatile("st.global.v2.s32 [%0], {%1,%2};" :: "l"(dst), "r"(a0), "r"(b0) : "memory");
+                            asm volatile("st.global.v2.s32 [%0+8], {%1,%2};" :: "l"(dst), "r"(c0), "r"(a1) : "memory");
+                            asm volatile("st.global.v2.s32 [%0+16], {%1,%2};" :: "l"(dst), "r"(b1), "r"(c1) : "memory");
+                        }
+                    }
+                }
+                if ( !done )
+                #pragma unroll 1
+                for (int half=0; half<2; half++)
+                {
+                    const int sidx = wb + 32*half + lane;
+                    const int s = min(sidx, n-1);
+                    const bool valid = sidx < n;
                     int pl[G]; double p[G]; double sum = 1; bool fast;
                     const uint32_t row_s = tile_s + (uint32_t)(s*G*ES);
                     const bool has = load_sample_w<NALS,PT>(row_s, pl2p_s, valid, unseen, a.tab, pl, p, sum, fast, tflags2);
@@ -972,6 +1052,7 @@ __global__ void __launch_bounds__(BLOCK, (MinBlocks<NALS,BLOCK>::value)) mcall_s
                         }
                     }
                 }
+                }
                 if ( !resident )
                 {
                     fence_proxy_async();
@@ -980,6 +1061,12 @@ __global__ void __launch_bounds__(BLOCK, (MinBlocks<NALS,BLOCK>::value)) mcall_s
                 }
             }
             flush_ac();
+            if constexpr ( FAST2 ) if ( fast2 )
+            {
+                #pragma unroll
+                for (int off=16; off; off>>=1) { f_alt += __shfl_xor_sync(0xffffffffu, f_alt, off); f_called += __shfl_xor_sync(0xffffffffu, f_called, off); }
+                if ( lane==0 && f_called ) { atomicAdd(&sh.ac[0], 2*f_called - f_alt); atomicAdd(&sh.ac[1], f_alt); }
+            }
             if ( tflags2 ) atomicOr(&sh.flags, tflags2);
         }
         __syncthreads();
