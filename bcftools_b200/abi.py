@@ -58,6 +58,7 @@ class McbResult(C.Structure):
         ("ret", C.c_void_p), ("als_new", C.c_void_p), ("als_map", C.c_void_p), ("qual", C.c_void_p),
         ("ac", C.c_void_p), ("an", C.c_void_p), ("site_flags", C.c_void_p), ("diag", C.c_void_p),
         ("gt", C.c_void_p), ("gq", C.c_void_p), ("gp", C.c_void_p), ("pl", C.c_void_p), ("pl_off_out", C.c_void_p),
+        ("gt8", C.c_void_p), ("gq8", C.c_void_p), ("pl16", C.c_void_p),
     ]
 
 
@@ -70,6 +71,7 @@ RESULT_FIELDS = {
     "ret": np.int32, "als_new": np.uint32, "als_map": np.int8, "qual": np.float32, "ac": np.int32,
     "an": np.int32, "site_flags": np.uint32, "diag": np.float64, "gt": np.int32, "gq": np.int32,
     "gp": np.float32, "pl": np.int32, "pl_off_out": np.int64,
+    "gt8": np.int8, "gq8": np.int8, "pl16": np.int16,
 }
 
 
@@ -213,8 +215,9 @@ class HostBatch:
 class HostResult:
     """numpy arrays of one mcb_result (host memory), sized for a HostBatch."""
 
-    def __init__(self, batch, want_gp=False, fill=True, compact=False):
+    def __init__(self, batch, want_gp=False, fill=True, compact=False, typed=False):
         R, S, M = batch.nsites, batch.nsmpl, batch.max_nals
+        self.typed = typed
         self.batch = batch
         self.ret = np.zeros(R, np.int32)
         self.als_new = np.zeros(R, np.uint32)
@@ -230,6 +233,24 @@ class HostResult:
         self.pl = np.zeros(batch.pl.size, np.int32)
         # compact=True: trimmed PL/GP blocks are packed at the front of pl/gp, site i at pl_off_out[i]
         self.pl_off_out = np.full(R, -1, np.int64) if compact else None
+        # typed=True (mcb_call_host): GT/GQ/PL arrive as BCF typed vectors (int8/int8/int16) instead of int32
+        self.gt8 = self.gq8 = self.pl16 = None
+        if typed:
+            self.gt8 = np.zeros((R, S, 2), np.int8)
+            self.gq8 = np.zeros((R, S), np.int8)
+            self.pl16 = np.zeros(batch.pl.size, np.int16)
+            self.gt = self.gq = self.pl = None
+
+    def widen(self):
+        """typed results -> the int32 arrays of the reference interface (BCF sentinels mapped to the int32 ones)."""
+        def w(a, bits):
+            lo = -(1 << (bits - 1))
+            o = a.astype(np.int32)
+            o[a == lo] = np.iinfo(np.int32).min
+            o[a == lo + 1] = np.iinfo(np.int32).min + 1
+            return o
+        self.gt, self.gq, self.pl = w(self.gt8, 8), w(self.gq8, 8), w(self.pl16, 16)
+        return self
 
     def _out_off(self, i):
         return self.batch.pl_off[i] if self.pl_off_out is None else self.pl_off_out[i]

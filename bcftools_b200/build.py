@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "lib", "libmcall_b200.so")
-SOURCES = ["mcall_kernels.cu", "mcall_groups.cu", "mcall_biallelic.cu", "mcall_generic.cu", "mcall_abi.cu", os.path.join("host", "b200_call.c")]
+SOURCES = ["mcall_kernels.cu", "mcall_groups.cu", "mcall_biallelic.cu", "mcall_pair.cu", "mcall_generic.cu", "mcall_abi.cu", os.path.join("host", "b200_call.c")]
 HEADERS = ["mcall_kernels.cuh", "mcall_device.cuh", os.path.join(ROOT, "include", "mcall_b200.h"), os.path.join(ROOT, "include", "b200_call.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--fmad=false",   # no FMA contraction: the reference's x86-64 -O2 build has none
@@ -23,15 +23,21 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def _compile_link(out_path, extra, verbose=False):
-    """One nvcc per source in parallel (objects under lib/obj/<name of the library>/), then one link."""
+def _compile_link(out_path, extra, verbose=False, incremental=False):
+    """One nvcc per source in parallel (objects under lib/obj/<name of the library>/), then one link.
+    incremental: objects newer than their source, every header and this file are kept."""
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     objdir = os.path.join(os.path.dirname(LIB), "obj", os.path.basename(out_path))
     os.makedirs(objdir, exist_ok=True)
-    procs = []
+    hdrs = [h if os.path.isabs(h) else os.path.join(CSRC, h) for h in HEADERS] + [os.path.abspath(__file__)]
+    procs, objs = [], []
     for s in SOURCES:
         obj = os.path.join(objdir, os.path.basename(s) + ".o")
-        cmd = [nvcc] + NVCC_FLAGS + extra + ["-c", "-o", obj, os.path.join(CSRC, s)]
+        objs.append(obj)
+        src = os.path.join(CSRC, s)
+        if incremental and os.path.exists(obj) and all(os.path.getmtime(d) < os.path.getmtime(obj) for d in [src] + hdrs):
+            continue
+        cmd = [nvcc] + NVCC_FLAGS + extra + ["-c", "-o", obj, src]
         procs.append((obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     failed = False
     for obj, pr in procs:
@@ -41,7 +47,7 @@ def _compile_link(out_path, extra, verbose=False):
         failed |= pr.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed building " + out_path)
-    r = subprocess.run([nvcc, "-shared", "-o", out_path] + [o for o, _ in procs], capture_output=True, text=True)
+    r = subprocess.run([nvcc, "-shared", "-o", out_path] + objs, capture_output=True, text=True)
     if verbose or r.returncode:
         sys.stderr.write(r.stdout + r.stderr)
     if r.returncode:
@@ -58,8 +64,8 @@ def build(force=False, verbose=False):
     if not force and not _stale():
         return LIB
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
-    return _compile_link(LIB, ["-Xptxas", "-v"] if verbose else [], verbose)
+    return _compile_link(LIB, ["-Xptxas", "-v"] if verbose else [], verbose, incremental=not force and not verbose)
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))     # no flag: incremental rebuild of what is stale

@@ -19,6 +19,9 @@
 using namespace mcb;
 
 #define NCLASS 6                /* allele-count classes 1..5 + class 0 = everything else */
+#define NCOUNTS (NCLASS+24)     /* class counts | +NCLASS: work counters | +NCLASS+8: pair-list counts | +NCLASS+16: pair work counters */
+/*  one allocation per batch/slab: NCLASS class lists, NCLASS pair lists (sites handed to the pair kernel), one PairRec per site  */
+static inline size_t lists_bytes(int cap) { return sizeof(int32_t)*(size_t)(2*NCLASS)*cap + sizeof(mcb::PairRec)*(size_t)cap; }
 #define MAX_STAGE 16
 
 #define NSLAB 3
@@ -27,7 +30,7 @@ struct HostSlab                 /* one stage of the host-path ring (H2D of slab 
     cudaStream_t stream = nullptr;
     cudaEvent_t  done = nullptr, cursor_ready = nullptr;
     /* compaction tail still owed by the slab in flight on this stage */
-    bool pending = false;  int p_beg = 0, p_n = 0;  size_t p_plout = 0, p_gp = 0;
+    bool pending = false;  int p_beg = 0, p_n = 0;  size_t p_plout = 0, p_gp = 0, p_pl16 = 0;
     /* the small per-site arrays of a slab travel as ONE copy each way through pinned staging buffers */
     char *h_in = nullptr, *h_out = nullptr;  size_t h_in_bytes = 0, h_out_bytes = 0;
     size_t s_out_beg = 0, s_ret = 0, s_als = 0, s_map = 0, s_qual = 0, s_ac = 0, s_an = 0, s_fl = 0, s_diag = 0, s_ploo = 0;
@@ -55,6 +58,7 @@ struct mcb_ctx
     HostSlab slab[NSLAB];
     /* options */
     int64_t opt_tile_bytes = 0, opt_ring_bytes = 0, opt_blocks_per_sm = 0, opt_slab_bytes = 64ll<<20, opt_slab_min = 8ll<<20, opt_block = 0;     /* 0 = automatic */
+    int64_t opt_defer2 = 0;              /* pair sites of the 3-5 allele classes: phase 2 in the warp-per-site pair kernel (0: stays fused) */
     int64_t opt_warp2 = -1;              /* biallelic warp-per-site kernel: -1 automatic, 0 off, n = force n warps per CTA */
     int64_t opt_order = 54321;           /* launch order of the allele-count classes */
     int64_t opt_time_kernels = 0, opt_concurrent = 1;    /* class kernels on their own streams: a class fills the tail of the previous one (-3.5 % per C3 step) */
@@ -156,6 +160,7 @@ extern "C" int mcb_set_option(mcb_ctx *ctx, const char *key, int64_t value)
     else if ( !strcmp(key,"time_kernels") )  ctx->opt_time_kernels = value;
     else if ( !strcmp(key,"concurrent") )    ctx->opt_concurrent = value;
     else if ( !strcmp(key,"order") )         ctx->opt_order = value;
+    else if ( !strcmp(key,"defer2") )        ctx->opt_defer2 = value;
     else if ( !strcmp(key,"warp2") )         { if ( value<-1 || value>biallelic_max_warps() ) return MCB_EINVAL; ctx->opt_warp2 = value; }
     else if ( !strncmp(key,"ring_bytes_",11) && key[11]>='1' && key[11]<='5' && !key[12] ) ctx->opt_ring_bytes_c[key[11]-'0'] = value;
     else if ( !strncmp(key,"block_",6) && key[6]>='1' && key[6]<='5' && !key[7] )
@@ -217,7 +222,7 @@ extern "C" int mcb_init(mcb_ctx **out, const mcb_params *params)
     ctx->nploidy = 1;
     int rc = upload_ploidy(ctx);
     if ( rc ) return rc;
-    CK(cudaMalloc(&ctx->d_counts, sizeof(int32_t)*(NCLASS+8)));     /* + work counter of the warp-per-site kernel */
+    CK(cudaMalloc(&ctx->d_counts, sizeof(int32_t)*NCOUNTS));     /* + work counter of the warp-per-site kernel */
     CK(cudaMalloc(&ctx->d_cursor, sizeof(unsigned long long)));
     if ( params->ngroups > 1 )         /* smpl_grp_t.smpl lists (mcall.c:250-349): every sample in exactly one group */
     {
@@ -244,7 +249,7 @@ extern "C" int mcb_init(mcb_ctx **out, const mcb_params *params)
         CK(cudaStreamCreateWithFlags(&ctx->slab[i].stream, cudaStreamNonBlocking));
         CK(cudaEventCreateWithFlags(&ctx->slab[i].done, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&ctx->slab[i].cursor_ready, cudaEventDisableTiming));
-        CK(cudaMalloc(&ctx->slab[i].counts, sizeof(int32_t)*(NCLASS+8)));
+        CK(cudaMalloc(&ctx->slab[i].counts, sizeof(int32_t)*NCOUNTS));
         CK(cudaMalloc(&ctx->slab[i].cursor, sizeof(unsigned long long)));
         CK(cudaHostAlloc(&ctx->slab[i].h_cursor, sizeof(unsigned long long), cudaHostAllocDefault));
     }
@@ -398,7 +403,7 @@ static int enqueue_class0(mcb_ctx *ctx, KArgs &a, const mcb_batch *b, const mcb_
 
 static int enqueue(mcb_ctx *ctx, const mcb_batch *b, const mcb_result *r, int32_t *lists, int32_t *counts, int list_stride, unsigned long long *cursor, cudaStream_t st)
 {
-    CK(cudaMemsetAsync(counts, 0, sizeof(int32_t)*(NCLASS+8), st));
+    CK(cudaMemsetAsync(counts, 0, sizeof(int32_t)*NCOUNTS, st));
     if ( r->pl_off_out ) CK(cudaMemsetAsync(cursor, 0, sizeof(unsigned long long), st));
     CK(launch_classify(b->nals, b->nsites, lists, counts, list_stride, st));
     int launches = 1;
@@ -531,8 +536,14 @@ static int enqueue(mcb_ctx *ctx, const mcb_batch *b, const mcb_result *r, int32_
         int grid = (int)std::min<int64_t>((int64_t)b->nsites, (int64_t)ctx->nsm*nb);
         cudaStream_t cs = fork ? ctx->cstream[nals] : st;
         if ( fork ) CK(cudaStreamWaitEvent(cs, ctx->cev_fork, 0));
+        /* pair sites (selected set = kept alleles = a pair) leave the fused kernel after phase 1: mcall_pair.cu */
+        const bool defer2 = ctx->opt_defer2 && nals>=3 && !ploidy && !gpk && pl_es==4 && !(a.nsmpl & 1) && a.gt && a.gq && a.out_pl;
+        a.pair_rec = defer2 ? reinterpret_cast<PairRec*>(lists + (size_t)(2*NCLASS)*list_stride) : nullptr;
+        a.pair_list = lists + (size_t)(NCLASS + nals)*list_stride;
+        a.pair_count = counts + NCLASS + 8 + nals; a.pair_work = counts + NCLASS + 16 + nals;
         {
             cudaError_t le = launch_site_kernel(nals, ploidy, gpk, block, pl_es, a, grid, ring, cs);
+            if ( le==cudaSuccess && defer2 ) { le = launch_pair_kernel(nals, a, ctx->nsm, cs); launches++; }
             if ( le==cudaSuccess && getenv("MCB_DEBUG_SYNC") ) le = cudaStreamSynchronize(cs);
             if ( le!=cudaSuccess )
             {
@@ -564,7 +575,7 @@ extern "C" int mcb_call_device(mcb_ctx *ctx, const mcb_batch *b, const mcb_resul
         CK(cudaStreamSynchronize(st));
         if ( ctx->d_lists ) CK(cudaFree(ctx->d_lists));
         ctx->list_cap = b->nsites;
-        CK(cudaMalloc(&ctx->d_lists, sizeof(int32_t)*(size_t)NCLASS*ctx->list_cap));
+        CK(cudaMalloc(&ctx->d_lists, lists_bytes(ctx->list_cap)));
     }
     ctx->stats[0] = ctx->stats[1] = 0;
     return enqueue(ctx, b, r, ctx->d_lists, ctx->d_counts, ctx->list_cap, ctx->d_cursor, st);
@@ -572,6 +583,35 @@ extern "C" int mcb_call_device(mcb_ctx *ctx, const mcb_batch *b, const mcb_resul
 
 /* ---- host path: slabs double-buffered over two streams ---------------------------------------------- */
 static inline size_t pad256(size_t n) { return (n + 255) & ~(size_t)255; }
+
+/*  BCF typed-vector outputs (mcb_result.gt8 / gq8 / pl16): the int32 arrays the kernels wrote are narrowed on the device before
+ *  they cross PCIe.  One pass over data that is still in L2 / HBM costs ~1 % of the transfer it shortens.  */
+template<typename T> __device__ __forceinline__ T narrow_one(int v)
+{
+    constexpr int LO = sizeof(T)==1 ? INT8_MIN : INT16_MIN, HI = sizeof(T)==1 ? INT8_MAX : INT16_MAX;
+    if ( v==INT32_MIN ) return (T)LO;               /* bcf_int32_missing    -> bcf_int8/16_missing */
+    if ( v==INT32_MIN+1 ) return (T)(LO+1);         /* bcf_int32_vector_end -> bcf_int8/16_vector_end */
+    return (T)(v > HI ? HI : (v < LO+2 ? LO+2 : v));
+}
+template<typename T> __global__ void narrow_kernel(const int32_t *src, T *dst, size_t n)
+{
+    const size_t n4 = n >> 2, stride = (size_t)gridDim.x*blockDim.x;
+    for (size_t i = (size_t)blockIdx.x*blockDim.x + threadIdx.x; i < n4; i += stride)
+    {
+        const int4 v = reinterpret_cast<const int4*>(src)[i];
+        T o[4] = { narrow_one<T>(v.x), narrow_one<T>(v.y), narrow_one<T>(v.z), narrow_one<T>(v.w) };
+        if ( sizeof(T)==1 ) reinterpret_cast<uint32_t*>(dst)[i] = *reinterpret_cast<uint32_t*>(o);
+        else reinterpret_cast<uint2*>(dst)[i] = *reinterpret_cast<uint2*>(o);
+    }
+    for (size_t i = (n4<<2) + (size_t)blockIdx.x*blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = narrow_one<T>(src[i]);
+}
+template<typename T> static cudaError_t launch_narrow(const int32_t *src, T *dst, size_t n, int nsm, cudaStream_t st)
+{
+    if ( !n ) return cudaSuccess;
+    const int grid = (int)std::min<size_t>((size_t)nsm*8, (n/4 + 255)/256 + 1);
+    narrow_kernel<T><<<grid, 256, 0, st>>>(src, dst, n);
+    return cudaGetLastError();
+}
 
 extern "C" int mcb_call_host(mcb_ctx *ctx, const mcb_batch *b, const mcb_result *r)
 {
@@ -599,8 +639,9 @@ extern "C" int mcb_call_host(mcb_ctx *ctx, const mcb_batch *b, const mcb_result 
         aext[i] = (((int64_t)S*b->nad[i]) + 3) & ~(int64_t)3;
         if ( i && b->ad_off[i] < b->ad_off[i-1] + aext[i-1] ) return MCB_EINVAL;
     }
-    const bool want_pl = r->pl != nullptr, want_gt = r->gt != nullptr;
-    const bool want_gq = r->gq && (ctx->p.output_tags & (MCB_CALL_FMT_GQ|MCB_CALL_FMT_GP));
+    const bool want_pl = r->pl || r->pl16, want_gt = r->gt || r->gt8;
+    const bool want_gq = (r->gq || r->gq8) && (ctx->p.output_tags & (MCB_CALL_FMT_GQ|MCB_CALL_FMT_GP));
+    const bool gt8 = r->gt8 != nullptr, gq8 = r->gq8 != nullptr, pl16 = r->pl16 != nullptr;     /* BCF typed outputs */
     const bool want_gp = r->gp && (ctx->p.output_tags & MCB_CALL_FMT_GP);
     const bool compact = r->pl_off_out != nullptr;      /* trimmed PL/GP leave the device compacted */
     int64_t out_total = 0;                              /* int32 units already placed in r->pl */
@@ -627,6 +668,12 @@ extern "C" int mcb_call_host(mcb_ctx *ctx, const mcb_batch *b, const mcb_result 
         memcpy(r->pl_off_out + beg, ho + sl.s_ploo, sizeof(int64_t)*(size_t)n);
         const int64_t used = (int64_t)*sl.h_cursor;
         char *base = (char*) sl.dev;
+        if ( want_pl && used && pl16 )
+        {
+            CK(launch_narrow<int16_t>((const int32_t*)(base + sl.p_plout), (int16_t*)(base + sl.p_pl16), (size_t)used, ctx->nsm, sl.stream));
+            CK(cudaMemcpyAsync(r->pl16 + out_total, base + sl.p_pl16, (size_t)used*2, cudaMemcpyDeviceToHost, sl.stream));
+        }
+        else
         if ( want_pl && used ) CK(cudaMemcpyAsync(r->pl + out_total, base + sl.p_plout, (size_t)used*4, cudaMemcpyDeviceToHost, sl.stream));
         if ( want_gp && used ) CK(cudaMemcpyAsync(r->gp + out_total, base + sl.p_gp, (size_t)used*4, cudaMemcpyDeviceToHost, sl.stream));
         slab_base.push_back(std::make_pair(sl.p_beg, out_total));
@@ -661,6 +708,8 @@ extern "C" int mcb_call_host(mcb_ctx *ctx, const mcb_batch *b, const mcb_result 
         const int64_t ad0 = have_ad ? b->ad_off[beg] : 0, ad_ints = have_ad ? b->ad_off[end-1] + aext[end-1] - ad0 : 0;
         size_t o_ad = have_ad ? carve((size_t)ad_ints*4) : 0;
         size_t o_gt = want_gt ? carve(8*(size_t)n*S) : 0, o_gq = want_gq ? carve(4*(size_t)n*S) : 0;
+        size_t o_gt8 = (want_gt && gt8) ? carve(2*(size_t)n*S) : 0, o_gq8 = (want_gq && gq8) ? carve((size_t)n*S) : 0;
+        size_t o_pl16 = (want_pl && pl16) ? carve((size_t)pl_ints*2) : 0;
         /* small inputs, contiguous: one upload */
         const size_t in_beg = off;
         size_t o_ploff = carve(sizeof(int64_t)*n), o_nals = carve(n), o_unseen = carve(n), o_pid = carve(2*(size_t)n);
@@ -696,7 +745,7 @@ extern "C" int mcb_call_host(mcb_ctx *ctx, const mcb_batch *b, const mcb_result 
         {
             if ( sl.lists ) CK(cudaFree(sl.lists));
             sl.list_cap = n + n/8;
-            CK(cudaMalloc(&sl.lists, sizeof(int32_t)*(size_t)NCLASS*sl.list_cap));
+            CK(cudaMalloc(&sl.lists, lists_bytes(sl.list_cap)));
         }
         char *base = (char*) sl.dev;
         cudaStream_t st = sl.stream;
@@ -758,11 +807,29 @@ extern "C" int mcb_call_host(mcb_ctx *ctx, const mcb_batch *b, const mcb_result 
         CK(cudaEventRecord(sl.cursor_ready, st));
         sl.s_out_beg = out_beg; sl.s_ret = o_ret; sl.s_als = o_als; sl.s_map = o_map; sl.s_qual = o_qual; sl.s_ac = o_ac;
         sl.s_an = o_an; sl.s_fl = o_fl; sl.s_diag = o_diag; sl.s_ploo = o_ploo;
-        sl.pending = true; sl.p_beg = beg; sl.p_n = n; sl.p_plout = o_plout; sl.p_gp = o_gp;
+        sl.pending = true; sl.p_beg = beg; sl.p_n = n; sl.p_plout = o_plout; sl.p_gp = o_gp; sl.p_pl16 = o_pl16;
+        if ( want_gt && gt8 )
+        {
+            CK(launch_narrow<int8_t>((const int32_t*)(base+o_gt), (int8_t*)(base+o_gt8), 2*(size_t)n*S, ctx->nsm, st));
+            D2H(r->gt8 + (size_t)beg*S*2, o_gt8, 2*(size_t)n*S);
+        }
+        else
         if ( want_gt ) D2H(r->gt + (size_t)beg*S*2, o_gt, 8*(size_t)n*S);
+        if ( want_gq && gq8 )
+        {
+            CK(launch_narrow<int8_t>((const int32_t*)(base+o_gq), (int8_t*)(base+o_gq8), (size_t)n*S, ctx->nsm, st));
+            D2H(r->gq8 + (size_t)beg*S, o_gq8, (size_t)n*S);
+        }
+        else
         if ( want_gq ) D2H(r->gq + (size_t)beg*S, o_gq, 4*(size_t)n*S);
         if ( !compact )
         {
+            if ( want_pl && pl16 )
+            {
+                CK(launch_narrow<int16_t>((const int32_t*)(base+o_plout), (int16_t*)(base+o_pl16), (size_t)pl_ints, ctx->nsm, st));
+                D2H(r->pl16 + pl0, o_pl16, (size_t)pl_ints*2);
+            }
+            else
             if ( want_pl ) D2H(r->pl + pl0, o_plout, (size_t)pl_ints*4);
             if ( want_gp ) D2H(r->gp + pl0, o_gp, (size_t)pl_ints*4);
             CK(cudaEventRecord(sl.done, st));

@@ -11,7 +11,7 @@
 #define MCB_UNROLL2 1       /* unroll factor of the phase-2 sample loop */
 #endif
 #ifndef MCB_FAST2
-#define MCB_FAST2 1         /* straight-line phase 2 for sites whose selected set is a pair (two adjacent samples per lane) */
+#define MCB_FAST2 0         /* 1: straight-line phase 2 for pair sites INSIDE this kernel (measured: slower, see below; the pair kernel does it) */
 #endif
 
 namespace mcb {
@@ -540,7 +540,7 @@ __global__ void __launch_bounds__(BLOCK, (MinBlocks<NALS,BLOCK>::value)) mcall_s
                 double M = 1.0; int E = 0;
                 #pragma unroll
                 for (int w=0; w<NW; w++) { M = __dmul_rn(M, sh.red_M[w][k]); E += sh.red_E[w][k]; }
-                return log(M) + (double)(E - 1023*n)*LN2;
+                return site_log(M) + (double)(E - 1023*n)*LN2;
             };
             const double lnN_all    = n_all ? total_log(NACC-2, n_all) : 0.0;
             const double lnN_called = PLOIDY ? (n_called ? total_log(NACC-1, n_called) : 0.0) : lnN_all;
@@ -597,10 +597,10 @@ __global__ void __launch_bounds__(BLOCK, (MinBlocks<NALS,BLOCK>::value)) mcall_s
             double mx = in_sum ? lk : -CUDART_INF;
             #pragma unroll
             for (int off=16; off; off>>=1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, off));
-            double term = in_sum ? exp(lk - mx) : 0.0;
+            double term = in_sum ? site_exp(lk - mx) : 0.0;
             #pragma unroll
             for (int off=16; off; off>>=1) term += __shfl_xor_sync(0xffffffffu, term, off);
-            const double grp_lk_sum = mx > -CUDART_INF ? mx + log(term) : -CUDART_INF;
+            const double grp_lk_sum = mx > -CUDART_INF ? mx + site_log(term) : -CUDART_INF;
             const double grp_ref_lk = __shfl_sync(0xffffffffu, lk, 0);
             const uint32_t grp_als = __shfl_sync(0xffffffffu, mask, best_lane & 31);
 
@@ -741,10 +741,40 @@ __global__ void __launch_bounds__(BLOCK, (MinBlocks<NALS,BLOCK>::value)) mcall_s
             /*  fast2: every sample diploid, the selected set is a pair s0<s1 whose alleles are exactly the kept ones (new alleles
              *  0 and 1, all three new genotypes below ngt_new), GT + GQ + PL all written, int32 PLs, an even sample count
              *  and 16-byte aligned outputs (pairs of samples leave in vector stores).  CTA-uniform.  */
-            constexpr bool FAST2 = MCB_FAST2 && !PLOIDY && !GPOUT && ES==4 && NALS>=2;
-            const bool fast2 = FAST2 && !ref_gt && nsel==2 && (inc_dip & 7u)==7u && nals_new==2 && sh.als_new==sh.grp_als && want_gq
-                               && oflags==7u && !(nsmpl & 1) && !(TS & 1)
+            constexpr bool PAIR_OK = !PLOIDY && !GPOUT && ES==4 && NALS>=2;
+            constexpr bool FAST2 = MCB_FAST2 && PAIR_OK;
+            const bool pair_site = PAIR_OK && !ref_gt && nsel==2 && (inc_dip & 7u)==7u && nals_new==2 && sh.als_new==sh.grp_als && want_gq
+                               && oflags==7u && !(nsmpl & 1)
                                && !((reinterpret_cast<uintptr_t>(out_gt) & 15) | (reinterpret_cast<uintptr_t>(out_gq) & 7) | (reinterpret_cast<uintptr_t>(out_pl) & 7));
+            /*  Pair sites leave the fused kernel here when the caller provided the hand-over buffers: their phase 2 runs in the
+             *  warp-per-site pair kernel (mcall_pair.cu), whose small straight-line loop does not compete with the general
+             *  phase-2 code below for instruction fetch (inside this kernel the same fast path made every class 10-19 % SLOWER:
+             *  the stall reason that grew is no_instruction).  */
+            if constexpr ( PAIR_OK && NALS>=3 ) if ( pair_site && a.pair_rec )
+            {
+                if ( tid==0 )
+                {
+                    PairRec pr;
+                    pr.q0 = q0; pr.q1 = q1; pr.max_qual = sh.max_qual; pr.lk_sum = sh.lk_sum; pr.ref_lk = sh.ref_lk; pr.gap = sh.gap;
+                    pr.out_off = sh.out_off; pr.flags = sh.flags; pr.als_new = sh.als_new;
+                    pr.g00 = jgt4[0]/ES; pr.g10 = jgt4[NSLOT>1 ? 1 : 0]/ES; pr.g11 = jgt4[NSLOT>2 ? 2 : 0]/ES; pr.nals_new = nals_new;
+                    #pragma unroll
+                    for (int j=0; j<8; j++) pr.als_map[j] = j<NALS ? (int8_t)sh.als_map[j] : (int8_t)-1;
+                    a.pair_rec[site] = pr;
+                    __threadfence();
+                    a.pair_list[atomicAdd(a.pair_count, 1)] = site;
+                }
+                if ( !resident )        /* drain the phase-2 tiles already in flight for this site */
+                    for (int v=ntiles; v<ntiles+nstage && v<total_visits; v++)
+                    {
+                        const int stage = v % nstage;
+                        mbar_wait(bars_s + 8*stage, (phase_bits>>stage)&1u);
+                        phase_bits ^= 1u<<stage;
+                    }
+                __syncthreads();
+                continue;
+            }
+            const bool fast2 = FAST2 && pair_site && !(TS & 1);
             const double fq0 = q0, fq1 = q1, fq1x2 = __dmul_rn(2.0, q1);
             const int fj0 = jgt4[0], fj1 = jgt4[NSLOT>1 ? 1 : 0], fj2 = jgt4[NSLOT>2 ? 2 : 0];
             int f_alt = 0, f_called = 0;

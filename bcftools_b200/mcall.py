@@ -152,9 +152,10 @@ class MCaller:
         lib().mcb_get_stats(self._ctx, out.ctypes.data)
         return out
 
-    def call_host(self, batch, result=None, want_gp=False, compact=False):
-        """mcb_call_host on numpy (host) arrays; returns an abi.HostResult."""
-        res = result if result is not None else abi.HostResult(batch, want_gp=want_gp, compact=compact)
+    def call_host(self, batch, result=None, want_gp=False, compact=False, typed=False):
+        """mcb_call_host on numpy (host) arrays; returns an abi.HostResult.  typed=True: GT/GQ/PL come back as the BCF
+        typed vectors gt8/gq8/pl16 (mcb_result.gt8 ...); HostResult.widen() maps them to the int32 arrays."""
+        res = result if result is not None else abi.HostResult(batch, want_gp=want_gp, compact=compact, typed=typed)
         b, r = batch.c_struct(), res.c_struct()
         self._check(lib().mcb_call_host(self._ctx, C.byref(b), C.byref(r)), "mcb_call_host")
         return res

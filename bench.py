@@ -354,6 +354,25 @@ def main():
             dt16 = float(t.item())
         e2e["int16_pl_transport"] = dict(value=world * args.steps * ne * params.nsmpl / dt16, h2d_bytes_per_step=int(sub16.pl.nbytes + h2d - sub.pl.nbytes),
                                          ms_per_step=1e3 * dt16 / args.steps)
+        # secondary: BCF typed vectors both ways -- int16 PL in, int8 GT / int8 GQ / int16 PL out (mcb_result.gt8/gq8/pl16)
+        hrest = mcall.pin_result(abi.HostResult(sub16, compact=True, typed=True))
+        for _ in range(2):
+            mc.call_host(sub16, hrest)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            mc.call_host(sub16, hrest)
+        torch.cuda.synchronize()
+        dtt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dtt], device=f"cuda:{local_rank}", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dtt = float(t.item())
+        d2ht = sum(getattr(hrest, k).nbytes for k in ("ret", "als_new", "als_map", "qual", "ac", "an", "site_flags", "diag", "gt8", "gq8", "pl_off_out")
+                   if getattr(hrest, k) is not None) + 2 * int(mc.stats()[2])
+        e2e["bcf_typed_transport"] = dict(value=world * args.steps * ne * params.nsmpl / dtt, ms_per_step=1e3 * dtt / args.steps,
+                                          h2d_bytes_per_step=int(sub16.pl.nbytes + h2d - sub.pl.nbytes), d2h_bytes_per_step=int(d2ht),
+                                          types="in: PL int16 (BCF_BT_INT16 as stored in the record); out: GT int8, GQ int8, PL int16, narrowed on the device")
 
     # ---- max over ranks of the device time
     if world > 1:

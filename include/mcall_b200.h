@@ -134,6 +134,14 @@ typedef struct mcb_result
     int64_t  *pl_off_out;   /* [nsites] optional.  If non-NULL the trimmed PLs (and GP) are written COMPACTED: site i lies
                                at pl + pl_off_out[i] (16-byte aligned blocks in no particular order, -1 when the site has
                                no PL); the used prefix of pl is all that travels device->host in mcb_call_host */
+    /* BCF typed-vector outputs (mcb_call_host only).  When non-NULL they are filled INSTEAD of gt / gq / pl:
+       the per-sample results are narrowed on the device to the types a BCF record stores them in (what bcf_update_genotypes /
+       bcf_update_format_int32 + vcf_write would re-encode the int32 arrays to), so 9 instead of 24 bytes per biallelic call
+       cross PCIe.  Sentinels are the BCF ones: missing = INT8_MIN / INT16_MIN, vector_end = INT8_MIN+1 / INT16_MIN+1;
+       a PL above INT16_MAX saturates (such sites carry MCB_SITE_PL_RANGE).  */
+    int8_t   *gt8;          /* [nsites][nsmpl][2] BCF_BT_INT8 */
+    int8_t   *gq8;          /* [nsites][nsmpl]    BCF_BT_INT8 */
+    int16_t  *pl16;         /* BCF_BT_INT16, same ELEMENT offsets as pl (pl_off, or pl_off_out when compacted) */
 }
 mcb_result;
 

@@ -261,6 +261,55 @@ def test_compacted_pl_output(oracle_built):
     assert ((got.pl_off_out < 0) == (dropped | (got.ret <= 0))).all()
 
 
+@pytest.mark.parametrize("compact", [False, True])
+@pytest.mark.parametrize("int16_in", [False, True])
+def test_bcf_typed_outputs(compact, int16_in, oracle_built):
+    """mcb_result.gt8 / gq8 / pl16: GT / GQ / trimmed PL narrowed on the device to the BCF types must
+    widen back to exactly the int32 results (sentinels included: haploid vector_end, ploidy-0 missing), several slabs."""
+    from bcftools_b200 import mcall
+    params, batch, tab = synth.make_batch("C3", 160, flag=0)
+    exp, _ = oracle_built.call("port", params, batch, tab)
+    bin_ = batch.to_int16() if int16_in else batch
+    with mcall.MCaller(params, ploidy_tab=tab, options={"slab_bytes": 4 << 20}) as mc:
+        got = mc.call_host(bin_, compact=compact, typed=True)
+    assert got.gt8.dtype == np.int8 and got.pl16.dtype == np.int16
+    st = parity.compare(got.widen(), exp, params)
+    assert st["compared"] > 0, st
+    rng = np.random.default_rng(11)
+    rb = parity.random_batch(rng, 150, 37, 5)
+    tabr = np.full((2, 37), 2, np.uint8)
+    tabr[1, ::3] = 1
+    tabr[1, 1::7] = 0
+    rb.ploidy_id = rng.integers(0, 2, rb.nsites).astype(np.uint16)
+    pr = abi.CallParams(37, 5, output_tags=abi.CALL_FMT_GQ)
+    expr, _ = oracle_built.call("port", pr, rb, tabr)
+    with mcall.MCaller(pr, ploidy_tab=tabr) as mc:
+        gotr = mc.call_host(rb, compact=compact, typed=True)
+    assert parity.compare(gotr.widen(), expr, pr)["compared"] > 0
+
+
+@pytest.mark.parametrize("S", [2, 64, 1000, 2504])
+def test_pair_kernel_option(S, oracle_built):
+    """defer2=1: pair sites of the 3-5 allele classes leave the fused kernel after phase 1 and are genotyped by the
+    CTA-per-site pair kernel (mcall_pair.cu); results must not change (missing values and PL >= 256 take its general path)."""
+    from bcftools_b200 import mcall
+    rng = np.random.default_rng(S)
+    batch = parity.random_batch(rng, 90 if S > 500 else 200, S, 5)
+    params = abi.CallParams(S, 5, output_tags=abi.CALL_FMT_GQ)
+    tab = np.full((1, S), 2, np.uint8)
+    exp, _ = oracle_built.call("port", params, batch, tab)
+    with mcall.MCaller(params, ploidy_tab=tab, options={"defer2": 1}) as mc:
+        got = mc.call_host(batch, compact=True)
+    assert parity.compare(got, exp, params)["compared"] > 0
+    if S == 2504:
+        p3, b3, t3 = synth.make_batch("C3", 160)
+        e3, _ = oracle_built.call("port", p3, b3, t3)
+        with mcall.MCaller(p3, ploidy_tab=t3, options={"defer2": 1}) as mc:
+            g3 = mc.call_host(b3)
+            assert int(mc.stats()[0]) > 7        # the pair kernels were launched
+        assert parity.compare(g3, e3, p3)["compared"] > 0
+
+
 def test_empty_batch():
     from bcftools_b200 import mcall
     params = abi.CallParams(8, 5)
