@@ -10,6 +10,9 @@
 #ifndef MCB_UNROLL2
 #define MCB_UNROLL2 1       /* unroll factor of the phase-2 sample loop */
 #endif
+#ifndef MCB_FAST2_N2
+#define MCB_FAST2_N2 1      /* the same path in the two-allele instances of this kernel (int32 PLs, S > 8,192: the biobank shape) */
+#endif
 #ifndef MCB_FAST2
 #define MCB_FAST2 0         /* 1: straight-line phase 2 for pair sites INSIDE this kernel (measured: slower, see below; the pair kernel does it) */
 #endif
@@ -742,7 +745,7 @@ __global__ void __launch_bounds__(BLOCK, (MinBlocks<NALS,BLOCK>::value)) mcall_s
              *  0 and 1, all three new genotypes below ngt_new), GT + GQ + PL all written, int32 PLs, an even sample count
              *  and 16-byte aligned outputs (pairs of samples leave in vector stores).  CTA-uniform.  */
             constexpr bool PAIR_OK = !PLOIDY && !GPOUT && ES==4 && NALS>=2;
-            constexpr bool FAST2 = MCB_FAST2 && PAIR_OK;
+            constexpr bool FAST2 = PAIR_OK && (MCB_FAST2 || (MCB_FAST2_N2 && NALS==2));     /* two alleles (S > 8,192, the biobank shape): the small kernel takes the extra path without fetch misses */
             const bool pair_site = PAIR_OK && !ref_gt && nsel==2 && (inc_dip & 7u)==7u && nals_new==2 && sh.als_new==sh.grp_als && want_gq
                                && oflags==7u && !(nsmpl & 1)
                                && !((reinterpret_cast<uintptr_t>(out_gt) & 15) | (reinterpret_cast<uintptr_t>(out_gq) & 7) | (reinterpret_cast<uintptr_t>(out_pl) & 7));
@@ -774,7 +777,9 @@ __global__ void __launch_bounds__(BLOCK, (MinBlocks<NALS,BLOCK>::value)) mcall_s
                 __syncthreads();
                 continue;
             }
-            const bool fast2 = FAST2 && pair_site && !(TS & 1);
+            /* two-allele instances: measured +16 % at 100,000 samples (C4), -4..-9 % at 1,000-2,504 (where the warp kernel of
+               mcall_biallelic.cu is the default path anyway) */
+            const bool fast2 = FAST2 && pair_site && !(TS & 1) && (MCB_FAST2 || nsmpl > 8192);
             const double fq0 = q0, fq1 = q1, fq1x2 = __dmul_rn(2.0, q1);
             const int fj0 = jgt4[0], fj1 = jgt4[NSLOT>1 ? 1 : 0], fj2 = jgt4[NSLOT>2 ? 2 : 0];
             int f_alt = 0, f_called = 0;

@@ -128,6 +128,23 @@ def test_biobank_shape_100k_samples(oracle_built):
     assert st["compared"] > 0 and not st["near_ties"], st
 
 
+@pytest.mark.parametrize("flag", [0, abi.CALL_KEEPALT])
+def test_tiled_two_allele_pair_path_above_8192_samples(flag, oracle_built):
+    """S > 8,192: the two-allele class runs the tiled kernel, whose variant sites take the straight-line pair path
+    (two adjacent samples per lane); adversarial PLs incl. missing values and zero QS send warps back to the general path."""
+    from bcftools_b200 import mcall
+    S = 8194
+    rng = np.random.default_rng(8194 + flag)
+    batch = parity.random_batch(rng, 24, S, 2, minA=2)
+    params = abi.CallParams(S, 2, flag=flag, output_tags=abi.CALL_FMT_GQ)
+    tab = np.full((1, S), 2, np.uint8)
+    exp, _ = oracle_built.call("port", params, batch, tab)
+    for opts in ({}, {"tile_bytes": 4096, "ring_bytes": 8192}):
+        with mcall.MCaller(params, ploidy_tab=tab, options=opts) as mc:
+            got = mc.call_host(batch, compact=True)
+        assert parity.compare(got, exp, params)["compared"] > 0, opts
+
+
 def test_full_size_properties_without_oracle():
     """Size-independent properties at a batch the CPU oracle would need minutes for (C3 shape, 4096 sites = 10 M calls):
     AN = sum(AC) = number of called alleles in GT; every GT allele index < ret; trimmed PL rows keep a zero for
