@@ -12,7 +12,8 @@ b, r = db.c_struct(), dr.c_struct()
 stream = torch.cuda.current_stream().cuda_stream
 for c in classes:
     best = None
-    for block, tile_kb, ring_kb in itertools.product((64, 128, 256), (4, 8, 16, 32), (8, 16, 32, 64)):
+    blocks = tuple(int(x) for x in sys.argv[2].split(",")) if len(sys.argv) > 2 else (64, 128, 256)
+    for block, tile_kb, ring_kb in itertools.product(blocks, (4, 8, 16, 32), (8, 16, 32, 64)):
         if ring_kb < tile_kb:
             continue
         opts = {"time_kernels": 1, "block_%d" % c: block, "tile_bytes_%d" % c: tile_kb << 10, "ring_bytes_%d" % c: ring_kb << 10}
