@@ -7,8 +7,9 @@ from bcftools_b200 import abi, synth, mcall
 sites = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
 params, hb, tab = synth.make_batch("C3", sites, with_groups=0)
 sub = mcall.pin_batch(hb.subset(range(sites)).to_int16())
-for slab_mb, min_mb in ((64, 8), (32, 4), (32, 2), (16, 2), (16, 1), (24, 2), (48, 4), (8, 1)):
-    mc = mcall.MCaller(params, ploidy_tab=tab, options={"slab_bytes": slab_mb << 20, "slab_min": min_mb << 20})
+extra = {k: int(v) for k, v in (o.split("=") for o in sys.argv[2:])}
+for slab_mb, min_mb in ((64, 8), (32, 4)):
+    mc = mcall.MCaller(params, ploidy_tab=tab, options=dict({"slab_bytes": slab_mb << 20, "slab_min": min_mb << 20}, **extra))
     res = mcall.pin_result(abi.HostResult(sub, compact=True, typed=True))
     for _ in range(2):
         mc.call_host(sub, res)
