@@ -21,7 +21,7 @@ struct b200_batcher
     mcb_result res;
     /* ploidy vectors registered with the context: a new id whenever the driver changed call->ploidy */
     uint8_t *last_ploidy;   int n_ploidy;
-    int grouped, use_prior;
+    int grouped, use_prior, typed;
 };
 
 static void default_handler(const char *msg) { fputs(msg, stderr); exit(-1); }      /* version.c:40-47 */
@@ -50,6 +50,7 @@ void b200_mcall_init(b200_call_t *call)
     b->cap = call->max_records>0 ? call->max_records : 4096;
     b->grouped = call->nsmpl_grp > 1;
     b->use_prior = call->use_prior;
+    b->typed = call->bcf_typed && !b->grouped;
 
     mcb_params p; memset(&p, 0, sizeof p);
     p.nsmpl = call->nsmpl;  p.max_nals = b->max_nals;
@@ -65,8 +66,8 @@ void b200_mcall_init(b200_call_t *call)
 
     const int S = b->nsmpl, M = b->max_nals, R = b->cap;
     const int64_t gmax = (int64_t)M*(M+1)/2;
-    b->pl_cap = (int64_t)R*(((int64_t)S*gmax + 3) & ~3ll);
-    b->pl = (int32_t*) pinned((size_t)b->pl_cap*4);
+    b->pl_cap = (int64_t)R*(((int64_t)S*gmax + 7) & ~7ll);      /* sites start on 16-byte boundaries (8 int16 / 4 int32 elements) */
+    b->pl = (int32_t*) pinned((size_t)b->pl_cap*(b->typed ? 2 : 4));      /* typed: an int16 slab (mcb_batch.pl_type = 2) */
     b->pl_off = (int64_t*) pinned(sizeof(int64_t)*R);
     if ( b->grouped )
     {
@@ -84,10 +85,19 @@ void b200_mcall_init(b200_call_t *call)
     b->res.als_map = (int8_t*) pinned((size_t)R*M);       b->res.qual = (float*) pinned(4*(size_t)R);
     b->res.ac = (int32_t*) pinned(4*(size_t)R*M);         b->res.an = (int32_t*) pinned(4*(size_t)R);
     b->res.site_flags = (uint32_t*) pinned(4*(size_t)R);  b->res.diag = NULL;
+    if ( b->typed )
+    {
+        b->res.gt8 = (int8_t*) pinned(2*(size_t)R*S);
+        b->res.gq8 = (p.output_tags & (CALL_FMT_GQ|CALL_FMT_GP)) ? (int8_t*) pinned((size_t)R*S) : NULL;
+        b->res.pl16 = (int16_t*) pinned((size_t)b->pl_cap*2);
+    }
+    else
+    {
     b->res.gt = (int32_t*) pinned(8*(size_t)R*S);
     b->res.gq = (p.output_tags & (CALL_FMT_GQ|CALL_FMT_GP)) ? (int32_t*) pinned(4*(size_t)R*S) : NULL;
-    b->res.gp = (p.output_tags & CALL_FMT_GP) ? (float*) pinned((size_t)b->pl_cap*4) : NULL;
     b->res.pl = (int32_t*) pinned((size_t)b->pl_cap*4);
+    }
+    b->res.gp = (p.output_tags & CALL_FMT_GP) ? (float*) pinned((size_t)b->pl_cap*4) : NULL;
     b->res.pl_off_out = (int64_t*) pinned(sizeof(int64_t)*R);
     b->last_ploidy = (uint8_t*) malloc(S);
     memset(b->last_ploidy, 2, S);               /* id 0 of the context = all diploid */
@@ -101,6 +111,7 @@ int b200_mcall_flush(b200_call_t *call)
     b->nready = 0;
     if ( !b->n ) return 0;
     mcb_batch in; memset(&in, 0, sizeof in);
+    in.pl_type = b->typed ? 2 : 4;
     in.nsites = b->n;  in.pl = b->pl;  in.pl_off = b->pl_off;  in.nals = b->nals;  in.unseen = b->unseen;
     in.ploidy_id = b->ploidy_id;
     if ( b->grouped ) { in.ad = b->ad; in.ad_off = b->ad_off; in.nad = b->nad; }
@@ -124,8 +135,23 @@ int b200_mcall(b200_call_t *call, const b200_rec_t *rec)
         b200_error("Wrong number of PL fields? nals=%d npl=%d\n", nals, rec->nPLs);
     int i = b->n;
     b->pl_off[i] = b->pl_used;
+    if ( b->typed )             /* the record's own typed vector goes into the int16 slab; int8 is widened here */
+    {
+        int16_t *dst = (int16_t*) b->pl + b->pl_used;
+        if ( !rec->PL_typed || (rec->PL_bt!=1 && rec->PL_bt!=2) ) b200_error("b200_mcall: bcf_typed needs FORMAT/PL as an int8 or int16 typed vector\n");
+        if ( rec->PL_bt==2 ) memcpy(dst, rec->PL_typed, sizeof(int16_t)*(size_t)rec->nPLs);
+        else
+        {
+            const int8_t *src = (const int8_t*) rec->PL_typed;
+            for (int k=0; k<rec->nPLs; k++) dst[k] = src[k]==INT8_MIN ? INT16_MIN : (src[k]==INT8_MIN+1 ? INT16_MIN+1 : src[k]);
+        }
+        b->pl_used += ((int64_t)rec->nPLs + 7) & ~7ll;         /* 16-byte aligned sites */
+    }
+    else
+    {
     memcpy(b->pl + b->pl_used, rec->PLs, sizeof(int32_t)*(size_t)rec->nPLs);
     b->pl_used += ((int64_t)rec->nPLs + 3) & ~3ll;
+    }
     b->nals[i] = (uint8_t)nals;  b->unseen[i] = call->unseen;
     if ( b->grouped )
     {
@@ -176,10 +202,21 @@ int b200_mcall_result(b200_call_t *call, int i, b200_out_t *out)
     out->als_map = b->res.als_map + (size_t)i*M;
     out->qual = b->res.qual[i];
     out->ac = b->res.ac + (size_t)i*M;  out->an = b->res.an[i];
+    const int ref_gt = (out->site_flags & MCB_SITE_REF_GT) != 0;
+    if ( b->typed )
+    {
+        out->gts8 = b->res.gt8 + (size_t)i*S*2;
+        out->GQs8 = (b->res.gq8 && !ref_gt) ? b->res.gq8 + (size_t)i*S : NULL;
+    }
+    else
+    {
     out->gts = b->res.gt + (size_t)i*S*2;
-    out->GQs = (b->res.gq && !(out->site_flags & MCB_SITE_REF_GT)) ? b->res.gq + (size_t)i*S : NULL;
+    out->GQs = (b->res.gq && !ref_gt) ? b->res.gq + (size_t)i*S : NULL;
+    }
     if ( !(out->site_flags & MCB_SITE_PL_DROPPED) && b->res.pl_off_out[i]>=0 )
     {
+        if ( b->typed ) out->PLs16 = b->res.pl16 + b->res.pl_off_out[i];
+        else
         out->PLs = b->res.pl + b->res.pl_off_out[i];
         out->nPLs = S*out->ret*(out->ret+1)/2;
         if ( b->res.gp && !(out->site_flags & MCB_SITE_REF_GT) ) out->GPs = b->res.gp + b->res.pl_off_out[i];
@@ -198,6 +235,7 @@ void b200_mcall_destroy(b200_call_t *call)
     mcb_host_free(b->res.ret); mcb_host_free(b->res.als_new); mcb_host_free(b->res.als_map); mcb_host_free(b->res.qual);
     mcb_host_free(b->res.ac); mcb_host_free(b->res.an); mcb_host_free(b->res.site_flags); mcb_host_free(b->res.gt);
     mcb_host_free(b->res.gq); mcb_host_free(b->res.gp); mcb_host_free(b->res.pl); mcb_host_free(b->res.pl_off_out);
+    mcb_host_free(b->res.gt8); mcb_host_free(b->res.gq8); mcb_host_free(b->res.pl16);
     free(b->user); free(b->last_ploidy); free(b);
     call->batcher = NULL;
 }

@@ -11,20 +11,22 @@ class B200Call(C.Structure):
     _fields_ = [("nsmpl", C.c_int), ("flag", C.c_uint32), ("output_tags", C.c_uint32), ("theta", C.c_double),
                 ("ploidy", C.c_void_p), ("unseen", C.c_uint8), ("nsmpl_grp", C.c_int),
                 ("grp_off", C.c_void_p), ("grp_smpl", C.c_void_p), ("use_prior", C.c_int),
-                ("max_records", C.c_int), ("max_nals", C.c_int), ("device", C.c_int), ("batcher", C.c_void_p)]
+                ("max_records", C.c_int), ("max_nals", C.c_int), ("device", C.c_int), ("bcf_typed", C.c_int),
+                ("batcher", C.c_void_p)]
 
 
 class B200Rec(C.Structure):
     _fields_ = [("n_allele", C.c_int), ("PLs", C.c_void_p), ("nPLs", C.c_int), ("QS", C.c_void_p), ("nQS", C.c_int),
                 ("ADs", C.c_void_p), ("nADs", C.c_int), ("prior_an", C.c_int32), ("prior_ac", C.c_void_p),
-                ("n_prior_ac", C.c_int), ("user", C.c_void_p)]
+                ("n_prior_ac", C.c_int), ("user", C.c_void_p), ("PL_typed", C.c_void_p), ("PL_bt", C.c_int)]
 
 
 class B200Out(C.Structure):
     _fields_ = [("ret", C.c_int), ("als_new", C.c_uint32), ("als_map", C.POINTER(C.c_int8)), ("qual", C.c_float),
                 ("ac", C.POINTER(C.c_int32)), ("an", C.c_int), ("site_flags", C.c_uint32),
                 ("gts", C.POINTER(C.c_int32)), ("GQs", C.POINTER(C.c_int32)), ("PLs", C.POINTER(C.c_int32)), ("nPLs", C.c_int),
-                ("GPs", C.POINTER(C.c_float)), ("user", C.c_void_p)]
+                ("GPs", C.POINTER(C.c_float)), ("user", C.c_void_p),
+                ("gts8", C.POINTER(C.c_int8)), ("GQs8", C.POINTER(C.c_int8)), ("PLs16", C.POINTER(C.c_int16))]
 
 
 HOST_EXPORTS = ["b200_mcall_init", "b200_mcall", "b200_mcall_flush", "b200_mcall_result", "b200_mcall_destroy",
@@ -46,9 +48,19 @@ def _lib():
     return L
 
 
-def replay(params, batch, ploidy_tab=None, max_records=64):
+def _widen(a, bits):
+    lo = -(1 << (bits - 1))
+    o = a.astype(np.int32)
+    o[a == lo] = np.iinfo(np.int32).min
+    o[a == lo + 1] = np.iinfo(np.int32).min + 1
+    return o
+
+
+def replay(params, batch, ploidy_tab=None, max_records=64, typed=False):
     """Feed a HostBatch record by record through b200_mcall (like vcfcall.c:1089-1148 feeds mcall) and collect the
-    results into an abi.HostResult laid out like the C-ABI's, so that the usual comparison helpers apply."""
+    results into an abi.HostResult laid out like the C-ABI's, so that the usual comparison helpers apply.
+    typed=True: b200_call_t.bcf_typed -- PL goes in as the int8/int16 typed vector a BCF record would hold (int8 when
+    every value fits, like bcf_enc_vint chooses) and GT / GQ / PL come back as int8 / int8 / int16 vectors."""
     from . import abi
     L = _lib()
     S = params.nsmpl
@@ -60,6 +72,7 @@ def replay(params, batch, ploidy_tab=None, max_records=64):
     if params.ngroups > 1:
         call.grp_off, call.grp_smpl = params.grp_off.ctypes.data, params.grp_smpl.ctypes.data
     call.use_prior, call.max_records, call.max_nals, call.device = int(params.use_prior), max_records, params.max_nals, params.device
+    call.bcf_typed = int(typed)
     L.b200_mcall_init(C.byref(call))
     res = abi.HostResult(batch, want_gp=bool(params.output_tags & abi.CALL_FMT_GP))
     done = [0]
@@ -75,6 +88,17 @@ def replay(params, batch, ploidy_tab=None, max_records=64):
             res.als_new[i], res.qual[i], res.an[i] = out.als_new, out.qual, out.an
             res.als_map[i] = np.ctypeslib.as_array(out.als_map, (params.max_nals,))
             res.ac[i] = np.ctypeslib.as_array(out.ac, (params.max_nals,))
+            if typed:
+                assert not out.gts and not out.PLs
+                res.gt[i] = _widen(np.ctypeslib.as_array(out.gts8, (S, 2)), 8)
+                if out.GQs8:
+                    res.gq[i] = _widen(np.ctypeslib.as_array(out.GQs8, (S,)), 8)
+                if out.PLs16:
+                    o = batch.pl_off[i]
+                    res.pl[o:o + out.nPLs] = _widen(np.ctypeslib.as_array(out.PLs16, (out.nPLs,)), 16)
+                    if out.GPs and res.gp is not None:
+                        res.gp[o:o + out.nPLs] = np.ctypeslib.as_array(out.GPs, (out.nPLs,))
+                continue
             res.gt[i] = np.ctypeslib.as_array(out.gts, (S, 2))
             if out.GQs:
                 res.gq[i] = np.ctypeslib.as_array(out.GQs, (S,))
@@ -94,6 +118,15 @@ def replay(params, batch, ploidy_tab=None, max_records=64):
             pl = np.ascontiguousarray(batch.site_pl(i))
             rec.n_allele, rec.PLs, rec.nPLs = int(batch.nals[i]), pl.ctypes.data, pl.size
             keep = [pl]
+            if typed:
+                real = pl[pl > np.iinfo(np.int32).min + 1]
+                bits = 8 if real.size == 0 or (real.max() <= 127 and real.min() >= -120) else 16
+                lo = -(1 << (bits - 1))
+                nar = pl.astype(np.int8 if bits == 8 else np.int16)
+                nar[pl == np.iinfo(np.int32).min] = lo
+                nar[pl == np.iinfo(np.int32).min + 1] = lo + 1
+                rec.PLs, rec.PL_typed, rec.PL_bt = None, nar.ctypes.data, bits // 8
+                keep.append(nar)
             if params.ngroups > 1:
                 ad = np.ascontiguousarray(batch.site_ad(i))
                 rec.ADs, rec.nADs = ad.ctypes.data, ad.size

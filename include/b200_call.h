@@ -40,6 +40,9 @@ typedef struct
     int      max_records;       /* records per batch, 0 = 4096 */
     int      max_nals;          /* 0 = 5 (B2B_MAX_ALLELES, bam2bcf.h:64) */
     int      device;            /* CUDA device ordinal */
+    int      bcf_typed;         /* 1: BCF typed vectors both ways: FORMAT/PL is handed over as the record's own
+                                   int8/int16 vector (b200_rec_t.PL_typed, e.g. bcf_fmt_t.p or b200_bcf_fmt_t.p) and GT / GQ / PL
+                                   come back as int8 / int8 / int16 vectors (b200_out_t.gts8 / GQs8 / PLs16); pooled calling only */
     /* ---- owned by this layer ---- */
     b200_batcher_t *batcher;
 }
@@ -55,6 +58,7 @@ typedef struct
     int32_t prior_an;               /* -F: INFO AN or INT32_MIN if absent (mcall.c:1507) */
     const int32_t *prior_ac; int n_prior_ac;
     void *user;                 /* e.g. the retained bcf1_t*, handed back with the result */
+    const void *PL_typed; int PL_bt;    /* bcf_typed: the PL vector as stored in the record, nPLs values of BCF_BT_INT8 (1) or BCF_BT_INT16 (2) */
 }
 b200_rec_t;
 
@@ -72,6 +76,10 @@ typedef struct
     const int32_t *PLs; int nPLs;   /* trimmed PLs: nsmpl*G' values, NULL when the tag is dropped (mcall.c:1583) */
     const float   *GPs;             /* FORMAT/GP (-a GP, mcall.c:859-884, 1621): nPLs float32 values laid out like PLs, or NULL */
     void *user;
+    /* bcf_typed: the same three vectors in the types a BCF record stores them in (gts / GQs / PLs are NULL then) */
+    const int8_t  *gts8;        /* [nsmpl*2] */
+    const int8_t  *GQs8;        /* [nsmpl] or NULL */
+    const int16_t *PLs16;       /* nPLs values or NULL */
 }
 b200_out_t;
 

@@ -360,3 +360,19 @@ def test_host_batcher_replays_reference_goldens(name):
         pytest.skip("no QS")
     res = host_call.replay(params, batch, tab, max_records=16)
     assert golden_util.check_against_expect(case, params, batch, res) == len(case["expect"])
+
+
+@pytest.mark.parametrize("name", golden_util.case_names())
+def test_host_batcher_bcf_typed_replays_reference_goldens(name):
+    """b200_call_t.bcf_typed: the same replay with FORMAT/PL handed over as the int8/int16 typed vector a BCF record
+    holds and GT / GQ / PL coming back as int8 / int8 / int16 vectors."""
+    from bcftools_b200 import host_call
+    params, batch, tab, case = golden_util.load_case(name)
+    if params.ngroups > 1:
+        pytest.skip("typed transport is for pooled calling")
+    if any(s.get("qs") is None for s in case["sites"]):
+        pytest.skip("no QS")
+    if batch.pl.max() > 32767:
+        pytest.skip("PL beyond int16")
+    res = host_call.replay(params, batch, tab, max_records=16, typed=True)
+    assert golden_util.check_against_expect(case, params, batch, res) == len(case["expect"])
