@@ -19,7 +19,9 @@ namespace mcb {
 
 #define GBLOCK 128
 #define GNW    (GBLOCK/32)
+#ifndef BIG_GROUP
 #define BIG_GROUP 64        /* groups of at least this many samples are reduced by the whole CTA, sample-parallel */
+#endif
 
 struct GroupRec
 {
