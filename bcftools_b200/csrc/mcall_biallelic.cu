@@ -606,8 +606,10 @@ __global__ void __launch_bounds__(BW_MAXWARP*32, BW_MINCTA) mcall_biallelic_warp
              *  no escape-list overflow, an even sample count (16-byte aligned GT pairs): straight-line code, each lane takes
              *  TWO ADJACENT samples per iteration so that their dependency chains interleave and GT / GQ / PL of the pair
              *  leave as one 128-bit, one 64-bit and three 64-bit stores (a warp still writes contiguous rows).  */
-            const bool fast2 = !PLOIDY && !ref_gt && c.nsel==2 && c.inc_dip==7 && want_gq && out_pl && pl3 && out_gt && out_gq
-                               && !esc_overflow && !(S & 1);
+            const bool pair_ok = !ref_gt && c.nsel==2 && c.inc_dip==7 && want_gq && out_pl && pl3 && out_gt && out_gq && !esc_overflow && !(S & 1)
+                                 && !((reinterpret_cast<uintptr_t>(out_gt) & 15) | (reinterpret_cast<uintptr_t>(out_gq) & 7) | (reinterpret_cast<uintptr_t>(out_pl) & 7));
+            const bool fast2 = !PLOIDY && pair_ok;
+            const bool fastp = PLOIDY && pair_ok && inc_hap==3;
             if ( fast2 )
             {
                 const double q1x2 = __dmul_rn(2.0, c.q1);
@@ -646,6 +648,56 @@ __global__ void __launch_bounds__(BW_MAXWARP*32, BW_MINCTA) mcall_biallelic_warp
                         if ( !esc1 ) { stg64(out_gt + 4*(size_t)pr + 2, o1.x, o1.y); stg32(out_gq + 2*(size_t)pr + 1, q1); }
                     }
                 }
+            }
+            else if ( fastp )
+            {
+                /*  The same site under a ploidy vector (chrX): per-sample ploidy 0 / 1 / 2 is folded into the straight-line code with
+                 *  selects -- haploid likelihoods are the intermediates of the diploid ones (fast2_call), GT / PL rows take the
+                 *  shapes of mcall.c:793-808, 1158-1194 -- so diploid and haploid lanes of a warp do not diverge.  */
+                const double q1x2 = __dmul_rn(2.0, c.q1);
+                const int npair = S >> 1;
+                int nall = 0;
+                #pragma unroll 1
+                for (int pr=lane; pr<npair; pr+=32)
+                {
+                    const uint32_t ad = buf_s + 6u*(uint32_t)pr;
+                    const uint32_t pa0 = ldsu8(ad), pb0 = ldsu8(ad + 1u), pc0 = ldsu8(ad + 2u);
+                    const uint32_t pa1 = ldsu8(ad + 3u), pb1 = ldsu8(ad + 4u), pc1 = ldsu8(ad + 5u);
+                    const int pd0 = (int)__ldg(ploidy + 2*pr), pd1 = (int)__ldg(ploidy + 2*pr + 1);
+                    int k0, k1, q0, q1;
+                    {
+                        const double p0 = lds64c(pl2p_s + 8u*pa0), p1 = lds64c(pl2p_s + 8u*pb0), p2 = lds64c(pl2p_s + 8u*pc0);
+                        fast2_call(p0, p1, p2, __dadd_rn(__dadd_rn(p0, p1), p2), c.q0, c.q1, q1x2, thr_s, k0, q0, pd0!=2);
+                    }
+                    {
+                        const double p0 = lds64c(pl2p_s + 8u*pa1), p1 = lds64c(pl2p_s + 8u*pb1), p2 = lds64c(pl2p_s + 8u*pc1);
+                        fast2_call(p0, p1, p2, __dadd_rn(__dadd_rn(p0, p1), p2), c.q0, c.q1, q1x2, thr_s, k1, q1, pd1!=2);
+                    }
+                    const bool esc0 = (pa0 & pb0 & pc0) == 255u, esc1 = (pa1 & pb1 & pc1) == 255u;
+                    const bool cl0 = (pa0 | pb0 | pc0) != 0 && !esc0 && pd0, cl1 = (pa1 | pb1 | pc1) != 0 && !esc1 && pd1;   /* PL=0,0,0 / ploidy 0: no call */
+                    /* trimmed PL rows (mcall.c:1158-1194): diploid a,b,c; haploid the two homozygous values, vector_end; ploidy 0 missing */
+                    const int r00 = pd0 ? (int)pa0 : I32_MISSING, r01 = pd0==2 ? (int)pb0 : (pd0 ? (int)pc0 : I32_VEC_END), r02 = pd0==2 ? (int)pc0 : I32_VEC_END;
+                    const int r10 = pd1 ? (int)pa1 : I32_MISSING, r11 = pd1==2 ? (int)pb1 : (pd1 ? (int)pc1 : I32_VEC_END), r12 = pd1==2 ? (int)pc1 : I32_VEC_END;
+                    int32_t *dpl = out_pl + 6*(size_t)pr;       /* escaped samples: placeholders, rewritten after the loop */
+                    stg64(dpl, r00, r01); stg64(dpl + 2, r02, r10); stg64(dpl + 4, r11, r12);
+                    /* new alleles 0 and 1 = GT codes 2 and 4; haploid: one allele then vector_end (mcall.c:805-807) */
+                    const int x0 = cl0 ? (k0==2 ? 4 : 2) : 0, y0 = pd0==2 ? (cl0 ? (k0 ? 4 : 2) : 0) : I32_VEC_END;
+                    const int x1 = cl1 ? (k1==2 ? 4 : 2) : 0, y1 = pd1==2 ? (cl1 ? (k1 ? 4 : 2) : 0) : I32_VEC_END;
+                    ac1 += (cl0 ? (pd0==2 ? k0 : (k0>>1)) : 0) + (cl1 ? (pd1==2 ? k1 : (k1>>1)) : 0);
+                    nall += (cl0 ? pd0 : 0) + (cl1 ? pd1 : 0);
+                    q0 = cl0 ? q0 : 0; q1 = cl1 ? q1 : 0;
+                    if ( !(esc0 | esc1) )
+                    {
+                        stg128(out_gt + 4*(size_t)pr, x0, y0, x1, y1);
+                        stg64(out_gq + 2*(size_t)pr, q0, q1);
+                    }
+                    else            /* on the escape list: called after this loop */
+                    {
+                        if ( !esc0 ) { stg64(out_gt + 4*(size_t)pr, x0, y0); stg32(out_gq + 2*(size_t)pr, q0); }
+                        if ( !esc1 ) { stg64(out_gt + 4*(size_t)pr + 2, x1, y1); stg32(out_gq + 2*(size_t)pr + 1, q1); }
+                    }
+                }
+                ac0 += nall - ac1;          /* ac1 is still this loop's own count here */
             }
             else
 #endif

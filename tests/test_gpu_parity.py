@@ -71,6 +71,33 @@ def test_mixed_ploidy(S, oracle_built):
     assert st["compared"] > 0, st
 
 
+@pytest.mark.parametrize("S", [2, 64, 1000, 2504])
+@pytest.mark.parametrize("flag", [0, abi.CALL_KEEPALT])
+def test_two_allele_kernel_under_ploidy_vectors(S, flag, oracle_built):
+    """Two-allele sites with per-sample ploidy 0 / 1 / 2 (even S: the straight-line pair path of the warp kernel with the
+    ploidy folded into selects; missing values and zero QS send sites / samples through the general code)."""
+    from bcftools_b200 import mcall
+    rng = np.random.default_rng(100 + S + flag)
+    batch = parity.random_batch(rng, 60 if S > 500 else 160, S, 2, minA=2)
+    tab = np.full((3, S), 2, np.uint8)
+    tab[1, ::2] = 1
+    tab[2, ::3] = 1
+    tab[2, 1::5] = 0
+    batch.ploidy_id = rng.integers(0, 3, batch.nsites).astype(np.uint16)
+    params = abi.CallParams(S, 2, flag=flag, output_tags=abi.CALL_FMT_GQ)
+    exp, _ = oracle_built.call("port", params, batch, tab)
+    with mcall.MCaller(params, ploidy_tab=tab) as mc:
+        got = mc.call_host(batch, compact=True)
+    assert parity.compare(got, exp, params)["compared"] > 0
+    if S == 2504:       # the C5 shape, pooled: every 2nd sample haploid
+        p5, b5, t5 = synth.make_batch("C5", 200, with_groups=0)
+        e5, _ = oracle_built.call("port", p5, b5, t5)
+        with mcall.MCaller(p5, ploidy_tab=t5) as mc:
+            g5 = mc.call_host(b5)
+        st = parity.compare(g5, e5, p5)
+        assert st["compared"] > 0 and not st["near_ties"], st
+
+
 @pytest.mark.parametrize("S,maxA,mode,flag", [(30, 5, 3, 0), (9, 4, "single", abi.CALL_VARONLY), (200, 5, 7, abi.CALL_KEEPALT), (64, 3, 2, 0),
                                               (300, 5, "mixed", 0), (700, 4, 3, abi.CALL_VARONLY)])
 def test_sample_groups(S, maxA, mode, flag, oracle_built):
