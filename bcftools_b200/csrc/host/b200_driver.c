@@ -1,0 +1,275 @@
+/*  b200_driver.c -- ploidy definitions, -G group files and the unseen allele without htslib (include/b200_driver.h).  */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <ctype.h>
+#include <limits.h>
+#include "b200_driver.h"
+
+typedef struct { char *chr; int64_t beg, end; int sex, ploidy; } preg_t;      /* 0-based inclusive */
+struct b200_ploidy
+{
+    int nsex, dflt, min, max, nreg;
+    char **id2sex;  int *sex2dflt;
+    preg_t *reg;
+};
+
+static char *dup_n(const char *s, size_t n) { char *d = (char*) malloc(n+1); if ( d ) { memcpy(d, s, n); d[n] = 0; } return d; }
+
+static int sex_id(const b200_ploidy_t *p, const char *sex)
+{
+    for (int i=0; i<p->nsex; i++) if ( !strcmp(p->id2sex[i], sex) ) return i;
+    return -1;
+}
+static int sex_new(b200_ploidy_t *p, const char *sex, int dflt)
+{
+    char **a = (char**) realloc(p->id2sex, sizeof(char*)*(p->nsex+1));
+    if ( !a ) return -1;
+    p->id2sex = a;
+    int *d = (int*) realloc(p->sex2dflt, sizeof(int)*(p->nsex+1));
+    if ( !d ) return -1;
+    p->sex2dflt = d;
+    p->id2sex[p->nsex] = dup_n(sex, strlen(sex));
+    p->sex2dflt[p->nsex] = dflt;
+    return p->nsex++;
+}
+
+/*  one definition line (ploidy_parse, ploidy.c:55-121); 0 ok, 1 skipped (empty / comment), <0 error  */
+static int parse_line(b200_ploidy_t *p, const char *ss, const char *end)
+{
+    const char *f[5]; size_t fl[5]; int nf = 0;
+    while ( ss < end && nf < 5 )
+    {
+        while ( ss < end && isspace((unsigned char)*ss) ) ss++;
+        if ( ss >= end ) break;
+        const char *se = ss;
+        while ( se < end && !isspace((unsigned char)*se) ) se++;
+        f[nf] = ss; fl[nf] = (size_t)(se - ss); nf++;
+        ss = se;
+    }
+    if ( !nf || f[0][0]=='#' ) return 1;
+    if ( nf < 5 ) return B200_DRV_EPARSE;
+    const int is_dflt = fl[0]==1 && f[0][0]=='*';       /* "* * * <sex> <ploidy>" */
+    char *sex = dup_n(f[3], fl[3]), *num = dup_n(f[4], fl[4]), *e = NULL;
+    if ( !sex || !num ) { free(sex); free(num); return B200_DRV_ENOMEM; }
+    const long pl = strtol(num, &e, 10);
+    int rc = (e==num) ? B200_DRV_EPARSE : 0;
+    int id = -1;
+    if ( !rc )
+    {
+        id = sex_id(p, sex);
+        if ( id < 0 ) id = sex_new(p, sex, -1);
+        if ( id < 0 ) rc = B200_DRV_ENOMEM;
+    }
+    if ( !rc )
+    {
+        if ( p->min<0 || pl < p->min ) p->min = (int)pl;
+        if ( p->max<0 || pl > p->max ) p->max = (int)pl;
+        /* ploidy.c:114-118 stores the default under the most recently ADDED sex, not under the line's own one: kept */
+        if ( is_dflt ) p->sex2dflt[p->nsex-1] = (int)pl;
+        else
+        {
+            char *b = dup_n(f[1], fl[1]), *t = dup_n(f[2], fl[2]), *eb = NULL, *et = NULL;
+            const long long beg = b ? strtoll(b, &eb, 10) : 0, to = t ? strtoll(t, &et, 10) : 0;
+            if ( !b || !t ) rc = B200_DRV_ENOMEM;
+            else if ( eb==b || et==t || beg<1 || to<beg ) rc = B200_DRV_EPARSE;
+            else
+            {
+                preg_t *r = (preg_t*) realloc(p->reg, sizeof(preg_t)*(p->nreg+1));
+                if ( !r ) rc = B200_DRV_ENOMEM;
+                else
+                {
+                    p->reg = r;
+                    r[p->nreg].chr = dup_n(f[0], fl[0]); r[p->nreg].beg = beg-1; r[p->nreg].end = to-1;
+                    r[p->nreg].sex = id; r[p->nreg].ploidy = (int)pl;
+                    p->nreg++;
+                }
+            }
+            free(b); free(t);
+        }
+    }
+    free(sex); free(num);
+    return rc;
+}
+
+b200_ploidy_t *b200_ploidy_init_string(const char *str, int dflt)
+{
+    b200_ploidy_t *p = (b200_ploidy_t*) calloc(1, sizeof *p);
+    if ( !p ) return NULL;
+    p->min = p->max = -1;
+    const char *ss = str;
+    while ( *ss )
+    {
+        const char *se = ss;
+        while ( *se && *se!='\r' && *se!='\n' ) se++;
+        if ( parse_line(p, ss, se) < 0 ) { b200_ploidy_destroy(p); return NULL; }
+        while ( *se=='\r' || *se=='\n' ) se++;
+        ss = se;
+    }
+    /* _set_defaults (ploidy.c:123-134) */
+    const int star = sex_id(p, "*");
+    if ( star >= 0 ) dflt = p->sex2dflt[star];
+    for (int i=0; i<p->nsex; i++) if ( p->sex2dflt[i]==-1 ) p->sex2dflt[i] = dflt;
+    p->dflt = dflt;
+    if ( p->min<0 || dflt < p->min ) p->min = dflt;
+    if ( p->max<0 || dflt > p->max ) p->max = dflt;
+    return p;
+}
+
+void b200_ploidy_destroy(b200_ploidy_t *p)
+{
+    if ( !p ) return;
+    for (int i=0; i<p->nsex; i++) free(p->id2sex[i]);
+    for (int i=0; i<p->nreg; i++) free(p->reg[i].chr);
+    free(p->id2sex); free(p->sex2dflt); free(p->reg); free(p);
+}
+
+int b200_ploidy_add_sex(b200_ploidy_t *p, const char *sex)
+{
+    const int id = sex_id(p, sex);
+    return id >= 0 ? id : sex_new(p, sex, p->dflt);
+}
+int b200_ploidy_nsex(const b200_ploidy_t *p) { return p->nsex; }
+int b200_ploidy_sex2id(const b200_ploidy_t *p, const char *sex) { return sex_id(p, sex); }
+const char *b200_ploidy_id2sex(const b200_ploidy_t *p, int id) { return (id<0 || id>=p->nsex) ? NULL : p->id2sex[id]; }
+int b200_ploidy_min(const b200_ploidy_t *p) { return p->dflt < p->min ? p->dflt : p->min; }
+int b200_ploidy_max(const b200_ploidy_t *p) { return p->dflt > p->max ? p->dflt : p->max; }
+
+int b200_ploidy_query(const b200_ploidy_t *p, const char *seq, int64_t pos, int *sex2ploidy, int *min, int *max)
+{
+    int hit = 0, mn = INT_MAX, mx = -1;
+    for (int i=0; i<p->nreg; i++)
+    {
+        const preg_t *r = p->reg + i;
+        if ( pos < r->beg || pos > r->end || strcmp(r->chr, seq) ) continue;
+        if ( !hit && sex2ploidy ) for (int k=0; k<p->nsex; k++) sex2ploidy[k] = p->dflt;
+        hit = 1;
+        if ( r->ploidy != p->dflt )
+        {
+            if ( sex2ploidy ) sex2ploidy[r->sex] = r->ploidy;
+            if ( mn > r->ploidy ) mn = r->ploidy;
+            if ( mx < r->ploidy ) mx = r->ploidy;
+        }
+    }
+    if ( !hit )
+    {
+        if ( min ) *min = p->dflt;
+        if ( max ) *max = p->dflt;
+        if ( sex2ploidy ) for (int k=0; k<p->nsex; k++) sex2ploidy[k] = p->sex2dflt[k];
+        return 0;
+    }
+    if ( mx==-1 ) mx = mn = p->dflt;
+    if ( min ) *min = mn;
+    if ( max ) *max = mx;
+    return 1;
+}
+
+int b200_set_ploidy(const b200_ploidy_t *p, const char *seq, int64_t pos, const int *sample2sex, int nsmpl,
+                    int *sex2ploidy_prev, uint8_t *ploidy)
+{
+    int cur[64], *s2p = cur, i;
+    if ( p->nsex > 64 && !(s2p = (int*) malloc(sizeof(int)*p->nsex)) ) return B200_DRV_ENOMEM;
+    b200_ploidy_query(p, seq, pos, s2p, NULL, NULL);
+    for (i=0; i<p->nsex; i++) if ( s2p[i]!=sex2ploidy_prev[i] ) break;
+    const int changed = i < p->nsex;
+    if ( changed )
+    {
+        for (i=0; i<nsmpl; i++) ploidy[i] = (uint8_t)(sample2sex[i]<0 ? -sample2sex[i] : s2p[sample2sex[i]]);
+        memcpy(sex2ploidy_prev, s2p, sizeof(int)*p->nsex);
+    }
+    if ( s2p != cur ) free(s2p);
+    return changed;
+}
+
+/* ---- -G groups ------------------------------------------------------------------------------------ */
+static void set_err(char *err, size_t n, const char *fmt, const char *a)
+{
+    if ( err && n ) snprintf(err, n, fmt, a);
+}
+
+int b200_groups_parse(const char *text, const char *const *samples, int nsmpl, uint32_t *grp_off, uint32_t *grp_smpl,
+                      int *ngroups, char *err, size_t errlen)
+{
+    int i;
+    if ( !strcmp(text, "-") )           /* single-sample calling: every sample is its own group (mcall.c:285-296) */
+    {
+        for (i=0; i<nsmpl; i++) { grp_off[i] = (uint32_t)i; grp_smpl[i] = (uint32_t)i; }
+        grp_off[nsmpl] = (uint32_t)nsmpl;
+        *ngroups = nsmpl;
+        return 0;
+    }
+    int *smpl2grp = (int*) calloc(nsmpl ? nsmpl : 1, sizeof(int));        /* group + 1, 0 = not listed */
+    char **gname = (char**) calloc(nsmpl ? nsmpl : 1, sizeof(char*));
+    uint32_t *cnt = (uint32_t*) calloc(nsmpl ? nsmpl : 1, sizeof(uint32_t));
+    if ( !smpl2grp || !gname || !cnt ) { free(smpl2grp); free(gname); free(cnt); return B200_DRV_ENOMEM; }
+    int ng = 0, rc = 0;
+    const char *ss = text;
+    while ( *ss && !rc )
+    {
+        const char *le = ss;
+        while ( *le && *le!='\n' && *le!='\r' ) le++;
+        if ( le > ss )                  /* hts_readlist drops empty lines */
+        {
+            const char *p = ss;
+            while ( p<le && !isspace((unsigned char)*p) ) p++;
+            const char *name_end = p;
+            while ( p<le && isspace((unsigned char)*p) ) p++;
+            if ( name_end==le || p==le )
+            {
+                char *l = dup_n(ss, (size_t)(le-ss));
+                set_err(err, errlen, "Could not parse the line, expected a sample name followed by tab and a population name: %s", l ? l : "");
+                free(l);
+                rc = B200_DRV_EPARSE;
+                break;
+            }
+            /* mcall.c:310-325 leaves ptr on the FIRST character of the population name and keys the hash with ptr+1: groups
+               are told apart by the remainder of the line behind that character ("CEU" and "YEU" are one group).  Kept. */
+            const char *g = p + 1; size_t gl = (size_t)(le - g);
+            int ismpl = -1;
+            for (i=0; i<nsmpl; i++) if ( strlen(samples[i])==(size_t)(name_end-ss) && !strncmp(samples[i], ss, (size_t)(name_end-ss)) ) { ismpl = i; break; }
+            if ( ismpl >= 0 )
+            {
+                if ( smpl2grp[ismpl] )
+                {
+                    set_err(err, errlen, "Error: the sample \"%s\" is listed twice", samples[ismpl]);
+                    rc = B200_DRV_EDUP;
+                    break;
+                }
+                int ig = -1;
+                for (i=0; i<ng; i++) if ( strlen(gname[i])==gl && !strncmp(gname[i], g, gl) ) { ig = i; break; }
+                if ( ig < 0 ) { gname[ng] = dup_n(g, gl); ig = ng++; }
+                cnt[ig]++;
+                smpl2grp[ismpl] = ig + 1;
+            }
+        }
+        while ( *le=='\n' || *le=='\r' ) le++;
+        ss = le;
+    }
+    if ( !rc && !ng ) { set_err(err, errlen, "Could not parse the file, no matching samples found%s", ""); rc = B200_DRV_EMISSING; }
+    if ( !rc )
+        for (i=0; i<nsmpl; i++)
+            if ( !smpl2grp[i] ) { set_err(err, errlen, "Error: The sample \"%s\" is not listed", samples[i]); rc = B200_DRV_EMISSING; break; }
+    if ( !rc )
+    {
+        grp_off[0] = 0;
+        for (i=0; i<ng; i++) grp_off[i+1] = grp_off[i] + cnt[i];
+        for (i=0; i<ng; i++) cnt[i] = 0;
+        for (i=0; i<nsmpl; i++) { const int ig = smpl2grp[i] - 1; grp_smpl[grp_off[ig] + cnt[ig]++] = (uint32_t)i; }    /* header order */
+        *ngroups = ng;
+    }
+    for (i=0; i<ng; i++) free(gname[i]);
+    free(smpl2grp); free(gname); free(cnt);
+    return rc;
+}
+
+/* ---- unseen allele ---------------------------------------------------------------------------------- */
+int b200_unseen_allele(const char *const *alleles, int n_allele)
+{
+    for (int i=1; i<n_allele; i++)
+    {
+        const char *a = alleles[i];
+        if ( a[0]=='X' ) return i;                                          /* old X */
+        if ( a[0]=='<' && (a[1]=='X' || a[1]=='*') && a[2]=='>' ) return i; /* old <X>, new <*> */
+    }
+    return 0;
+}

@@ -1,0 +1,100 @@
+"""ctypes mirror of include/b200_driver.h: ploidy definitions, -G group files, the unseen allele (host code of libmcall_b200.so)."""
+import ctypes as C
+
+import numpy as np
+
+from . import mcall
+
+DRIVER_EXPORTS = ["b200_ploidy_init_string", "b200_ploidy_destroy", "b200_ploidy_add_sex", "b200_ploidy_nsex", "b200_ploidy_sex2id",
+                  "b200_ploidy_id2sex", "b200_ploidy_min", "b200_ploidy_max", "b200_ploidy_query", "b200_set_ploidy",
+                  "b200_groups_parse", "b200_unseen_allele"]
+
+
+class DriverError(ValueError):
+    pass
+
+
+def _lib():
+    L = mcall.lib()
+    if not getattr(L, "_drv_ready", False):
+        L.b200_ploidy_init_string.argtypes = [C.c_char_p, C.c_int]
+        L.b200_ploidy_init_string.restype = C.c_void_p
+        L.b200_ploidy_destroy.argtypes = [C.c_void_p]
+        L.b200_ploidy_destroy.restype = None
+        L.b200_ploidy_add_sex.argtypes = [C.c_void_p, C.c_char_p]
+        L.b200_ploidy_sex2id.argtypes = [C.c_void_p, C.c_char_p]
+        for f in ("nsex", "min", "max"):
+            getattr(L, "b200_ploidy_" + f).argtypes = [C.c_void_p]
+        L.b200_ploidy_id2sex.argtypes = [C.c_void_p, C.c_int]
+        L.b200_ploidy_id2sex.restype = C.c_char_p
+        L.b200_ploidy_query.argtypes = [C.c_void_p, C.c_char_p, C.c_int64, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.b200_set_ploidy.argtypes = [C.c_void_p, C.c_char_p, C.c_int64, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.b200_groups_parse.argtypes = [C.c_char_p, C.POINTER(C.c_char_p), C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_int),
+                                        C.c_char_p, C.c_size_t]
+        L.b200_unseen_allele.argtypes = [C.POINTER(C.c_char_p), C.c_int]
+        L._drv_ready = True
+    return L
+
+
+class Ploidy:
+    """ploidy_t of ploidy.c: definitions "CHROM FROM TO SEX PLOIDY" and per-position queries."""
+
+    def __init__(self, text, dflt=2):
+        self._p = _lib().b200_ploidy_init_string(text.encode(), dflt)
+        if not self._p:
+            raise DriverError("could not parse the ploidy definition")
+
+    def close(self):
+        if self._p:
+            _lib().b200_ploidy_destroy(self._p)
+            self._p = None
+
+    def __del__(self):
+        self.close()
+
+    def add_sex(self, sex):
+        return _lib().b200_ploidy_add_sex(self._p, sex.encode())
+
+    @property
+    def sexes(self):
+        L = _lib()
+        return [L.b200_ploidy_id2sex(self._p, i).decode() for i in range(L.b200_ploidy_nsex(self._p))]
+
+    def sex2id(self, sex):
+        return _lib().b200_ploidy_sex2id(self._p, sex.encode())
+
+    def min(self):
+        return _lib().b200_ploidy_min(self._p)
+
+    def max(self):
+        return _lib().b200_ploidy_max(self._p)
+
+    def query(self, seq, pos):
+        """(hit, {sex: ploidy}, min, max) at 0-based pos."""
+        L = _lib()
+        s2p = np.zeros(max(1, L.b200_ploidy_nsex(self._p)), np.int32)
+        mn, mx = C.c_int(), C.c_int()
+        hit = L.b200_ploidy_query(self._p, seq.encode(), pos, s2p.ctypes.data, C.byref(mn), C.byref(mx))
+        return hit, dict(zip(self.sexes, s2p.tolist())), mn.value, mx.value
+
+    def set_ploidy(self, seq, pos, sample2sex, prev, ploidy):
+        """vcfcall.c:807-825 on numpy state arrays (int32 sample2sex, int32 prev[nsex], uint8 ploidy[nsmpl])."""
+        return _lib().b200_set_ploidy(self._p, seq.encode(), pos, sample2sex.ctypes.data, len(sample2sex), prev.ctypes.data, ploidy.ctypes.data)
+
+
+def groups_parse(text, samples):
+    """(grp_off, grp_smpl) as mcb_params wants them, from a -G file's content or "-"."""
+    n = len(samples)
+    arr = (C.c_char_p * max(1, n))(*[s.encode() for s in samples])
+    off, smp = np.zeros(n + 1, np.uint32), np.zeros(max(1, n), np.uint32)
+    ng = C.c_int()
+    err = C.create_string_buffer(512)
+    rc = _lib().b200_groups_parse(text.encode(), arr, n, off.ctypes.data, smp.ctypes.data, C.byref(ng), err, len(err))
+    if rc:
+        raise DriverError("%d: %s" % (rc, err.value.decode()))
+    return off[:ng.value + 1].copy(), smp[:n].copy()
+
+
+def unseen_allele(alleles):
+    arr = (C.c_char_p * len(alleles))(*[a.encode() for a in alleles])
+    return _lib().b200_unseen_allele(arr, len(alleles))

@@ -1,0 +1,122 @@
+"""include/b200_driver.h: ploidy definitions + set_ploidy, -G group files, the unseen allele -- against
+the committed golden cases (whose per-site ploidy vectors / unseen alleles / groups reproduce the reference's outputs),
+the reference's own option files where the reference tree is present, and the quirks of ploidy.c / mcall.c."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from bcftools_b200 import driver
+from tests import golden_util
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_TEST = "/root/reference/test"
+
+# the definition the reference's chrX tests use (test/test.pl:281-283), in the format of ploidy.c:40-53
+PLOIDY_X = "X 1 1000 M 1\nX 3104 5000 M 1\n* * * M 2\n* * * F 2\n"
+
+
+def test_symbols_are_exported():
+    from bcftools_b200 import mcall
+    hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "b200_driver.h")).read(), flags=re.S)
+    syms = sorted(set(re.findall(r"\b(b200_[a-z0-9_]+)\s*\(", hdr)))
+    assert syms == sorted(driver.DRIVER_EXPORTS)
+    assert all(hasattr(mcall.lib(), s) for s in syms)
+
+
+def test_unseen_allele_of_every_golden_site():
+    n = 0
+    for name in golden_util.case_names():
+        case = golden_util.load_case(name)[3]
+        for s in case["sites"]:
+            assert driver.unseen_allele(s["alleles"]) == s["unseen"], (name, s["alleles"])
+            n += 1
+    assert n > 100
+    assert driver.unseen_allele(["A", "C", "<*>"]) == 2 and driver.unseen_allele(["A", "<X>"]) == 1
+    assert driver.unseen_allele(["A", "X"]) == 1 and driver.unseen_allele(["A", "<NON_REF>", "C"]) == 0
+    assert driver.unseen_allele(["<*>"]) == 0          # REF is never looked at (vcfcall.c:1103 starts at 1)
+
+
+@pytest.mark.parametrize("name,sexes", [("mpileup.X", "FMF"), ("mpileup.X.ped", "FMF")])
+def test_set_ploidy_replays_the_chrX_goldens(name, sexes):
+    """vcfcall.c:807-825 over the records of the golden case: the ploidy vector in force at every site must be the one the
+    golden was generated (and reproduces the reference's output) with."""
+    case = golden_util.load_case(name)[3]
+    pl = driver.Ploidy(PLOIDY_X, 2)
+    assert pl.sexes == ["M", "F"] and (pl.min(), pl.max()) == (1, 2)
+    s2s = np.array([pl.sex2id(s) for s in sexes], np.int32)
+    prev = np.full(len(pl.sexes), pl.max(), np.int32)           # vcfcall.c:652-655
+    ploidy = np.full(len(sexes), pl.max(), np.uint8)
+    changes = 0
+    for s in case["sites"]:
+        changes += pl.set_ploidy(s["chrom"], s["pos"] - 1, s2s, prev, ploidy)
+        assert ploidy.tolist() == case["ploidy_vectors"][s["ploidy_id"]], (s["pos"], ploidy)
+    assert changes >= 2
+    pl.close()
+
+
+def test_ploidy_query_semantics():
+    pl = driver.Ploidy("X 1 60000 M 1\nX 2699521 154931043 M 1\nY 1 59373566 M 1\nY 1 59373566 F 0\nMT 1 16569 M 1\nMT 1 16569 F 1\n"
+                       "*  * *     M 2\n*  * *     F 2\n", 2)
+    assert pl.sexes == ["M", "F"] and (pl.min(), pl.max()) == (0, 2)
+    assert pl.query("X", 0) == (1, {"M": 1, "F": 2}, 1, 1)
+    assert pl.query("X", 59999) == (1, {"M": 1, "F": 2}, 1, 1)      # 1-based inclusive end 60000 = 0-based 59999
+    assert pl.query("X", 60000) == (0, {"M": 2, "F": 2}, 2, 2)
+    assert pl.query("Y", 100) == (1, {"M": 1, "F": 0}, 0, 1)
+    assert pl.query("MT", 5) == (1, {"M": 1, "F": 1}, 1, 1)
+    assert pl.query("1", 5) == (0, {"M": 2, "F": 2}, 2, 2)
+    assert pl.add_sex("U") == 2 and pl.query("Y", 100)[1] == {"M": 1, "F": 0, "U": 2}
+    # a region whose ploidy equals the default does not count as a hit for min/max but still is an overlap (ploidy.c:214-226)
+    p2 = driver.Ploidy("1 10 20 M 2\n* * * M 1\n", 2)
+    assert p2.query("1", 10) == (1, {"M": 2}, 2, 2) and p2.query("1", 30) == (0, {"M": 1}, 2, 2)
+    # SEX "*" sets the default of everything (ploidy.c:126)
+    p3 = driver.Ploidy("* * * * 1\nX 1 5 F 2\n", 2)
+    assert p3.query("2", 0)[1] == {"*": 1, "F": 1} and p3.query("X", 0)[1]["F"] == 2
+    # ploidy.c:114-118 files a default under the most recently ADDED sex, not under the line's own: reproduced
+    p4 = driver.Ploidy("X 1 5 M 1\nX 1 5 F 2\n* * * M 0\n", 2)
+    assert p4.query("2", 0)[1] == {"M": 2, "F": 0}
+    with pytest.raises(driver.DriverError):
+        driver.Ploidy("X 1 5 M\n", 2)
+    with pytest.raises(driver.DriverError):
+        driver.Ploidy("X 9 5 M 1\n", 2)
+
+
+def test_groups_parse_semantics():
+    smp = ["s0", "s1", "s2", "s3", "s4"]
+    off, g = driver.groups_parse("s3\tPOPB\nsX\tPOPC\ns0 \t POPA\ns1\tPOPB\ns4\tPOPA\ns2\tPOPB\n", smp)
+    assert off.tolist() == [0, 3, 5] and g.tolist() == [1, 2, 3, 0, 4]      # first-appearance order of groups, header order inside
+    off, g = driver.groups_parse("-", smp)
+    assert off.tolist() == [0, 1, 2, 3, 4, 5] and g.tolist() == [0, 1, 2, 3, 4]
+    # mcall.c:321-325 keys the populations WITHOUT their first character: "XEU" and "YEU" are one group
+    off, g = driver.groups_parse("s0 XEU\ns1 YEU\ns2 ZRI\ns3 ZRI\ns4 XEU\n", smp)
+    assert off.tolist() == [0, 3, 5] and g.tolist() == [0, 1, 4, 2, 3]
+    with pytest.raises(driver.DriverError, match="listed twice"):
+        driver.groups_parse("s0 A1\ns0 A2\n", smp)
+    with pytest.raises(driver.DriverError, match="not listed"):
+        driver.groups_parse("s0 A1\ns1 A1\n", smp)
+    with pytest.raises(driver.DriverError, match="no matching samples"):
+        driver.groups_parse("u0 A1\n", smp)
+    with pytest.raises(driver.DriverError, match="expected a sample name"):
+        driver.groups_parse("s0\n", smp)
+
+
+@pytest.mark.parametrize("name,fname", [("call.af-fixation.2", "call.af-fixation.txt"), ("mpileup.hwe.4", "mpileup.hwe.samples")])
+def test_groups_of_the_reference_option_files(name, fname):
+    """The reference's own -G files (test/test.pl:287, 306): the parsed member lists must be the groups the golden case
+    was generated with.  Needs the reference tree (this container); skipped elsewhere."""
+    path = os.path.join(REF_TEST, fname)
+    if not os.path.exists(path):
+        pytest.skip("reference tree not present")
+    case = golden_util.load_case(name)[3]
+    off, g = driver.groups_parse(open(path).read(), case["samples"])
+    got = [g[off[k]:off[k + 1]].tolist() for k in range(len(off) - 1)]
+    assert got == case["groups"]
+
+
+def test_driver_state_feeds_the_c_abi_structs():
+    """grp_off / grp_smpl go straight into mcb_params (abi.CallParams accepts member lists: same content)."""
+    from bcftools_b200 import abi
+    off, g = driver.groups_parse("a P1\nb Q2\nc P1\n", ["a", "b", "c"])
+    p = abi.CallParams(3, 5, groups=[g[off[k]:off[k + 1]].tolist() for k in range(len(off) - 1)])
+    assert p.ngroups == 2 and p.grp_off.tolist() == off.tolist() and p.grp_smpl.tolist() == g.tolist()
