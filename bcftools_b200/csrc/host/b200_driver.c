@@ -181,6 +181,142 @@ int b200_set_ploidy(const b200_ploidy_t *p, const char *seq, int64_t pos, const 
     return changed;
 }
 
+/* ---- -S samples ----------------------------------------------------------------------------------- */
+typedef struct { char **line; int n, m; } lines_t;
+
+static int lines_push(lines_t *l, const char *s, size_t n)
+{
+    if ( l->n==l->m )
+    {
+        int m = l->m ? 2*l->m : 16;
+        char **a = (char**) realloc(l->line, sizeof(char*)*m);
+        if ( !a ) return -1;
+        l->line = a; l->m = m;
+    }
+    if ( !(l->line[l->n] = dup_n(s, n)) ) return -1;
+    l->n++;
+    return 0;
+}
+static void lines_free(lines_t *l) { for (int i=0; i<l->n; i++) free(l->line[i]); free(l->line); l->line = NULL; l->n = l->m = 0; }
+
+/*  add_sample (vcfcall.c:114-130): "name sex" unless the name is known already  */
+static int ped_add(lines_t *out, const char *name, char sex)
+{
+    const size_t len = strlen(name);
+    for (int i=0; i<out->n; i++) if ( !strncmp(out->line[i], name, len) && out->line[i][len]==' ' && strlen(out->line[i])==len+2 ) return 0;
+    char buf[1024];
+    if ( len + 3 > sizeof buf ) return -1;
+    memcpy(buf, name, len); buf[len] = ' '; buf[len+1] = sex; buf[len+2] = 0;
+    return lines_push(out, buf, len+2);
+}
+
+/*  parse_ped_samples (vcfcall.c:200-261): 1 = PED (out filled), 0 = not PED, <0 error  */
+static int ped_parse(const lines_t *in, lines_t *out)
+{
+    int i;
+    for (i=0; i<in->n; i++)
+    {
+        char *str = dup_n(in->line[i], strlen(in->line[i]));
+        if ( !str ) return B200_DRV_ENOMEM;
+        char *col[5], *tmp = str;
+        int j = 0;
+        while ( *tmp && j<5 )
+        {
+            if ( isspace((unsigned char)*tmp) )
+            {
+                *tmp = 0; ++tmp;
+                while ( isspace((unsigned char)*tmp) ) tmp++;       /* allow multiple spaces */
+                col[j++] = tmp;                                     /* first character of column j+1 */
+                continue;
+            }
+            tmp++;
+        }
+        if ( j!=5 ) { free(str); break; }
+        /* columns: family, sample = col[0], father = col[1], mother = col[2], sex = col[3]; each ends at the next separator */
+        const char sex = col[3][0]=='1' ? 'M' : 'F';
+        int rc = ped_add(out, col[0], sex);
+        if ( !rc && strcmp(col[1], "0") && strcmp(col[2], "0") ) { rc = ped_add(out, col[1], 'M'); if ( !rc ) rc = ped_add(out, col[2], 'F'); }
+        free(str);
+        if ( rc ) return B200_DRV_ENOMEM;
+    }
+    if ( i!=in->n ) return i>0 ? B200_DRV_EPARSE : 0;      /* "Could not parse samples, not a PED format." / a plain list */
+    return 1;
+}
+
+void b200_samples_default(const b200_ploidy_t *ploidy, int nhdr, int *samples_map, int *sample2sex)
+{
+    for (int i=0; i<nhdr; i++) { if ( samples_map ) samples_map[i] = i; sample2sex[i] = ploidy->nsex - 1; }
+}
+
+int b200_samples_parse(const char *text, const char *const *hdr_samples, int nhdr, b200_ploidy_t *ploidy,
+                       int *samples_map, int *sample2sex, int *nsel, int *nwarn, char *err, size_t errlen)
+{
+    lines_t in = {0,0,0}, ped = {0,0,0};
+    int rc = 0, i;
+    const char *ss = text;
+    while ( *ss )                       /* hts_readlist: one entry per non-empty line */
+    {
+        const char *le = ss;
+        while ( *le && *le!='\n' && *le!='\r' ) le++;
+        if ( le > ss && lines_push(&in, ss, (size_t)(le-ss)) ) { lines_free(&in); return B200_DRV_ENOMEM; }
+        while ( *le=='\n' || *le=='\r' ) le++;
+        ss = le;
+    }
+    rc = ped_parse(&in, &ped);
+    if ( rc < 0 )
+    {
+        if ( rc==B200_DRV_EPARSE && err && errlen ) snprintf(err, errlen, "Could not parse samples, not a PED format.");
+        lines_free(&in); lines_free(&ped);
+        return rc;
+    }
+    const lines_t *L = rc ? &ped : &in;
+    rc = 0;
+    int *old2new = (int*) malloc(sizeof(int)*(nhdr ? nhdr : 1));
+    if ( !old2new ) { lines_free(&in); lines_free(&ped); return B200_DRV_ENOMEM; }
+    const int dflt_sex = ploidy->nsex - 1;                  /* vcfcall.c:288-289 */
+    for (i=0; i<nhdr; i++) { sample2sex[i] = dflt_sex; old2new[i] = -1; }
+    int n = 0, warn = 0;
+    for (i=0; i<L->n && !rc; i++)
+    {
+        const char *s0 = L->line[i];
+        while ( *s0 && isspace((unsigned char)*s0) ) s0++;
+        if ( !*s0 ) { if ( err && errlen ) snprintf(err, errlen, "Could not parse: %s", L->line[i]); rc = B200_DRV_EPARSE; break; }
+        if ( *s0=='#' ) continue;
+        const char *e0 = s0;
+        while ( *e0 && !isspace((unsigned char)*e0) ) e0++;
+        int ismpl = -1;
+        for (int k=0; k<nhdr; k++) if ( strlen(hdr_samples[k])==(size_t)(e0-s0) && !strncmp(hdr_samples[k], s0, (size_t)(e0-s0)) ) { ismpl = k; break; }
+        if ( ismpl < 0 ) { warn++; continue; }              /* "Warning: No such sample in the VCF" */
+        if ( old2new[ismpl] != -1 ) { warn++; continue; }   /* "Warning: The sample is listed multiple times" */
+        const char *s1 = e0;
+        while ( *s1 && isspace((unsigned char)*s1) ) s1++;
+        char sex[256] = "2";                                /* default ploidy */
+        if ( *s1 )
+        {
+            const char *e1 = s1;
+            while ( *e1 && !isspace((unsigned char)*e1) ) e1++;
+            size_t l = (size_t)(e1-s1);
+            if ( l >= sizeof sex ) l = sizeof sex - 1;
+            memcpy(sex, s1, l); sex[l] = 0;
+        }
+        if ( !sex[1] && (sex[0]=='0' || sex[0]=='1' || sex[0]=='2') ) sample2sex[n] = -(sex[0]-'0');
+        else
+        {
+            const int id = b200_ploidy_add_sex(ploidy, sex);
+            if ( id < 0 ) { rc = B200_DRV_ENOMEM; break; }
+            sample2sex[n] = id;
+        }
+        samples_map[n] = ismpl;
+        old2new[ismpl] = n;
+        n++;
+    }
+    free(old2new); lines_free(&in); lines_free(&ped);
+    if ( rc ) return rc;
+    *nsel = n;
+    if ( nwarn ) *nwarn = warn;
+    return 0;
+}
+
 /* ---- -G groups ------------------------------------------------------------------------------------ */
 static void set_err(char *err, size_t n, const char *fmt, const char *a)
 {

@@ -7,7 +7,7 @@ from . import mcall
 
 DRIVER_EXPORTS = ["b200_ploidy_init_string", "b200_ploidy_destroy", "b200_ploidy_add_sex", "b200_ploidy_nsex", "b200_ploidy_sex2id",
                   "b200_ploidy_id2sex", "b200_ploidy_min", "b200_ploidy_max", "b200_ploidy_query", "b200_set_ploidy",
-                  "b200_groups_parse", "b200_unseen_allele"]
+                  "b200_groups_parse", "b200_unseen_allele", "b200_samples_parse", "b200_samples_default"]
 
 
 class DriverError(ValueError):
@@ -32,6 +32,10 @@ def _lib():
         L.b200_groups_parse.argtypes = [C.c_char_p, C.POINTER(C.c_char_p), C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_int),
                                         C.c_char_p, C.c_size_t]
         L.b200_unseen_allele.argtypes = [C.POINTER(C.c_char_p), C.c_int]
+        L.b200_samples_parse.argtypes = [C.c_char_p, C.POINTER(C.c_char_p), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_char_p, C.c_size_t]
+        L.b200_samples_default.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.b200_samples_default.restype = None
         L._drv_ready = True
     return L
 
@@ -76,6 +80,23 @@ class Ploidy:
         mn, mx = C.c_int(), C.c_int()
         hit = L.b200_ploidy_query(self._p, seq.encode(), pos, s2p.ctypes.data, C.byref(mn), C.byref(mx))
         return hit, dict(zip(self.sexes, s2p.tolist())), mn.value, mx.value
+
+    def samples_parse(self, text, hdr_samples):
+        """-S file content -> (samples_map, sample2sex, warnings); new sexes are added to this definition (vcfcall.c:270-344)."""
+        n = len(hdr_samples)
+        arr = (C.c_char_p * max(1, n))(*[s.encode() for s in hdr_samples])
+        smap, s2s = np.zeros(max(1, n), np.int32), np.zeros(max(1, n), np.int32)
+        nsel, nwarn = C.c_int(), C.c_int()
+        err = C.create_string_buffer(512)
+        rc = _lib().b200_samples_parse(text.encode(), arr, n, self._p, smap.ctypes.data, s2s.ctypes.data, C.byref(nsel), C.byref(nwarn), err, len(err))
+        if rc:
+            raise DriverError("%d: %s" % (rc, err.value.decode()))
+        return smap[:nsel.value].copy(), s2s[:nsel.value].copy(), nwarn.value
+
+    def samples_default(self, nhdr):
+        smap, s2s = np.zeros(nhdr, np.int32), np.zeros(nhdr, np.int32)
+        _lib().b200_samples_default(self._p, nhdr, smap.ctypes.data, s2s.ctypes.data)
+        return smap, s2s
 
     def set_ploidy(self, seq, pos, sample2sex, prev, ploidy):
         """vcfcall.c:807-825 on numpy state arrays (int32 sample2sex, int32 prev[nsex], uint8 ploidy[nsmpl])."""

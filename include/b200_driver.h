@@ -2,6 +2,7 @@
  *
  *    ploidy definitions and the per-record ploidy vector   ploidy.c:40-260 (ploidy_init_string, ploidy_query,
  *                                                           ploidy_add_sex), vcfcall.c:807-825 (set_ploidy)
+ *    -S sample / PED files -> sample subset and sexes        vcfcall.c:200-344 (parse_ped_samples, set_samples)
  *    -G sample-group files -> group member lists            mcall.c:250-349 (init_sample_groups)
  *    the unseen allele <*> of a record                      vcfcall.c:1101-1111
  *
@@ -43,6 +44,17 @@ int  b200_ploidy_query(const b200_ploidy_t *p, const char *seq, int64_t pos, int
  *  state, initialised to the maximum ploidy (vcfcall.c:652-655).  Returns 1 if ploidy[] was rewritten.  */
 int  b200_set_ploidy(const b200_ploidy_t *p, const char *seq, int64_t pos, const int *sample2sex, int nsmpl,
                      int *sex2ploidy_prev, uint8_t *ploidy);
+
+/* ---- -S samples files (vcfcall.c:114-130, 200-344) ---------------------------------------------- */
+/*  text: the content of the -S file -- "name [sex-or-ploidy]" lines, '#' comments, or a PED file (>= 6 columns on every line:
+ *  family, sample, father, mother, sex 1=M / other=F; parents named on a line are added as M / F when not listed themselves).
+ *  For the i-th selected sample (file order): samples_map[i] = its index in hdr_samples, sample2sex[i] = the sex id
+ *  (b200_ploidy_add_sex) or -ploidy for a literal 0 / 1 / 2; a missing second column means ploidy 2.  Samples that are not in
+ *  the header or listed twice are skipped and counted in *nwarn (the reference prints a warning).  Capacity of both arrays:
+ *  nhdr.  Without -S every sample gets the sex id nsex-1 (vcfcall.c:645-649): b200_samples_default.  */
+int  b200_samples_parse(const char *text, const char *const *hdr_samples, int nhdr, b200_ploidy_t *ploidy,
+                        int *samples_map, int *sample2sex, int *nsel, int *nwarn, char *err, size_t errlen);
+void b200_samples_default(const b200_ploidy_t *ploidy, int nhdr, int *samples_map, int *sample2sex);
 
 /* ---- -G groups (mcall.c:250-349) ------------------------------------------------------------------ */
 /*  text: the content of the group file ("sample<whitespace>group" lines) or "-" for one group per sample.  Groups are

@@ -120,3 +120,45 @@ def test_driver_state_feeds_the_c_abi_structs():
     off, g = driver.groups_parse("a P1\nb Q2\nc P1\n", ["a", "b", "c"])
     p = abi.CallParams(3, 5, groups=[g[off[k]:off[k + 1]].tolist() for k in range(len(off) - 1)])
     assert p.ngroups == 2 and p.grp_off.tolist() == off.tolist() and p.grp_smpl.tolist() == g.tolist()
+
+
+HDR3 = ["HG00100", "HG00101", "HG00102"]        # sample columns of the reference's test/mpileup*.vcf
+
+
+def test_samples_parse_semantics():
+    pl = driver.Ploidy(PLOIDY_X, 2)
+    smap, s2s, warn = pl.samples_parse("HG00102 F\n# comment\nNA1 M\nHG00100\tM\nHG00102 M\nHG00101 1\n", HDR3)
+    assert smap.tolist() == [2, 0, 1] and warn == 2                       # unknown sample + listed twice are skipped with a warning
+    assert s2s.tolist() == [pl.sex2id("F"), pl.sex2id("M"), -1]            # literal ploidy 1 -> -1 (vcfcall.c:317-320)
+    smap, s2s, _ = pl.samples_parse("HG00101\n", HDR3)
+    assert smap.tolist() == [1] and s2s.tolist() == [-2]                   # no second column: ploidy 2
+    smap, s2s, _ = pl.samples_parse("HG00100 U\n", HDR3)                   # a sex the ploidy file does not know is added with the default
+    assert pl.sexes == ["M", "F", "U"] and s2s.tolist() == [2]
+    # PED: >= 6 columns on every line; sex 1 = M, anything else F; named parents are added as M / F
+    smap, s2s, _ = pl.samples_parse("f1 HG00102 HG00100 HG00101 2 0\n", HDR3)
+    assert smap.tolist() == [2, 0, 1] and s2s.tolist() == [pl.sex2id("F"), pl.sex2id("M"), pl.sex2id("F")]
+    with pytest.raises(driver.DriverError, match="not a PED"):
+        pl.samples_parse("f1 HG00102 0 0 2 0\nHG00100 M\n", HDR3)
+    smap, s2s = pl.samples_default(3)
+    assert smap.tolist() == [0, 1, 2] and s2s.tolist() == [2, 2, 2]        # nsex-1 (vcfcall.c:645-649)
+    pl.close()
+
+
+@pytest.mark.parametrize("name,fname", [("mpileup.3", "mpileup.3.samples"), ("mpileup.4", "mpileup.4.samples"), ("mpileup.5", "mpileup.5.samples"),
+                                        ("mpileup.X", "mpileup.samples"), ("mpileup.X.ped", "mpileup.ped"), ("mpileup.X.2", "mpileup.2.samples")])
+def test_samples_of_the_reference_option_files(name, fname):
+    """The reference's own -S files (test/test.pl:278-283): selected samples in the order of the golden case, and -- with the
+    chrX ploidy definition -- the per-site ploidy vectors of the golden via set_ploidy.  Needs the reference tree."""
+    path = os.path.join(REF_TEST, fname)
+    if not os.path.exists(path):
+        pytest.skip("reference tree not present")
+    case = golden_util.load_case(name)[3]
+    pl = driver.Ploidy(PLOIDY_X if "X" in name else "* * * M 2\n* * * F 2\n", 2)
+    smap, s2s, warn = pl.samples_parse(open(path).read(), HDR3)
+    assert [HDR3[m] for m in smap] == case["samples"]
+    prev = np.full(len(pl.sexes), pl.max(), np.int32)
+    ploidy = np.full(len(smap), pl.max(), np.uint8)
+    for s in case["sites"]:
+        pl.set_ploidy(s["chrom"], s["pos"] - 1, s2s, prev, ploidy)
+        assert ploidy.tolist() == case["ploidy_vectors"][s["ploidy_id"]], (s["pos"], ploidy)
+    pl.close()
