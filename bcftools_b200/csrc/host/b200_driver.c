@@ -398,6 +398,28 @@ int b200_groups_parse(const char *text, const char *const *samples, int nsmpl, u
     return rc;
 }
 
+/* ---- record finaliser pieces ------------------------------------------------------------------------- */
+int b200_trim_numberR(const void *src, void *dst, int nvec, int nals_ori, int nals_new, const int8_t *als_map)
+{
+    const uint32_t *s = (const uint32_t*) src;
+    uint32_t *d = (uint32_t*) dst;
+    for (int v=0; v<nvec; v++)
+        for (int k=0; k<nals_ori; k++)
+        {
+            const int l = als_map[k];
+            if ( l==-1 ) continue;              /* to be dropped */
+            d[(size_t)v*nals_new + l] = s[(size_t)v*nals_ori + k];
+        }
+    return nals_new;
+}
+
+void b200_i16_to_dp4_mq(const float *a, int32_t *dp4, int32_t *mq)
+{
+    for (int i=0; i<4; i++) dp4[i] = (int32_t) a[i];
+    const float den = a[0] + a[1] + a[2] + a[3];
+    *mq = (int32_t)( (a[8] + a[10]) / den );
+}
+
 /* ---- unseen allele ---------------------------------------------------------------------------------- */
 int b200_unseen_allele(const char *const *alleles, int n_allele)
 {

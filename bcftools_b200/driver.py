@@ -7,7 +7,8 @@ from . import mcall
 
 DRIVER_EXPORTS = ["b200_ploidy_init_string", "b200_ploidy_destroy", "b200_ploidy_add_sex", "b200_ploidy_nsex", "b200_ploidy_sex2id",
                   "b200_ploidy_id2sex", "b200_ploidy_min", "b200_ploidy_max", "b200_ploidy_query", "b200_set_ploidy",
-                  "b200_groups_parse", "b200_unseen_allele", "b200_samples_parse", "b200_samples_default"]
+                  "b200_groups_parse", "b200_unseen_allele", "b200_samples_parse", "b200_samples_default",
+                  "b200_trim_numberR", "b200_i16_to_dp4_mq"]
 
 
 class DriverError(ValueError):
@@ -36,6 +37,9 @@ def _lib():
                                          C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_char_p, C.c_size_t]
         L.b200_samples_default.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.b200_samples_default.restype = None
+        L.b200_trim_numberR.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.b200_i16_to_dp4_mq.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]
+        L.b200_i16_to_dp4_mq.restype = None
         L._drv_ready = True
     return L
 
@@ -119,3 +123,21 @@ def groups_parse(text, samples):
 def unseen_allele(alleles):
     arr = (C.c_char_p * len(alleles))(*[a.encode() for a in alleles])
     return _lib().b200_unseen_allele(arr, len(alleles))
+
+
+def trim_numberR(vals, als_map, nals_new):
+    """vals[nvec][nals_ori] (int32 or float32) -> [nvec][nals_new] under als_map (mcall.c:1196-1265)."""
+    a = np.ascontiguousarray(vals)
+    assert a.dtype.itemsize == 4
+    a = a.reshape(-1, a.shape[-1])
+    out = np.zeros((a.shape[0], nals_new), a.dtype)
+    m = np.ascontiguousarray(als_map, np.int8)
+    _lib().b200_trim_numberR(a.ctypes.data, out.ctypes.data, a.shape[0], a.shape[1], nals_new, m.ctypes.data)
+    return out
+
+
+def i16_to_dp4_mq(i16):
+    a = np.ascontiguousarray(i16, np.float32)
+    dp4, mq = np.zeros(4, np.int32), C.c_int32()
+    _lib().b200_i16_to_dp4_mq(a.ctypes.data, dp4.ctypes.data, C.byref(mq))
+    return dp4.tolist(), mq.value

@@ -64,6 +64,14 @@ void b200_samples_default(const b200_ploidy_t *ploidy, int nhdr, int *samples_ma
 int  b200_groups_parse(const char *text, const char *const *samples, int nsmpl, uint32_t *grp_off, uint32_t *grp_smpl,
                        int *ngroups, char *err, size_t errlen);
 
+/* ---- record finaliser pieces ---------------------------------------------------- */
+/*  mcall_trim_and_update_numberR (mcall.c:1196-1265) on one Number=R tag of 4-byte values (int32 or float): nvec vectors
+ *  (1 for INFO, nsmpl for FORMAT) of nals_ori values each; dst[v][als_map[k]] = src[v][k] for every kept allele k
+ *  (als_map from mcb_result.als_map).  Returns the number of values per output vector (nals_new).  */
+int  b200_trim_numberR(const void *src, void *dst, int nvec, int nals_ori, int nals_new, const int8_t *als_map);
+/*  INFO/I16 -> DP4 and MQ (mcall.c:1660-1666): float arithmetic as the reference does it, truncated to int32  */
+void b200_i16_to_dp4_mq(const float *i16, int32_t *dp4, int32_t *mq);
+
 /* ---- unseen allele (vcfcall.c:1101-1111) ---------------------------------------------------------- */
 int  b200_unseen_allele(const char *const *alleles, int n_allele);         /* index of X, <X> or <*> among the ALTs, 0 = none */
 

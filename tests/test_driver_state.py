@@ -20,7 +20,7 @@ PLOIDY_X = "X 1 1000 M 1\nX 3104 5000 M 1\n* * * M 2\n* * * F 2\n"
 def test_symbols_are_exported():
     from bcftools_b200 import mcall
     hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "b200_driver.h")).read(), flags=re.S)
-    syms = sorted(set(re.findall(r"\b(b200_[a-z0-9_]+)\s*\(", hdr)))
+    syms = sorted(set(re.findall(r"\b(b200_[A-Za-z0-9_]+)\s*\(", hdr)))
     assert syms == sorted(driver.DRIVER_EXPORTS)
     assert all(hasattr(mcall.lib(), s) for s in syms)
 
@@ -162,3 +162,54 @@ def test_samples_of_the_reference_option_files(name, fname):
         pl.set_ploidy(s["chrom"], s["pos"] - 1, s2s, prev, ploidy)
         assert ploidy.tolist() == case["ploidy_vectors"][s["ploidy_id"]], (s["pos"], ploidy)
     pl.close()
+
+
+def _vcf_records(path):
+    out = []
+    for l in open(path):
+        if l.startswith("#"):
+            continue
+        f = l.rstrip("\n").split("\t")
+        info = dict(kv.split("=", 1) if "=" in kv else (kv, "") for kv in f[7].split(";"))
+        out.append(dict(chrom=f[0], pos=int(f[1]), ref=f[3], alt=f[4].split(","), info=info, fmt=f[8].split(":") if len(f) > 8 else [],
+                        smpl=[x.split(":") for x in f[9:]]))
+    return out
+
+
+def test_trim_numberR_semantics():
+    ad = np.array([[10, 3, 0, 7], [5, 0, 2, 1]], np.int32)                  # two samples, REF + 3 ALTs
+    assert driver.trim_numberR(ad, [0, -1, -1, 1], 2).tolist() == [[10, 7], [5, 1]]
+    assert driver.trim_numberR(ad, [0, 1, 2, -1], 3).tolist() == [[10, 3, 0], [5, 0, 2]]
+    assert driver.trim_numberR(np.array([[0.5, 0.25, 0.125]], np.float32), [0, -1, 1], 2).tolist() == [[0.5, 0.125]]
+
+
+@pytest.mark.parametrize("vcf,out", [("mpileup.vcf", "mpileup.1.out"), ("mpileup.X.vcf", "mpileup.X.out"), ("call-G.vcf", "call-G.1.out"),
+                                     ("mpileup.hwe.vcf", "mpileup.hwe.2.out"), ("call.af-fixation.vcf", "call.af-fixation.1.out")])
+def test_finaliser_pieces_against_the_reference_outputs(vcf, out):
+    """DP4 / MQ from INFO/I16 (mcall.c:1660-1666) and the Number=R trimming of FORMAT/AD (mcall.c:1196-1265) against the records
+    of the reference's own expected outputs.  Needs the reference tree (this container); skipped elsewhere."""
+    if not os.path.exists(os.path.join(REF_TEST, vcf)):
+        pytest.skip("reference tree not present")
+    src = {(r["chrom"], r["pos"], r["ref"]): r for r in _vcf_records(os.path.join(REF_TEST, vcf))}
+    n_dp4 = n_ad = 0
+    for o in _vcf_records(os.path.join(REF_TEST, out)):
+        r = src.get((o["chrom"], o["pos"], o["ref"]))
+        if r is None or "I16" not in r["info"]:
+            continue
+        dp4, mq = driver.i16_to_dp4_mq([float(x) for x in r["info"]["I16"].split(",")])
+        assert ",".join(map(str, dp4)) == o["info"]["DP4"] and str(mq) == o["info"]["MQ"], (o["pos"], dp4, mq)
+        n_dp4 += 1
+        if "AD" in r["fmt"] and "AD" in o["fmt"]:
+            old = [r["ref"]] + r["alt"]
+            new = [o["ref"]] + [a for a in o["alt"] if a != "."]
+            if len(new) == len(old):
+                continue
+            als_map = [new.index(a) if a in new else -1 for a in old]
+            k, ko = r["fmt"].index("AD"), o["fmt"].index("AD")
+            rows = [s[k].split(",") for s in r["smpl"]]
+            if any(len(x) != len(old) or "." in x for x in rows):
+                continue
+            got = driver.trim_numberR(np.array(rows, np.int32), als_map, len(new))
+            assert [",".join(map(str, g)) for g in got.tolist()] == [s[ko] for s in o["smpl"]], o["pos"]
+            n_ad += 1
+    assert n_dp4 >= 1 and (n_ad >= 1 or vcf.startswith("mpileup.") and "hwe" not in vcf)
