@@ -116,6 +116,44 @@ b200_ploidy_t *b200_ploidy_init_string(const char *str, int dflt)
     return p;
 }
 
+/*  The assemblies' sex-chromosome layout: first PAR end, second non-PAR start, X length, Y length, MT length.  Males are
+ *  haploid on X outside the PARs, on Y and on MT; females have no Y and one MT (vcfcall.c:138-175).  */
+typedef struct { const char *alias; long par1_end, nonpar_beg, x_len, y_len, mt_len; } assembly_t;
+static const assembly_t assemblies[] =
+{
+    { "GRCh37", 60000, 2699521, 154931043, 59373566, 16569 },
+    { "GRCh38",  9999, 2781480, 155701381, 57227415, 16569 },
+};
+
+static int same_nocase(const char *a, const char *b)
+{
+    while ( *a && *b && tolower((unsigned char)*a)==tolower((unsigned char)*b) ) { a++; b++; }
+    return !*a && !*b;
+}
+
+b200_ploidy_t *b200_ploidy_init_alias(const char *alias)
+{
+    char buf[1024];
+    for (size_t k=0; k<sizeof assemblies/sizeof assemblies[0]; k++)
+    {
+        const assembly_t *a = assemblies + k;
+        if ( !same_nocase(alias, a->alias) ) continue;
+        size_t n = 0;
+        const char *pre[2] = { "", "chr" }, *mt[2] = { "MT", "M" };
+        for (int v=0; v<2; v++)
+            n += (size_t) snprintf(buf+n, sizeof buf - n,
+                     "%sX 1 %ld M 1\n%sX %ld %ld M 1\n%sY 1 %ld M 1\n%sY 1 %ld F 0\n%s%s 1 %ld M 1\n%s%s 1 %ld F 1\n",
+                     pre[v], a->par1_end, pre[v], a->nonpar_beg, a->x_len, pre[v], a->y_len, pre[v], a->y_len,
+                     pre[v], mt[v], a->mt_len, pre[v], mt[v], a->mt_len);
+        snprintf(buf+n, sizeof buf - n, "* * * M 2\n* * * F 2\n");
+        return b200_ploidy_init_string(buf, 2);
+    }
+    if ( same_nocase(alias, "X") ) return b200_ploidy_init_string("* * * M 1\n* * * F 2\n", 2);
+    if ( same_nocase(alias, "Y") ) return b200_ploidy_init_string("* * * M 1\n* * * F 0\n", 2);
+    if ( same_nocase(alias, "1") ) return b200_ploidy_init_string("* * * * 1\n", 2);
+    return NULL;
+}
+
 void b200_ploidy_destroy(b200_ploidy_t *p)
 {
     if ( !p ) return;

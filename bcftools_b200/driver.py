@@ -5,7 +5,7 @@ import numpy as np
 
 from . import mcall
 
-DRIVER_EXPORTS = ["b200_ploidy_init_string", "b200_ploidy_destroy", "b200_ploidy_add_sex", "b200_ploidy_nsex", "b200_ploidy_sex2id",
+DRIVER_EXPORTS = ["b200_ploidy_init_string", "b200_ploidy_init_alias", "b200_ploidy_destroy", "b200_ploidy_add_sex", "b200_ploidy_nsex", "b200_ploidy_sex2id",
                   "b200_ploidy_id2sex", "b200_ploidy_min", "b200_ploidy_max", "b200_ploidy_query", "b200_set_ploidy",
                   "b200_groups_parse", "b200_unseen_allele", "b200_samples_parse", "b200_samples_default",
                   "b200_trim_numberR", "b200_i16_to_dp4_mq"]
@@ -20,6 +20,8 @@ def _lib():
     if not getattr(L, "_drv_ready", False):
         L.b200_ploidy_init_string.argtypes = [C.c_char_p, C.c_int]
         L.b200_ploidy_init_string.restype = C.c_void_p
+        L.b200_ploidy_init_alias.argtypes = [C.c_char_p]
+        L.b200_ploidy_init_alias.restype = C.c_void_p
         L.b200_ploidy_destroy.argtypes = [C.c_void_p]
         L.b200_ploidy_destroy.restype = None
         L.b200_ploidy_add_sex.argtypes = [C.c_void_p, C.c_char_p]
@@ -47,7 +49,12 @@ def _lib():
 class Ploidy:
     """ploidy_t of ploidy.c: definitions "CHROM FROM TO SEX PLOIDY" and per-position queries."""
 
-    def __init__(self, text, dflt=2):
+    def __init__(self, text=None, dflt=2, alias=None):
+        if alias is not None:
+            self._p = _lib().b200_ploidy_init_alias(alias.encode())
+            if not self._p:
+                raise DriverError("no such ploidy alias: %s" % alias)
+            return
         self._p = _lib().b200_ploidy_init_string(text.encode(), dflt)
         if not self._p:
             raise DriverError("could not parse the ploidy definition")

@@ -30,6 +30,10 @@ typedef struct b200_ploidy b200_ploidy_t;
 /*  ploidy_init_string (ploidy.c:154-181): lines "CHROM FROM TO SEX PLOIDY", 1-based inclusive coordinates; CHROM "*" sets the
  *  default of a sex, SEX "*" the default of everything else; `dflt` applies where nothing is given.  NULL on a parse error.  */
 b200_ploidy_t *b200_ploidy_init_string(const char *str, int dflt);
+/*  --ploidy <alias> (init_ploidy, vcfcall.c:138-198, 827-861; case-insensitive): GRCh37, GRCh38 (sex chromosomes and MT of the
+ *  two assemblies, with and without the "chr" prefix), X (males haploid), Y (males haploid, females absent), 1 (all haploid).
+ *  NULL for an unknown alias.  */
+b200_ploidy_t *b200_ploidy_init_alias(const char *alias);
 void b200_ploidy_destroy(b200_ploidy_t *p);
 int  b200_ploidy_add_sex(b200_ploidy_t *p, const char *sex);               /* ploidy.c:247-257: id of the sex, added with the default ploidy */
 int  b200_ploidy_nsex(const b200_ploidy_t *p);

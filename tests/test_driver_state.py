@@ -213,3 +213,42 @@ def test_finaliser_pieces_against_the_reference_outputs(vcf, out):
             assert [",".join(map(str, g)) for g in got.tolist()] == [s[ko] for s in o["smpl"]], o["pos"]
             n_ad += 1
     assert n_dp4 >= 1 and (n_ad >= 1 or vcf.startswith("mpileup.") and "hwe" not in vcf)
+
+
+def test_ploidy_aliases():
+    g38 = driver.Ploidy(alias="grch38")                         # case-insensitive (vcfcall.c:834)
+    assert g38.sexes == ["M", "F"] and (g38.min(), g38.max()) == (0, 2)
+    assert g38.query("chrX", 9998)[1] == {"M": 1, "F": 2} and g38.query("chrX", 9999)[1] == {"M": 2, "F": 2}       # PAR1 starts behind 9,999
+    assert g38.query("X", 2781479)[1] == {"M": 1, "F": 2} and g38.query("X", 2781478)[1] == {"M": 2, "F": 2}
+    assert g38.query("chrY", 5)[1] == {"M": 1, "F": 0} and g38.query("chrM", 5)[1] == {"M": 1, "F": 1} and g38.query("MT", 5)[1] == {"M": 1, "F": 1}
+    assert g38.query("chr1", 5)[1] == {"M": 2, "F": 2}
+    g37 = driver.Ploidy(alias="GRCh37")
+    assert g37.query("X", 59999)[1] == {"M": 1, "F": 2} and g37.query("X", 60000)[1] == {"M": 2, "F": 2} and g37.query("X", 2699520)[1]["M"] == 1
+    assert driver.Ploidy(alias="X").query("7", 1)[1] == {"M": 1, "F": 2}
+    assert driver.Ploidy(alias="Y").query("7", 1)[1] == {"M": 1, "F": 0}
+    assert driver.Ploidy(alias="1").query("7", 1)[1] == {"*": 1}
+    with pytest.raises(driver.DriverError):
+        driver.Ploidy(alias="hg18")
+
+
+def test_ploidy_aliases_against_the_reference_source():
+    """Every preset of vcfcall.c:138-198, parsed out of the reference source where the tree is present, answers the same
+    per-sex ploidies as the alias on a grid of positions around all of its region boundaries."""
+    src = "/root/reference/vcfcall.c"
+    if not os.path.exists(src):
+        pytest.skip("reference tree not present")
+    text = open(src).read()
+    n = 0
+    for m in re.finditer(r'\.alias\s*=\s*"([^"]+)".*?\.ploidy\s*=\s*((?:\s*"[^"]*"\s*)+)', text, flags=re.S):
+        alias, body = m.group(1), "".join(re.findall(r'"([^"]*)"', m.group(2))).replace("\\n", "\n")
+        ref, mine = driver.Ploidy(body, 2), driver.Ploidy(alias=alias)
+        assert ref.sexes == mine.sexes, alias
+        probes = [("7", 100)]
+        for l in body.splitlines():
+            c = l.split()
+            if c and c[0] != "*":
+                probes += [(c[0], int(x) + d) for x in c[1:3] for d in (-2, -1, 0, 1)]
+        for seq, pos in probes:
+            assert ref.query(seq, max(0, pos)) == mine.query(seq, max(0, pos)), (alias, seq, pos)
+        n += 1
+    assert n == 5
