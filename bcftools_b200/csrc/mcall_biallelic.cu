@@ -41,6 +41,9 @@ namespace mcb {
 #ifndef BW_PF_DIST
 #define BW_PF_DIST   4                  /* L2 prefetch distance of phase 1, in 128-sample iterations */
 #endif
+#ifndef BW_PF_L1
+#define BW_PF_L1     0                  /* 1: the next iteration's 12 lines are also prefetched into L1 (measured: see DESIGN.md 4a) */
+#endif
 #define BW_REC_BYTES 384                /* per-warp site record in shared memory */
 
 struct BWRec                            /* written by lane 0 after phase 1, read by the whole warp */
@@ -206,6 +209,7 @@ __device__ __forceinline__ void stg32(void *p, int x)
 __device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ uint32_t ldsu32(uint32_t a) { uint32_t v; asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
 __device__ __forceinline__ uint32_t ldsu8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ uint32_t byte_of(uint32_t w, int k) { return (w >> (8*k)) & 0xffu; }
 
@@ -346,6 +350,9 @@ __global__ void __launch_bounds__(BW_MAXWARP*32, BW_MINCTA) mcall_biallelic_warp
         {
             const int g = it*32 + lane;
             if ( lane < 12 && pf < site_end ) prefetch_l2(pf);      /* 12 lines of 128 bytes = the 128 samples of iteration it+BW_PF_DIST */
+#if BW_PF_L1
+            if ( lane < 12 && pf - (BW_PF_DIST-1)*1536 < site_end ) prefetch_l1(pf - (BW_PF_DIST-1)*1536);     /* iteration it+1 into L1 */
+#endif
             pf += 1536;
             int4 v0, v1, v2;
             load_group(g, v0, v1, v2);
