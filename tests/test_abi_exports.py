@@ -60,3 +60,48 @@ def test_error_strings():
     L = mcall.lib()
     assert b"CPU fallback" in L.mcb_strerror(-4)
     assert L.mcb_strerror(0) == b"ok"
+
+
+def test_headers_are_plain_c99(tmp_path):
+    """The boundary is a C ABI: every header under include/ must compile as C99 on its own (no C++-isms, no torch types)
+    and a driver written against all of them must type-check."""
+    import shutil
+    import subprocess
+    if not shutil.which("gcc"):
+        pytest.skip("no gcc")
+    inc = os.path.join(ROOT, "include")
+    hdrs = sorted(h for h in os.listdir(inc) if h.endswith(".h"))
+    assert {"mcall_b200.h", "b200_call.h", "b200_bcf.h", "b200_driver.h"} <= set(hdrs)
+    for h in hdrs:
+        src = tmp_path / ("only_" + h.replace(".h", ".c"))
+        src.write_text('#include "%s"\nint main(void) { return 0; }\n' % h)
+        subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-fsyntax-only", "-I", inc, str(src)], check=True)
+    prog = tmp_path / "driver.c"
+    prog.write_text('''
+#include <string.h>
+#include "mcall_b200.h"
+#include "b200_call.h"
+#include "b200_bcf.h"
+#include "b200_driver.h"
+int run(const char *const *alleles, int n_allele, const uint8_t *indiv, size_t len, int nsmpl)
+{
+    b200_ploidy_t *pl = b200_ploidy_init_alias("GRCh38");
+    int prev[8], s2s[4] = {0,1,0,1}; uint8_t ploidy[4];
+    b200_call_t call; memset(&call, 0, sizeof call);
+    call.nsmpl = nsmpl; call.bcf_typed = 1; call.ploidy = ploidy;
+    b200_set_ploidy(pl, "chrX", 5000000, s2s, 4, prev, ploidy);
+    call.unseen = (uint8_t) b200_unseen_allele(alleles, n_allele);
+    b200_bcf_fmt_t fmt[4];
+    if ( b200_bcf_unpack_fmt(indiv, len, 1, nsmpl, fmt) ) return -1;
+    b200_rec_t rec; memset(&rec, 0, sizeof rec);
+    rec.n_allele = n_allele; rec.PL_typed = fmt[0].p; rec.PL_bt = fmt[0].type; rec.nPLs = fmt[0].n*nsmpl;
+    b200_mcall_init(&call);
+    int ready = b200_mcall(&call, &rec);
+    b200_out_t out;
+    if ( ready ) b200_mcall_result(&call, 0, &out);
+    b200_mcall_destroy(&call);
+    b200_ploidy_destroy(pl);
+    return mcb_version();
+}
+''')
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-I", inc, str(prog)], check=True)
