@@ -19,9 +19,9 @@
 using namespace mcb;
 
 #define NCLASS 6                /* allele-count classes 1..5 + class 0 = everything else */
-#define NCOUNTS (NCLASS+24)     /* class counts | +NCLASS: work counters | +NCLASS+8: pair-list counts | +NCLASS+16: pair work counters */
-/*  one allocation per batch/slab: NCLASS class lists, NCLASS pair lists (sites handed to the pair kernel), one PairRec per site  */
-static inline size_t lists_bytes(int cap) { return sizeof(int32_t)*(size_t)(2*NCLASS)*cap + sizeof(mcb::PairRec)*(size_t)cap; }
+#define NCOUNTS (NCLASS+24)     /* class counts | +NCLASS: work counters | +NCLASS+8: fallback-list counts | +NCLASS+16: fallback work counters */
+/*  one allocation per batch/slab: NCLASS class lists, NCLASS fallback lists (sites the multi-allelic kernel hands to the general one)  */
+static inline size_t lists_bytes(int cap) { return sizeof(int32_t)*(size_t)(2*NCLASS)*cap; }
 #define MAX_STAGE 16
 
 #define NSLAB 3
@@ -58,7 +58,10 @@ struct mcb_ctx
     HostSlab slab[NSLAB];
     /* options */
     int64_t opt_tile_bytes = 0, opt_ring_bytes = 0, opt_blocks_per_sm = 0, opt_slab_bytes = 64ll<<20, opt_slab_min = 8ll<<20, opt_block = 0;     /* 0 = automatic */
-    int64_t opt_defer2 = 0;              /* pair sites of the 3-5 allele classes: phase 2 in the warp-per-site pair kernel (0: stays fused) */
+    int64_t opt_multi = 1;               /* 3-5 allele classes: the CTA-per-site kernel of mcall_multi.cu (0: the general tiled kernel) */
+    int64_t opt_mm_nst = 0;              /* its ring stages per warp (0 = automatic) */
+    int64_t opt_mm_nst_c[NCLASS] = {0,0,0,0,0,0};       /* ... per allele-count class */
+    int64_t opt_mm_block = 0;            /* its CTA size (0 = by sample count) */
     int64_t opt_warp2 = -1;              /* biallelic warp-per-site kernel: -1 automatic, 0 off, n = force n warps per CTA */
     int64_t opt_order = 54321;           /* launch order of the allele-count classes */
     int64_t opt_time_kernels = 0, opt_concurrent = 1;    /* class kernels on their own streams: a class fills the tail of the previous one (-3.5 % per C3 step) */
@@ -160,7 +163,10 @@ extern "C" int mcb_set_option(mcb_ctx *ctx, const char *key, int64_t value)
     else if ( !strcmp(key,"time_kernels") )  ctx->opt_time_kernels = value;
     else if ( !strcmp(key,"concurrent") )    ctx->opt_concurrent = value;
     else if ( !strcmp(key,"order") )         ctx->opt_order = value;
-    else if ( !strcmp(key,"defer2") )        ctx->opt_defer2 = value;
+    else if ( !strcmp(key,"multi") )         ctx->opt_multi = value;
+    else if ( !strcmp(key,"mm_nst") )        { if ( value<0 || value>4 ) return MCB_EINVAL; ctx->opt_mm_nst = value; }
+    else if ( !strncmp(key,"mm_nst_",7) && key[7]>='3' && key[7]<='5' && !key[8] ) { if ( value<0 || value>4 ) return MCB_EINVAL; ctx->opt_mm_nst_c[key[7]-'0'] = value; }
+    else if ( !strcmp(key,"mm_block") )      { if ( value!=0 && value!=128 && value!=256 && value!=512 ) return MCB_EINVAL; ctx->opt_mm_block = value; }
     else if ( !strcmp(key,"warp2") )         { if ( value<-1 || value>biallelic_max_warps() ) return MCB_EINVAL; ctx->opt_warp2 = value; }
     else if ( !strncmp(key,"ring_bytes_",11) && key[11]>='1' && key[11]<='5' && !key[12] ) ctx->opt_ring_bytes_c[key[11]-'0'] = value;
     else if ( !strncmp(key,"block_",6) && key[6]>='1' && key[6]<='5' && !key[7] )
@@ -536,14 +542,50 @@ static int enqueue(mcb_ctx *ctx, const mcb_batch *b, const mcb_result *r, int32_
         int grid = (int)std::min<int64_t>((int64_t)b->nsites, (int64_t)ctx->nsm*nb);
         cudaStream_t cs = fork ? ctx->cstream[nals] : st;
         if ( fork ) CK(cudaStreamWaitEvent(cs, ctx->cev_fork, 0));
-        /* pair sites (selected set = kept alleles = a pair) leave the fused kernel after phase 1: mcall_pair.cu */
-        const bool defer2 = ctx->opt_defer2 && nals>=3 && !ploidy && !gpk && pl_es==4 && !(a.nsmpl & 1) && a.gt && a.gq && a.out_pl;
-        a.pair_rec = defer2 ? reinterpret_cast<PairRec*>(lists + (size_t)(2*NCLASS)*list_stride) : nullptr;
-        a.pair_list = lists + (size_t)(NCLASS + nals)*list_stride;
-        a.pair_count = counts + NCLASS + 8 + nals; a.pair_work = counts + NCLASS + 16 + nals;
+        /*  3-5 alleles, int32 PLs, every sample diploid, GT + GQ + PL requested: the CTA-per-site kernel of mcall_multi.cu.
+         *  Sites it has no straight-line code for come back on a fallback list, which the general kernel below walks.  */
+        bool multi = false;
+        if ( nals>=3 && ctx->opt_multi && !ctx->opt_block && !ctx->opt_block_c[nals] && pl_es==4 && !ploidy && !gpk && a.gt && a.gq && a.out_pl && !(a.flag & MCB_CALL_KEEPALT)
+             && (a.output_tags & (MCB_CALL_FMT_GQ|MCB_CALL_FMT_GP))
+             && !((reinterpret_cast<uintptr_t>(a.gt) | reinterpret_cast<uintptr_t>(a.gq) | reinterpret_cast<uintptr_t>(a.out_pl)) & 15) )
+        {
+            int mblock = ctx->opt_mm_block ? (int)ctx->opt_mm_block : multi_block_for(a.nsmpl);
+            if ( mblock && (a.nsmpl & 1) ) mblock = 0;
+            if ( mblock && (a.nsmpl + 1)/2 > 5*mblock ) mblock = 0;         /* more than 10 samples per thread: out of range */
+            int nst = ctx->opt_mm_nst_c[nals] ? (int)ctx->opt_mm_nst_c[nals] : (ctx->opt_mm_nst ? (int)ctx->opt_mm_nst : (nals==3 ? 3 : 2));
+            const size_t cap = 227u*1024u;
+            while ( mblock && nst>1 && multi_smem_bytes(nals, mblock, a.nsmpl, nst) > cap ) nst--;
+            if ( mblock && multi_smem_bytes(nals, mblock, a.nsmpl, nst) <= cap )
+            {
+                int mnb = 0;
+                CK(multi_kernel_occupancy(nals, mblock, a.nsmpl, nst, &mnb));
+                if ( mnb >= 1 )
+                {
+                    if ( ctx->opt_bps_c[nals]>0 ) mnb = std::min<int>(mnb, (int)ctx->opt_bps_c[nals]);
+                    KArgs am = a;
+                    am.nstage = nst;
+                    am.fb_list = lists + (size_t)(NCLASS + nals)*list_stride;
+                    am.fb_count = counts + NCLASS + 8 + nals;
+                    const int mgrid = (int)std::min<int64_t>((int64_t)b->nsites, (int64_t)ctx->nsm*mnb);
+                    cudaError_t le = launch_multi_kernel(nals, mblock, am, mgrid, cs);
+                    if ( le==cudaSuccess && getenv("MCB_DEBUG_SYNC") ) le = cudaStreamSynchronize(cs);
+                    if ( le!=cudaSuccess )
+                    {
+                        char what[160];
+                        snprintf(what, sizeof what, "multi-allelic kernel nals=%d block=%d grid=%d nst=%d smem=%zu", nals, mblock, mgrid, nst, multi_smem_bytes(nals, mblock, a.nsmpl, nst));
+                        return cuda_fail(ctx, le, what);
+                    }
+                    launches++;
+                    multi = true;
+                    /* the general kernel now walks the fallback list only */
+                    a.site_list = am.fb_list; a.site_count = am.fb_count;
+                    a.work_counter = counts + NCLASS + 16 + nals;
+                    grid = std::min(grid, ctx->nsm);
+                }
+            }
+        }
         {
             cudaError_t le = launch_site_kernel(nals, ploidy, gpk, block, pl_es, a, grid, ring, cs);
-            if ( le==cudaSuccess && defer2 ) { le = launch_pair_kernel(nals, a, ctx->nsm, cs); launches++; }
             if ( le==cudaSuccess && getenv("MCB_DEBUG_SYNC") ) le = cudaStreamSynchronize(cs);
             if ( le!=cudaSuccess )
             {

@@ -14,7 +14,7 @@
 #define MCB_FAST2_N2 1      /* the same path in the two-allele instances of this kernel (int32 PLs, S > 8,192: the biobank shape) */
 #endif
 #ifndef MCB_FAST2
-#define MCB_FAST2 0         /* 1: straight-line phase 2 for pair sites INSIDE this kernel (measured: slower, see below; the pair kernel does it) */
+#define MCB_FAST2 0         /* 1: straight-line phase 2 for pair sites INSIDE the 3-5 allele instances (measured slower: instruction fetch; mcall_multi.cu is the fast path of those classes) */
 #endif
 
 namespace mcb {
@@ -749,34 +749,6 @@ __global__ void __launch_bounds__(BLOCK, (MinBlocks<NALS,BLOCK>::value)) mcall_s
             const bool pair_site = PAIR_OK && !ref_gt && nsel==2 && (inc_dip & 7u)==7u && nals_new==2 && sh.als_new==sh.grp_als && want_gq
                                && oflags==7u && !(nsmpl & 1)
                                && !((reinterpret_cast<uintptr_t>(out_gt) & 15) | (reinterpret_cast<uintptr_t>(out_gq) & 7) | (reinterpret_cast<uintptr_t>(out_pl) & 7));
-            /*  Pair sites leave the fused kernel here when the caller provided the hand-over buffers: their phase 2 runs in the
-             *  warp-per-site pair kernel (mcall_pair.cu), whose small straight-line loop does not compete with the general
-             *  phase-2 code below for instruction fetch (inside this kernel the same fast path made every class 10-19 % SLOWER:
-             *  the stall reason that grew is no_instruction).  */
-            if constexpr ( PAIR_OK && NALS>=3 ) if ( pair_site && a.pair_rec )
-            {
-                if ( tid==0 )
-                {
-                    PairRec pr;
-                    pr.q0 = q0; pr.q1 = q1; pr.max_qual = sh.max_qual; pr.lk_sum = sh.lk_sum; pr.ref_lk = sh.ref_lk; pr.gap = sh.gap;
-                    pr.out_off = sh.out_off; pr.flags = sh.flags; pr.als_new = sh.als_new;
-                    pr.g00 = jgt4[0]/ES; pr.g10 = jgt4[NSLOT>1 ? 1 : 0]/ES; pr.g11 = jgt4[NSLOT>2 ? 2 : 0]/ES; pr.nals_new = nals_new;
-                    #pragma unroll
-                    for (int j=0; j<8; j++) pr.als_map[j] = j<NALS ? (int8_t)sh.als_map[j] : (int8_t)-1;
-                    a.pair_rec[site] = pr;
-                    __threadfence();
-                    a.pair_list[atomicAdd(a.pair_count, 1)] = site;
-                }
-                if ( !resident )        /* drain the phase-2 tiles already in flight for this site */
-                    for (int v=ntiles; v<ntiles+nstage && v<total_visits; v++)
-                    {
-                        const int stage = v % nstage;
-                        mbar_wait(bars_s + 8*stage, (phase_bits>>stage)&1u);
-                        phase_bits ^= 1u<<stage;
-                    }
-                __syncthreads();
-                continue;
-            }
             /* two-allele instances: measured +16 % at 100,000 samples (C4), -4..-9 % at 1,000-2,504 (where the warp kernel of
                mcall_biallelic.cu is the default path anyway) */
             const bool fast2 = FAST2 && pair_site && !(TS & 1) && (MCB_FAST2 || nsmpl > 8192);

@@ -40,19 +40,6 @@ struct DevTables
     double pl2p_big[MCB_PL2P_BIG];  /* same function for PL >= 256 (mcall.c:472), rare path, read from global */
 };
 
-/*  Site record handed from the fused kernel to the pair kernel (mcall_pair.cu): everything phase 2 and the site
- *  epilogue need once phase 1 decided that the selected allele set is a pair s0<s1 whose alleles are exactly the kept ones.  */
-struct PairRec
-{
-    double q0, q1;                      /* (double)qsum of s0, s1 (mcall.c:797, 820) */
-    double max_qual, lk_sum, ref_lk, gap;
-    long long out_off;                  /* where the site's trimmed PL block goes */
-    uint32_t flags, als_new;
-    int    g00, g10, g11;               /* genotype indices of (s0,s0), (s1,s0), (s1,s1) in the ORIGINAL PL vector */
-    int    nals_new;
-    int8_t als_map[8];
-};
-
 struct KArgs
 {
     /* batch (device pointers) */
@@ -70,8 +57,8 @@ struct KArgs
     const uint32_t *grp_off;  const uint32_t *grp_smpl;  const uint32_t *smpl2grp;  int ngroups;
     const int32_t *site_list;  const int32_t *site_count;      /* the sites of this allele-count class */
     int32_t *work_counter;                                      /* next unclaimed entry of site_list (warp-per-site kernel) */
-    /* pair sites deferred by the fused kernel to the pair kernel (NULL: phase 2 stays fused) */
-    PairRec *pair_rec;  int32_t *pair_list;  int32_t *pair_count;  int32_t *pair_work;
+    /* sites the multi-allelic kernel (mcall_multi.cu) hands back to the general tiled kernel */
+    int32_t *fb_list;  int32_t *fb_count;
     int nsmpl, max_nals;
     uint32_t flag, output_tags;
     double theta, tie_eps;
@@ -96,7 +83,10 @@ size_t biallelic_smem_bytes(int nsmpl, int nwarp);
 int biallelic_max_warps();
 int biallelic_ctas_per_sm();
 cudaError_t launch_biallelic_warp_kernel(const KArgs &a, bool ploidy, int grid, int nwarp, cudaStream_t st);
-/*  warp-per-site phase 2 for the pair sites of the 3-5 allele classes (mcall_pair.cu)  */
-cudaError_t launch_pair_kernel(int nals, const KArgs &a, int nsm, cudaStream_t st);
+/*  CTA-per-site kernel of the 3-5 allele classes over a byte-packed shared-memory copy (mcall_multi.cu)  */
+int multi_block_for(int nsmpl);
+size_t multi_smem_bytes(int nals, int block, int nsmpl, int nst);
+cudaError_t multi_kernel_occupancy(int nals, int block, int nsmpl, int nst, int *blocks_per_sm);
+cudaError_t launch_multi_kernel(int nals, int block, const KArgs &a, int grid, cudaStream_t st);
 cudaError_t launch_selftest_div(const DevTables *tab, int mode, unsigned long long n, unsigned long long seed, unsigned long long *mismatch, cudaStream_t st);
 }

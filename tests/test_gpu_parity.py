@@ -11,11 +11,18 @@ pytestmark = pytest.mark.gpu
 BLOCKS = (0, 256, 128, 64, 32)      # 0 = the automatic per-class choice
 
 
-def _run(params, batch, tab, oracle_built, options=None, kind="port"):
-    """Runs the CUDA path with both CTA sizes and compares each against the oracle."""
+def ORACLE(pyoracle):
+    """The checker: the reference's own mcall.c compiled in place (oracle/_ref, ships to the GPU box); the plain-C port
+    only where that library is missing."""
+    return "reference" if pyoracle.have_ref() else "port"
+
+
+def _run(params, batch, tab, oracle_built, options=None, kind=None):
+    """Runs the CUDA path with every CTA size (0 = automatic: the class kernels of mcall_biallelic.cu / mcall_multi.cu where
+    they apply; an explicit size = the general tiled kernel) and compares each against the oracle."""
     from bcftools_b200 import mcall
     want_gp = bool(params.output_tags & abi.CALL_FMT_GP)
-    exp, _ = oracle_built.call(kind, params, batch, tab, want_gp=want_gp)
+    exp, _ = oracle_built.call(kind or ORACLE(oracle_built), params, batch, tab, want_gp=want_gp)
     st = None
     for block in BLOCKS:
         opts = dict(options or {})
@@ -53,7 +60,7 @@ def test_gp_output(S, maxA, oracle_built):
     tab[1, 1::7] = 0
     batch.ploidy_id = rng.integers(0, 2, batch.nsites).astype(np.uint16)
     params = abi.CallParams(S, maxA, output_tags=abi.CALL_FMT_GQ | abi.CALL_FMT_GP)
-    st = _run(params, batch, tab, oracle_built)
+    st = _run(params, batch, tab, oracle_built, kind="port")    # the compiled reference aborts on these inputs (assert(max), mcall.c:881)
     assert st["compared"] > 0, st
 
 
@@ -85,13 +92,13 @@ def test_two_allele_kernel_under_ploidy_vectors(S, flag, oracle_built):
     tab[2, 1::5] = 0
     batch.ploidy_id = rng.integers(0, 3, batch.nsites).astype(np.uint16)
     params = abi.CallParams(S, 2, flag=flag, output_tags=abi.CALL_FMT_GQ)
-    exp, _ = oracle_built.call("port", params, batch, tab)
+    exp, _ = oracle_built.call(ORACLE(oracle_built), params, batch, tab)
     with mcall.MCaller(params, ploidy_tab=tab) as mc:
         got = mc.call_host(batch, compact=True)
     assert parity.compare(got, exp, params)["compared"] > 0
     if S == 2504:       # the C5 shape, pooled: every 2nd sample haploid
         p5, b5, t5 = synth.make_batch("C5", 200, with_groups=0)
-        e5, _ = oracle_built.call("port", p5, b5, t5)
+        e5, _ = oracle_built.call(ORACLE(oracle_built), p5, b5, t5)
         with mcall.MCaller(p5, ploidy_tab=t5) as mc:
             g5 = mc.call_host(b5)
         st = parity.compare(g5, e5, p5)
@@ -136,7 +143,7 @@ def test_more_than_five_alleles(S, maxA, groups, flag, tags, oracle_built):
     tab[1, 1::7] = 0
     batch.ploidy_id = rng.integers(0, 2, batch.nsites).astype(np.uint16)
     params = abi.CallParams(S, maxA, flag=flag, output_tags=tags, groups=g)
-    st = _run(params, batch, tab, oracle_built)
+    st = _run(params, batch, tab, oracle_built, kind="port" if tags & abi.CALL_FMT_GP else None)   # GP: assert(max), mcall.c:881
     assert st["compared"] > 0 and (batch.nals > 5).sum() > 0, st
 
 
@@ -165,7 +172,7 @@ def test_tiled_two_allele_pair_path_above_8192_samples(flag, oracle_built):
     batch = parity.random_batch(rng, 24, S, 2, minA=2)
     params = abi.CallParams(S, 2, flag=flag, output_tags=abi.CALL_FMT_GQ)
     tab = np.full((1, S), 2, np.uint8)
-    exp, _ = oracle_built.call("port", params, batch, tab)
+    exp, _ = oracle_built.call(ORACLE(oracle_built), params, batch, tab)
     for opts in ({}, {"tile_bytes": 4096, "ring_bytes": 8192}):
         with mcall.MCaller(params, ploidy_tab=tab, options=opts) as mc:
             got = mc.call_host(batch, compact=True)
@@ -208,7 +215,7 @@ def test_int16_pl_transport(cfg, nsites, flag, oracle_built):
     (SURVEY.md 8f N1); results must equal the int32 path bit for bit, including missing values and the PL fill."""
     from bcftools_b200 import mcall
     params, batch, tab = synth.make_batch(cfg, nsites, flag=flag)
-    exp, _ = oracle_built.call("port", params, batch, tab)
+    exp, _ = oracle_built.call(ORACLE(oracle_built), params, batch, tab)
     b16 = batch.to_int16()
     with mcall.MCaller(params, ploidy_tab=tab) as mc:
         got = mc.call_host(b16, compact=True)
@@ -221,7 +228,7 @@ def test_int16_pl_transport(cfg, nsites, flag, oracle_built):
     tabr[1, 1::7] = 0
     rb.ploidy_id = rng.integers(0, 2, rb.nsites).astype(np.uint16)
     pr = abi.CallParams(40, 5, output_tags=abi.CALL_FMT_GQ)
-    expr, _ = oracle_built.call("port", pr, rb, tabr)
+    expr, _ = oracle_built.call(ORACLE(oracle_built), pr, rb, tabr)
     with mcall.MCaller(pr, ploidy_tab=tabr) as mc:
         gotr = mc.call_host(rb.to_int16())
     assert parity.compare(gotr, expr, pr)["compared"] > 0
@@ -242,7 +249,7 @@ def test_idle_warps_do_not_index_the_table_with_sentinels(int16, oracle_built):
     qs[:, :rb.qs.shape[1]] = rb.qs
     rb.qs = qs
     pr = abi.CallParams(40, 5, output_tags=abi.CALL_FMT_GQ)
-    exp, _ = oracle_built.call("port", pr, rb, None)
+    exp, _ = oracle_built.call(ORACLE(oracle_built), pr, rb, None)
     with mcall.MCaller(pr) as mc:
         got = mc.call_host(rb.to_int16() if int16 else rb)
     assert parity.compare(got, exp, pr)["compared"] > 0
@@ -266,7 +273,9 @@ def test_biallelic_warp_kernel(S, flag, oracle_built):
         blk[...] = rng.integers(0, 256, blk.shape)
         blk[np.arange(S), rng.integers(0, 3, S)] = 0
     params = abi.CallParams(S, 2, flag=flag, output_tags=abi.CALL_FMT_GQ)
-    exp, _ = oracle_built.call("port", params, batch, None)
+    # PL >= 256 inside a partially missing row indexes pl2p[] out of bounds in the reference (mcall.c:522): the port defines it
+    BW_ORACLE = "port" if S in (37, 131) else ORACLE(oracle_built)
+    exp, _ = oracle_built.call(BW_ORACLE, params, batch, None)
     for opts, compact in (({"warp2": 14}, False), ({"warp2": 3}, True), ({"warp2": 0}, False)):
         with mcall.MCaller(params, options=opts) as mc:
             got = mc.call_host(batch, compact=compact)
@@ -278,7 +287,7 @@ def test_biallelic_warp_kernel(S, flag, oracle_built):
     tab[2, ::3] = 1
     tab[2, 1::5] = 0
     batch.ploidy_id = rng.integers(0, 3, R).astype(np.uint16)
-    exp, _ = oracle_built.call("port", params, batch, tab)
+    exp, _ = oracle_built.call(BW_ORACLE, params, batch, tab)
     for opts, compact in (({"warp2": 14}, True), ({"warp2": 0}, False)):
         with mcall.MCaller(params, ploidy_tab=tab, options=opts) as mc:
             got = mc.call_host(batch, compact=compact)
@@ -291,7 +300,7 @@ def test_compacted_pl_output(oracle_built):
     the host path); content must be identical to the in-place layout, several slabs per call."""
     from bcftools_b200 import mcall
     params, batch, tab = synth.make_batch("C3", 200, flag=abi.CALL_VARONLY)
-    exp, _ = oracle_built.call("port", params, batch, tab)
+    exp, _ = oracle_built.call(ORACLE(oracle_built), params, batch, tab)
     with mcall.MCaller(params, ploidy_tab=tab, options={"slab_bytes": 4 << 20}) as mc:
         got = mc.call_host(batch, compact=True)
     st = parity.compare(got, exp, params)
@@ -312,7 +321,7 @@ def test_bcf_typed_outputs(compact, int16_in, oracle_built):
     widen back to exactly the int32 results (sentinels included: haploid vector_end, ploidy-0 missing), several slabs."""
     from bcftools_b200 import mcall
     params, batch, tab = synth.make_batch("C3", 160, flag=0)
-    exp, _ = oracle_built.call("port", params, batch, tab)
+    exp, _ = oracle_built.call(ORACLE(oracle_built), params, batch, tab)
     bin_ = batch.to_int16() if int16_in else batch
     with mcall.MCaller(params, ploidy_tab=tab, options={"slab_bytes": 4 << 20}) as mc:
         got = mc.call_host(bin_, compact=compact, typed=True)
@@ -326,32 +335,70 @@ def test_bcf_typed_outputs(compact, int16_in, oracle_built):
     tabr[1, 1::7] = 0
     rb.ploidy_id = rng.integers(0, 2, rb.nsites).astype(np.uint16)
     pr = abi.CallParams(37, 5, output_tags=abi.CALL_FMT_GQ)
-    expr, _ = oracle_built.call("port", pr, rb, tabr)
+    expr, _ = oracle_built.call(ORACLE(oracle_built), pr, rb, tabr)
     with mcall.MCaller(pr, ploidy_tab=tabr) as mc:
         gotr = mc.call_host(rb, compact=compact, typed=True)
     assert parity.compare(gotr.widen(), expr, pr)["compared"] > 0
 
 
-@pytest.mark.parametrize("S", [2, 64, 1000, 2504])
-def test_pair_kernel_option(S, oracle_built):
-    """defer2=1: pair sites of the 3-5 allele classes leave the fused kernel after phase 1 and are genotyped by the
-    CTA-per-site pair kernel (mcall_pair.cu); results must not change (missing values and PL >= 256 take its general path)."""
+@pytest.mark.parametrize("flag", [0, abi.CALL_VARONLY])
+@pytest.mark.parametrize("S", [256, 300, 1000, 1280, 1282, 2504, 2560, 4000])
+def test_multi_allelic_kernel(S, flag, oracle_built):
+    """The CTA-per-site kernel of the 3-5 allele classes (mcall_multi.cu): sample counts around its 64-sample warp tiles
+    and its three CTA sizes (128 / 256 / 512 threads), adversarial PLs -- missing and partially missing rows (the list
+    warp 0 evaluates), zero QS entries (dead allele sets), unseen alleles and PL >= 256 (sites handed back to the general
+    kernel through the fallback list) -- compacted and in-place PL output, every ring depth; compared with the oracle
+    and with the general tiled kernel."""
     from bcftools_b200 import mcall
-    rng = np.random.default_rng(S)
-    batch = parity.random_batch(rng, 90 if S > 500 else 200, S, 5)
-    params = abi.CallParams(S, 5, output_tags=abi.CALL_FMT_GQ)
-    tab = np.full((1, S), 2, np.uint8)
-    exp, _ = oracle_built.call("port", params, batch, tab)
-    with mcall.MCaller(params, ploidy_tab=tab, options={"defer2": 1}) as mc:
+    rng = np.random.default_rng([S, flag, 23])
+    R = 60 if S > 1500 else 120
+    batch = parity.random_batch(rng, R, S, 5, minA=3, pl_max=256)
+    for i in range(0, R, 5):            # PL >= 256 on some sites
+        blk = batch.site_pl(i)
+        blk[rng.integers(0, S, 3), rng.integers(0, blk.shape[1], 3)] = 300
+    for i in range(1, R, 4):            # clean sites: every pair on the fast path, every allele live
+        blk = batch.site_pl(i)
+        blk[...] = rng.integers(0, 256, blk.shape)
+        blk[np.arange(S), rng.integers(0, blk.shape[1], S)] = 0
+        batch.qs[i, :batch.nals[i]] = (1 + rng.random(int(batch.nals[i])) * 10).astype(np.float32)
+        batch.unseen[i] = 0
+    for i in range(2, R, 9):            # mpileup-shaped sites: most samples REF/REF, so that pairs and triples WITH the REF allele win
+        A = int(batch.nals[i]); blk = batch.site_pl(i)
+        truth = rng.choice(A, size=(S, 2), p=np.array([0.8] + [0.2 / (A - 1)] * (A - 1)))
+        k = 0
+        for x in range(A):
+            for y in range(x + 1):
+                m = ((truth[:, 0] == x) & (truth[:, 1] == y)) | ((truth[:, 0] == y) & (truth[:, 1] == x))
+                one = (truth == x).any(1) | (truth == y).any(1)
+                blk[:, k] = np.where(m, 0, np.where(one, 20 + rng.integers(0, 9, S), 200 + rng.integers(0, 50, S)))
+                k += 1
+        batch.qs[i, :A] = np.array([((truth == x).sum()) for x in range(A)], np.float32)
+        batch.unseen[i] = 0
+    params = abi.CallParams(S, 5, flag=flag, output_tags=abi.CALL_FMT_GQ)
+    exp, _ = oracle_built.call("port", params, batch, None)     # PL >= 256 next to missing values: undefined in the reference (mcall.c:522)
+    for opts, compact in (({}, False), ({"mm_nst": 1}, True), ({"mm_nst": 4}, False), ({"multi": 0}, True)):
+        with mcall.MCaller(params, options=opts) as mc:
+            got = mc.call_host(batch, compact=compact)
+        st = parity.compare(got, exp, params)
+        assert st["compared"] > 0, (opts, st)
+
+
+@pytest.mark.parametrize("cfg,nsites", [("C3", 2048)])
+def test_multi_allelic_kernel_on_the_bench_workload(cfg, nsites, oracle_built):
+    """2,048 sites of the C3 mix against the compiled reference; the multi-allelic classes must run mcall_multi.cu
+    (launch count) and hand only a small share of their sites back to the general kernel."""
+    from bcftools_b200 import mcall
+    params, batch, tab = synth.make_batch(cfg, nsites)
+    exp, _ = oracle_built.call(ORACLE(oracle_built), params, batch, tab)
+    with mcall.MCaller(params, ploidy_tab=tab) as mc:
         got = mc.call_host(batch, compact=True)
-    assert parity.compare(got, exp, params)["compared"] > 0
-    if S == 2504:
-        p3, b3, t3 = synth.make_batch("C3", 160)
-        e3, _ = oracle_built.call("port", p3, b3, t3)
-        with mcall.MCaller(p3, ploidy_tab=t3, options={"defer2": 1}) as mc:
-            g3 = mc.call_host(b3)
-            assert int(mc.stats()[0]) > 7        # the pair kernels were launched
-        assert parity.compare(g3, e3, p3)["compared"] > 0
+        n_multi = int(mc.stats()[0])
+    with mcall.MCaller(params, ploidy_tab=tab, options={"multi": 0}) as mc:
+        mc.call_host(batch, compact=True)
+        n_old = int(mc.stats()[0])
+    assert n_multi > n_old                   # three more launches per slab: the multi-allelic kernels
+    st = parity.compare(got, exp, params)
+    assert st["compared"] > 0 and not st["near_ties"], st
 
 
 def test_empty_batch():
