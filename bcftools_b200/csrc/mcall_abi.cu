@@ -24,6 +24,21 @@ using namespace mcb;
 static inline size_t lists_bytes(int cap) { return sizeof(int32_t)*(size_t)(2*NCLASS)*cap; }
 #define MAX_STAGE 16
 
+/*  Scratch of the grouped (-G) and generic (6..32 allele) kernels, indexed by blockIdx inside a launch.  One set per host
+ *  slab and one for the device path: slabs run on independent streams, so their launches may overlap and must not share it.  */
+struct KernelScratch
+{
+    void *grp = nullptr;  size_t grp_bytes = 0;
+    void *gen_grp = nullptr, *gen_pl = nullptr, *gen_sum = nullptr;  int gen_grid = 0;
+    double *mm_sums[6] = {};  size_t mm_sums_bytes[6] = {};     /* mcall_multi.cu: per-CTA rows of normalisers, one buffer per allele-count class (the classes run concurrently) */
+};
+static void free_scratch(KernelScratch &k)
+{
+    cudaFree(k.grp); cudaFree(k.gen_grp); cudaFree(k.gen_pl); cudaFree(k.gen_sum);
+    for (int i=0; i<6; i++) cudaFree(k.mm_sums[i]);
+    k = KernelScratch();
+}
+
 #define NSLAB 3
 struct HostSlab                 /* one stage of the host-path ring (H2D of slab k+1 overlaps kernels and D2H of slab k) */
 {
@@ -38,6 +53,7 @@ struct HostSlab                 /* one stage of the host-path ring (H2D of slab 
     int32_t *lists = nullptr, *counts = nullptr;  int list_cap = 0;
     unsigned long long *cursor = nullptr;           /* device: compacted-PL allocation cursor (int32 units) */
     unsigned long long *h_cursor = nullptr;         /* pinned host copy */
+    KernelScratch scratch;
 };
 
 struct mcb_ctx
@@ -50,8 +66,7 @@ struct mcb_ctx
     uint8_t  *d_ploidy = nullptr;  int nploidy = 0, ploidy_cap = 0;  bool any_nondiploid = false;
     std::vector<uint8_t> h_ploidy;
     uint32_t *d_grp_off = nullptr, *d_grp_smpl = nullptr, *d_smpl2grp = nullptr;  int ngroups = 1;
-    void *d_grp_scratch = nullptr;  size_t grp_scratch_bytes = 0;
-    void *d_gen_grp = nullptr, *d_gen_pl = nullptr, *d_gen_sum = nullptr;  int gen_grid = 0;    /* generic (6..32 allele) kernel scratch */
+    KernelScratch scratch;              /* device path (mcb_call_device) */
     /* device-path scratch */
     int32_t *d_lists = nullptr, *d_counts = nullptr;  int list_cap = 0;
     unsigned long long *d_cursor = nullptr;
@@ -61,7 +76,8 @@ struct mcb_ctx
     int64_t opt_multi = 1;               /* 3-5 allele classes: the CTA-per-site kernel of mcall_multi.cu (0: the general tiled kernel) */
     int64_t opt_mm_nst = 0;              /* its ring stages per warp (0 = automatic) */
     int64_t opt_mm_nst_c[NCLASS] = {0,0,0,0,0,0};       /* ... per allele-count class */
-    int64_t opt_mm_block = 0;            /* its CTA size (0 = by sample count) */
+    int64_t opt_mm_block = 0;            /* its CTA size (0 = automatic) */
+    int64_t opt_mm_block_c[NCLASS] = {0,0,0,0,0,0};     /* ... per allele-count class */
     int64_t opt_warp2 = -1;              /* biallelic warp-per-site kernel: -1 automatic, 0 off, n = force n warps per CTA */
     int64_t opt_order = 54321;           /* launch order of the allele-count classes */
     int64_t opt_time_kernels = 0, opt_concurrent = 1;    /* class kernels on their own streams: a class fills the tail of the previous one (-3.5 % per C3 step) */
@@ -166,7 +182,8 @@ extern "C" int mcb_set_option(mcb_ctx *ctx, const char *key, int64_t value)
     else if ( !strcmp(key,"multi") )         ctx->opt_multi = value;
     else if ( !strcmp(key,"mm_nst") )        { if ( value<0 || value>4 ) return MCB_EINVAL; ctx->opt_mm_nst = value; }
     else if ( !strncmp(key,"mm_nst_",7) && key[7]>='3' && key[7]<='5' && !key[8] ) { if ( value<0 || value>4 ) return MCB_EINVAL; ctx->opt_mm_nst_c[key[7]-'0'] = value; }
-    else if ( !strcmp(key,"mm_block") )      { if ( value!=0 && value!=128 && value!=256 && value!=512 ) return MCB_EINVAL; ctx->opt_mm_block = value; }
+    else if ( !strcmp(key,"mm_block") )      { if ( value!=0 && value!=64 && value!=128 && value!=256 ) return MCB_EINVAL; ctx->opt_mm_block = value; }
+    else if ( !strncmp(key,"mm_block_",9) && key[9]>='3' && key[9]<='5' && !key[10] ) { if ( value!=0 && value!=64 && value!=128 && value!=256 ) return MCB_EINVAL; ctx->opt_mm_block_c[key[9]-'0'] = value; }
     else if ( !strcmp(key,"warp2") )         { if ( value<-1 || value>biallelic_max_warps() ) return MCB_EINVAL; ctx->opt_warp2 = value; }
     else if ( !strncmp(key,"ring_bytes_",11) && key[11]>='1' && key[11]<='5' && !key[12] ) ctx->opt_ring_bytes_c[key[11]-'0'] = value;
     else if ( !strncmp(key,"block_",6) && key[6]>='1' && key[6]<='5' && !key[7] )
@@ -181,18 +198,22 @@ extern "C" int mcb_set_option(mcb_ctx *ctx, const char *key, int64_t value)
     return MCB_OK;
 }
 
-static int upload_ploidy(mcb_ctx *ctx)
+/*  Device copy of the ploidy table.  One row is uploaded per registration; the table is only reallocated (after a device
+ *  synchronisation: kernels in flight read it) when it outgrows its capacity, which starts at 64 vectors.  */
+static int upload_ploidy(mcb_ctx *ctx, int first, int count)
 {
-    int S = ctx->p.nsmpl;
+    const int S = ctx->p.nsmpl;
     if ( ctx->nploidy > ctx->ploidy_cap )
     {
+        CK(cudaDeviceSynchronize());
         if ( ctx->d_ploidy ) cudaFree(ctx->d_ploidy);
-        ctx->ploidy_cap = std::max(4, 2*ctx->nploidy);
+        ctx->ploidy_cap = std::max(64, 2*ctx->nploidy);
         CK(cudaMalloc(&ctx->d_ploidy, (size_t)ctx->ploidy_cap*S));
+        first = 0; count = ctx->nploidy;
     }
-    CK(cudaMemcpy(ctx->d_ploidy, ctx->h_ploidy.data(), (size_t)ctx->nploidy*S, cudaMemcpyHostToDevice));
-    ctx->any_nondiploid = false;
-    for (size_t i=0; i<ctx->h_ploidy.size(); i++) if ( ctx->h_ploidy[i]!=2 ) { ctx->any_nondiploid = true; break; }
+    CK(cudaMemcpy(ctx->d_ploidy + (size_t)first*S, ctx->h_ploidy.data() + (size_t)first*S, (size_t)count*S, cudaMemcpyHostToDevice));
+    if ( !ctx->any_nondiploid )
+        for (size_t i=(size_t)first*S; i<(size_t)(first+count)*S; i++) if ( ctx->h_ploidy[i]!=2 ) { ctx->any_nondiploid = true; break; }
     return MCB_OK;
 }
 
@@ -226,7 +247,7 @@ extern "C" int mcb_init(mcb_ctx **out, const mcb_params *params)
 
     ctx->h_ploidy.assign(params->nsmpl, 2);     /* id 0: all diploid */
     ctx->nploidy = 1;
-    int rc = upload_ploidy(ctx);
+    int rc = upload_ploidy(ctx, 0, 1);
     if ( rc ) return rc;
     CK(cudaMalloc(&ctx->d_counts, sizeof(int32_t)*NCOUNTS));     /* + work counter of the warp-per-site kernel */
     CK(cudaMalloc(&ctx->d_cursor, sizeof(unsigned long long)));
@@ -266,13 +287,14 @@ extern "C" void mcb_destroy(mcb_ctx *ctx)
 {
     if ( !ctx ) return;
     cudaSetDevice(ctx->device);
-    cudaFree(ctx->d_tab); cudaFree(ctx->d_ploidy); cudaFree(ctx->d_grp_off); cudaFree(ctx->d_grp_smpl); cudaFree(ctx->d_smpl2grp); cudaFree(ctx->d_grp_scratch); cudaFree(ctx->d_gen_grp); cudaFree(ctx->d_gen_pl); cudaFree(ctx->d_gen_sum);
+    cudaFree(ctx->d_tab); cudaFree(ctx->d_ploidy); cudaFree(ctx->d_grp_off); cudaFree(ctx->d_grp_smpl); cudaFree(ctx->d_smpl2grp); free_scratch(ctx->scratch);
     cudaFree(ctx->d_lists); cudaFree(ctx->d_counts); cudaFree(ctx->d_cursor);
     for (int i=0; i<NSLAB; i++)
     {
         if ( ctx->slab[i].stream ) cudaStreamDestroy(ctx->slab[i].stream);
         if ( ctx->slab[i].done ) cudaEventDestroy(ctx->slab[i].done);
         if ( ctx->slab[i].cursor_ready ) cudaEventDestroy(ctx->slab[i].cursor_ready);
+        free_scratch(ctx->slab[i].scratch);
         cudaFree(ctx->slab[i].dev); cudaFree(ctx->slab[i].lists); cudaFree(ctx->slab[i].counts); cudaFree(ctx->slab[i].cursor);
         if ( ctx->slab[i].h_cursor ) cudaFreeHost(ctx->slab[i].h_cursor);
         if ( ctx->slab[i].h_in ) cudaFreeHost(ctx->slab[i].h_in);
@@ -290,14 +312,24 @@ extern "C" int mcb_set_ploidy(mcb_ctx *ctx, int id, const uint8_t *ploidy)
     int S = ctx->p.nsmpl;
     for (int i=0; i<S; i++) if ( ploidy[i]>2 ) return MCB_EINVAL;
     CK(cudaSetDevice(ctx->device));
+    const int old_n = ctx->nploidy;
     if ( id >= ctx->nploidy )
     {
         ctx->h_ploidy.resize((size_t)(id+1)*S, 2);
         ctx->nploidy = id+1;
     }
+    const bool rewrite = id < old_n && memcmp(ctx->h_ploidy.data() + (size_t)id*S, ploidy, S);
     memcpy(ctx->h_ploidy.data() + (size_t)id*S, ploidy, S);
-    CK(cudaDeviceSynchronize());
-    return upload_ploidy(ctx);
+    if ( rewrite )
+    {
+        /* an id that batches already referred to changes its meaning: nothing in flight may still read the old row,
+           and the "every sample diploid" shortcut is re-derived from the whole table */
+        CK(cudaDeviceSynchronize());
+        ctx->any_nondiploid = false;
+        return upload_ploidy(ctx, 0, ctx->nploidy);
+    }
+    const int first = std::min(id, old_n);      /* ids skipped over are filled with all-diploid rows */
+    return upload_ploidy(ctx, first, ctx->nploidy - first);
 }
 
 extern "C" void *mcb_host_alloc(size_t bytes)
@@ -385,33 +417,33 @@ static void tile_geometry(const mcb_ctx *ctx, int nals, int es, int *tile_smpl, 
 
 /*  Sites with 0 or more than 5 alleles (class 0).  With max_nals <= 5 they cannot be legal input and are reported
  *  unsupported; otherwise the generic kernel of mcall_generic.cu handles 6..32 alleles (int32 PLs).            */
-static int enqueue_class0(mcb_ctx *ctx, KArgs &a, const mcb_batch *b, const mcb_result *r, int32_t *lists, int32_t *counts, int pl_es, cudaStream_t st)
+static int enqueue_class0(mcb_ctx *ctx, KArgs &a, const mcb_batch *b, const mcb_result *r, int32_t *lists, int32_t *counts, int pl_es, KernelScratch &sc, cudaStream_t st)
 {
     if ( ctx->p.max_nals <= 5 || pl_es != 4 )
     {
-        CK(launch_unsupported(lists, counts, r->ret, r->site_flags, b->nals, st));
+        CK(launch_unsupported(lists, counts, r->ret, r->site_flags, b->nals, r->pl_off_out, st));
         return MCB_OK;
     }
-    if ( !ctx->gen_grid )
+    if ( !sc.gen_grid )
     {
         size_t g1, g2, g3;
         generic_scratch_bytes(1, ctx->ngroups, ctx->p.nsmpl, &g1, &g2, &g3);
         int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ctx->nsm, (int64_t)(768ll<<20)/(int64_t)(g1+g2+g3)));
         generic_scratch_bytes(grid, ctx->ngroups, ctx->p.nsmpl, &g1, &g2, &g3);
-        CK(cudaMalloc(&ctx->d_gen_grp, g1)); CK(cudaMalloc(&ctx->d_gen_pl, g2)); CK(cudaMalloc(&ctx->d_gen_sum, g3));
-        ctx->gen_grid = grid;
+        CK(cudaMalloc(&sc.gen_grp, g1)); CK(cudaMalloc(&sc.gen_pl, g2)); CK(cudaMalloc(&sc.gen_sum, g3));
+        sc.gen_grid = grid;
     }
     a.site_list = lists; a.site_count = counts;
     a.grp_off = ctx->d_grp_off; a.grp_smpl = ctx->d_grp_smpl; a.smpl2grp = ctx->d_smpl2grp; a.ngroups = ctx->ngroups;
-    CK(launch_generic_kernel(a, ctx->d_gen_grp, ctx->d_gen_pl, ctx->d_gen_sum, std::min(ctx->gen_grid, std::max(1, b->nsites)), st));
+    CK(launch_generic_kernel(a, sc.gen_grp, sc.gen_pl, sc.gen_sum, std::min(sc.gen_grid, std::max(1, b->nsites)), st));
     return MCB_OK;
 }
 
-static int enqueue(mcb_ctx *ctx, const mcb_batch *b, const mcb_result *r, int32_t *lists, int32_t *counts, int list_stride, unsigned long long *cursor, cudaStream_t st)
+static int enqueue(mcb_ctx *ctx, const mcb_batch *b, const mcb_result *r, int32_t *lists, int32_t *counts, int list_stride, unsigned long long *cursor, KernelScratch &sc, cudaStream_t st)
 {
     CK(cudaMemsetAsync(counts, 0, sizeof(int32_t)*NCOUNTS, st));
     if ( r->pl_off_out ) CK(cudaMemsetAsync(cursor, 0, sizeof(unsigned long long), st));
-    CK(launch_classify(b->nals, b->nsites, lists, counts, list_stride, st));
+    CK(launch_classify(b->nals, b->nsites, lists, counts, list_stride, ctx->p.max_nals, r->ret, r->site_flags, r->pl_off_out, st));
     int launches = 1;
     KArgs a;
     memset(&a, 0, sizeof a);
@@ -436,21 +468,21 @@ static int enqueue(mcb_ctx *ctx, const mcb_batch *b, const mcb_result *r, int32_
         const size_t per_cta = groups_scratch_bytes(1, ctx->ngroups);
         grid = (int)std::max<int64_t>(1, std::min<int64_t>(grid, (int64_t)(512ll<<20)/(int64_t)per_cta));
         const size_t need = groups_scratch_bytes(grid, ctx->ngroups);
-        if ( need > ctx->grp_scratch_bytes )
+        if ( need > sc.grp_bytes )
         {
             CK(cudaStreamSynchronize(st));
-            if ( ctx->d_grp_scratch ) CK(cudaFree(ctx->d_grp_scratch));
-            CK(cudaMalloc(&ctx->d_grp_scratch, need));
-            ctx->grp_scratch_bytes = need;
+            if ( sc.grp ) CK(cudaFree(sc.grp));
+            CK(cudaMalloc(&sc.grp, need));
+            sc.grp_bytes = need;
         }
         for (int nals=1; nals<=5; nals++)
         {
             a.site_list = lists + (size_t)nals*list_stride; a.site_count = counts + nals;
             a.work_counter = counts + NCLASS + nals;
-            CK(launch_groups_kernel(nals, a, ctx->d_grp_scratch, grid, st));
+            CK(launch_groups_kernel(nals, a, sc.grp, grid, st));
             launches++;
         }
-        { int rc0 = enqueue_class0(ctx, a, b, r, lists, counts, pl_es, st); if ( rc0 ) return rc0; }
+        { int rc0 = enqueue_class0(ctx, a, b, r, lists, counts, pl_es, sc, st); if ( rc0 ) return rc0; }
         ctx->stats[0] += launches + 1;
         ctx->stats[1] += b->nsites;
         ctx->kev_valid = false;
@@ -549,10 +581,12 @@ static int enqueue(mcb_ctx *ctx, const mcb_batch *b, const mcb_result *r, int32_
              && (a.output_tags & (MCB_CALL_FMT_GQ|MCB_CALL_FMT_GP))
              && !((reinterpret_cast<uintptr_t>(a.gt) | reinterpret_cast<uintptr_t>(a.gq) | reinterpret_cast<uintptr_t>(a.out_pl)) & 15) )
         {
-            int mblock = ctx->opt_mm_block ? (int)ctx->opt_mm_block : multi_block_for(a.nsmpl);
-            if ( mblock && (a.nsmpl & 1) ) mblock = 0;
-            if ( mblock && (a.nsmpl + 1)/2 > 5*mblock ) mblock = 0;         /* more than 10 samples per thread: out of range */
-            int nst = ctx->opt_mm_nst_c[nals] ? (int)ctx->opt_mm_nst_c[nals] : (ctx->opt_mm_nst ? (int)ctx->opt_mm_nst : (nals==3 ? 3 : 2));
+            /* CTA size: explicit option, else the class default (sweeps in profiles/), never below what the 12-bit allele counters allow */
+            const int minblock = multi_block_for(a.nsmpl);
+            int mblock = ctx->opt_mm_block_c[nals] ? (int)ctx->opt_mm_block_c[nals] : (ctx->opt_mm_block ? (int)ctx->opt_mm_block : (nals==3 ? 64 : 128));
+            if ( !minblock ) mblock = 0;
+            else mblock = std::max(mblock, minblock);
+            int nst = ctx->opt_mm_nst_c[nals] ? (int)ctx->opt_mm_nst_c[nals] : (ctx->opt_mm_nst ? (int)ctx->opt_mm_nst : (nals==5 ? 1 : 2));
             const size_t cap = 227u*1024u;
             while ( mblock && nst>1 && multi_smem_bytes(nals, mblock, a.nsmpl, nst) > cap ) nst--;
             if ( mblock && multi_smem_bytes(nals, mblock, a.nsmpl, nst) <= cap )
@@ -562,11 +596,21 @@ static int enqueue(mcb_ctx *ctx, const mcb_batch *b, const mcb_result *r, int32_
                 if ( mnb >= 1 )
                 {
                     if ( ctx->opt_bps_c[nals]>0 ) mnb = std::min<int>(mnb, (int)ctx->opt_bps_c[nals]);
+                    const int mgrid = (int)std::min<int64_t>((int64_t)b->nsites, (int64_t)ctx->nsm*mnb);
+                    const size_t need = multi_scratch_bytes(a.nsmpl, mgrid);
+                    if ( need > sc.mm_sums_bytes[nals] )
+                    {
+                        CK(cudaStreamSynchronize(cs));
+                        if ( sc.mm_sums[nals] ) CK(cudaFree(sc.mm_sums[nals]));
+                        const size_t want = multi_scratch_bytes(a.nsmpl, ctx->nsm*mnb);      /* full grid: no regrowth with the next, larger batch */
+                        CK(cudaMalloc(&sc.mm_sums[nals], want));
+                        sc.mm_sums_bytes[nals] = want;
+                    }
                     KArgs am = a;
                     am.nstage = nst;
+                    am.mm_sums = sc.mm_sums[nals];
                     am.fb_list = lists + (size_t)(NCLASS + nals)*list_stride;
                     am.fb_count = counts + NCLASS + 8 + nals;
-                    const int mgrid = (int)std::min<int64_t>((int64_t)b->nsites, (int64_t)ctx->nsm*mnb);
                     cudaError_t le = launch_multi_kernel(nals, mblock, am, mgrid, cs);
                     if ( le==cudaSuccess && getenv("MCB_DEBUG_SYNC") ) le = cudaStreamSynchronize(cs);
                     if ( le!=cudaSuccess )
@@ -599,7 +643,7 @@ static int enqueue(mcb_ctx *ctx, const mcb_batch *b, const mcb_result *r, int32_
         if ( timing ) CK(cudaEventRecord(ctx->kev[nals], st));
     }
     ctx->kev_valid = timing;
-    { int rc0 = enqueue_class0(ctx, a, b, r, lists, counts, pl_es, st); if ( rc0 ) return rc0; }
+    { int rc0 = enqueue_class0(ctx, a, b, r, lists, counts, pl_es, sc, st); if ( rc0 ) return rc0; }
     launches++;
     ctx->stats[0] += launches;
     ctx->stats[1] += b->nsites;
@@ -620,7 +664,7 @@ extern "C" int mcb_call_device(mcb_ctx *ctx, const mcb_batch *b, const mcb_resul
         CK(cudaMalloc(&ctx->d_lists, lists_bytes(ctx->list_cap)));
     }
     ctx->stats[0] = ctx->stats[1] = 0;
-    return enqueue(ctx, b, r, ctx->d_lists, ctx->d_counts, ctx->list_cap, ctx->d_cursor, st);
+    return enqueue(ctx, b, r, ctx->d_lists, ctx->d_counts, ctx->list_cap, ctx->d_cursor, ctx->scratch, st);
 }
 
 /* ---- host path: slabs double-buffered over two streams ---------------------------------------------- */
@@ -671,6 +715,7 @@ extern "C" int mcb_call_host(mcb_ctx *ctx, const mcb_batch *b, const mcb_result 
     for (int i=0; i<R; i++)
     {
         int n = b->nals[i];
+        if ( n > M && n <= MCB_MAX_NALS ) return MCB_EINVAL;    /* the per-site allele arrays (qs, prior_ac, ac, als_map) have stride max_nals */
         ext[i] = (( (int64_t)S*n*(n+1)/2 ) + amask) & ~amask;
         if ( (b->pl_off[i] & amask) || (i && b->pl_off[i] < b->pl_off[i-1] + ext[i-1]) ) return MCB_EINVAL;
     }
@@ -840,7 +885,7 @@ extern "C" int mcb_call_host(mcb_ctx *ctx, const mcb_batch *b, const mcb_result 
             dr.pl_off_out = (int64_t*)(base+o_ploo);
         }
 
-        int rc = enqueue(ctx, &db, &dr, sl.lists, sl.counts, sl.list_cap, sl.cursor, st);
+        int rc = enqueue(ctx, &db, &dr, sl.lists, sl.counts, sl.list_cap, sl.cursor, sl.scratch, st);
         if ( rc ) return rc;
 
 #define D2H(dst,src,bytes) CK(cudaMemcpyAsync((dst), base+(src), (bytes), cudaMemcpyDeviceToHost, st))

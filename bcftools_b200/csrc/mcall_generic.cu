@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(XBLOCK) mcall_generic_kernel(const KArgs a, XG
         const int nals = a.nals[site];
         if ( nals<6 || nals>XMAXA )        /* 0 alleles or > 32: skipped like mcall.c:1539-1543 */
         {
-            if ( tid==0 ) { a.ret[site] = 0; if ( a.site_flags ) a.site_flags[site] = nals>XMAXA ? MCB_SITE_TOO_MANY_ALS : MCB_SITE_UNSUPPORTED; }
+            if ( tid==0 ) { a.ret[site] = 0; if ( a.site_flags ) a.site_flags[site] = nals>XMAXA ? MCB_SITE_TOO_MANY_ALS : MCB_SITE_UNSUPPORTED; if ( a.pl_off_out ) a.pl_off_out[site] = -1; }
             continue;
         }
         const int G = nals*(nals+1)/2, npair = nals*(nals-1)/2, nsub = nals + npair + nals*(nals-1)*(nals-2)/6;

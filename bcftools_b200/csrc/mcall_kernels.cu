@@ -1150,18 +1150,27 @@ cudaError_t launch_selftest_div(const DevTables *tab, int mode, unsigned long lo
 /* ------------------------------------------------------------------------------------------------
  *  site classification: one list of site indices per allele count (1..5), one for everything else
  * ---------------------------------------------------------------------------------------------- */
-__global__ void classify_sites_kernel(const uint8_t *nals, int nsites, int32_t *lists, int32_t *counts, int list_stride)
+__global__ void classify_sites_kernel(const uint8_t *nals, int nsites, int32_t *lists, int32_t *counts, int list_stride,
+                                      int max_nals, int32_t *ret, uint32_t *site_flags, int64_t *pl_off_out)
 {
     int i = blockIdx.x*blockDim.x + threadIdx.x;
     if ( i >= nsites ) return;
     int n = nals[i];
+    if ( n > max_nals && n <= MCB_MAX_NALS )
+    {
+        /* more alleles than the stride of the per-site allele arrays (qs, prior_ac, ac, als_map): no kernel may index them */
+        ret[i] = 0;
+        if ( site_flags ) site_flags[i] = MCB_SITE_UNSUPPORTED;
+        if ( pl_off_out ) pl_off_out[i] = -1;
+        return;
+    }
     int cls = (n>=1 && n<=5) ? n : 0;
     int pos = atomicAdd(&counts[cls], 1);
     lists[(size_t)cls*list_stride + pos] = i;
 }
 
 /*  sites the templated kernels do not cover (n_allele 0 or >5): reported as skipped for now  */
-__global__ void unsupported_sites_kernel(const int32_t *list, const int32_t *count, int32_t *ret, uint32_t *site_flags, const uint8_t *nals)
+__global__ void unsupported_sites_kernel(const int32_t *list, const int32_t *count, int32_t *ret, uint32_t *site_flags, const uint8_t *nals, int64_t *pl_off_out)
 {
     int n = *count;
     for (int i = blockIdx.x*blockDim.x + threadIdx.x; i<n; i += gridDim.x*blockDim.x)
@@ -1169,6 +1178,7 @@ __global__ void unsupported_sites_kernel(const int32_t *list, const int32_t *cou
         int site = list[i];
         ret[site] = 0;
         if ( site_flags ) site_flags[site] = nals[site] > 32 ? MCB_SITE_TOO_MANY_ALS : MCB_SITE_UNSUPPORTED;
+        if ( pl_off_out ) pl_off_out[site] = -1;
     }
 }
 
@@ -1237,15 +1247,15 @@ cudaError_t site_kernel_occupancy(int nals, bool ploidy, bool gp, int block, int
     return dispatch_nals(nals, ploidy, gp, gp ? 128 : block, pl_es, nullptr, 0, ring_bytes, nullptr, nb);
 }
 
-cudaError_t launch_classify(const uint8_t *nals, int nsites, int32_t *lists, int32_t *counts, int list_stride, cudaStream_t st)
+cudaError_t launch_classify(const uint8_t *nals, int nsites, int32_t *lists, int32_t *counts, int list_stride, int max_nals, int32_t *ret, uint32_t *site_flags, int64_t *pl_off_out, cudaStream_t st)
 {
     if ( nsites<=0 ) return cudaSuccess;
-    classify_sites_kernel<<<(nsites+255)/256, 256, 0, st>>>(nals, nsites, lists, counts, list_stride);
+    classify_sites_kernel<<<(nsites+255)/256, 256, 0, st>>>(nals, nsites, lists, counts, list_stride, max_nals, ret, site_flags, pl_off_out);
     return cudaGetLastError();
 }
-cudaError_t launch_unsupported(const int32_t *list, const int32_t *count, int32_t *ret, uint32_t *site_flags, const uint8_t *nals, cudaStream_t st)
+cudaError_t launch_unsupported(const int32_t *list, const int32_t *count, int32_t *ret, uint32_t *site_flags, const uint8_t *nals, int64_t *pl_off_out, cudaStream_t st)
 {
-    unsupported_sites_kernel<<<64, 256, 0, st>>>(list, count, ret, site_flags, nals);
+    unsupported_sites_kernel<<<64, 256, 0, st>>>(list, count, ret, site_flags, nals, pl_off_out);
     return cudaGetLastError();
 }
 

@@ -59,6 +59,7 @@ struct KArgs
     int32_t *work_counter;                                      /* next unclaimed entry of site_list (warp-per-site kernel) */
     /* sites the multi-allelic kernel (mcall_multi.cu) hands back to the general tiled kernel */
     int32_t *fb_list;  int32_t *fb_count;
+    double  *mm_sums;                                            /* its per-CTA rows of per-sample normalisers (L2-resident scratch) */
     int nsmpl, max_nals;
     uint32_t flag, output_tags;
     double theta, tie_eps;
@@ -71,8 +72,8 @@ struct KArgs
 namespace mcb {
 /*  launchers implemented in mcall_kernels.cu  */
 cudaError_t launch_site_kernel(int nals, bool ploidy, bool gp, int block, int pl_es, const KArgs &a, int grid, size_t ring_bytes, cudaStream_t st);
-cudaError_t launch_classify(const uint8_t *nals, int nsites, int32_t *lists, int32_t *counts, int list_stride, cudaStream_t st);
-cudaError_t launch_unsupported(const int32_t *list, const int32_t *count, int32_t *ret, uint32_t *site_flags, const uint8_t *nals, cudaStream_t st);
+cudaError_t launch_classify(const uint8_t *nals, int nsites, int32_t *lists, int32_t *counts, int list_stride, int max_nals, int32_t *ret, uint32_t *site_flags, int64_t *pl_off_out, cudaStream_t st);
+cudaError_t launch_unsupported(const int32_t *list, const int32_t *count, int32_t *ret, uint32_t *site_flags, const uint8_t *nals, int64_t *pl_off_out, cudaStream_t st);
 cudaError_t site_kernel_occupancy(int nals, bool ploidy, bool gp, int block, int pl_es, size_t ring_bytes, int *blocks_per_sm);
 size_t groups_scratch_bytes(int grid, int ngroups);
 cudaError_t launch_groups_kernel(int nals, const KArgs &a, void *scratch, int grid, cudaStream_t st);
@@ -86,6 +87,7 @@ cudaError_t launch_biallelic_warp_kernel(const KArgs &a, bool ploidy, int grid, 
 /*  CTA-per-site kernel of the 3-5 allele classes over a byte-packed shared-memory copy (mcall_multi.cu)  */
 int multi_block_for(int nsmpl);
 size_t multi_smem_bytes(int nals, int block, int nsmpl, int nst);
+size_t multi_scratch_bytes(int nsmpl, int grid);
 cudaError_t multi_kernel_occupancy(int nals, int block, int nsmpl, int nst, int *blocks_per_sm);
 cudaError_t launch_multi_kernel(int nals, int block, const KArgs &a, int grid, cudaStream_t st);
 cudaError_t launch_selftest_div(const DevTables *tab, int mode, unsigned long long n, unsigned long long seed, unsigned long long *mismatch, cudaStream_t st);

@@ -5,21 +5,24 @@
  *  group combine + QUAL 1546-1567 / 1631-1645, trimming maps 547-570, mcall_call_genotypes 745-886,
  *  mcall_set_ref_genotypes 713-743, mcall_trim_and_update_PLs 1158-1194); what differs is how a site is held and walked:
  *
- *    - ONE CTA owns one site.  HBM sees every PL byte once: phase 1 leaves a byte-packed copy of the site (8 / 12 / 16
- *      bytes per sample for 6 / 10 / 15 genotypes) plus the sample's normaliser `sum` (8 bytes) in shared memory, and
- *      phase 2 works from those -- it neither re-fetches the int32 block nor repeats the G table look-ups per sample.
+ *    - ONE small CTA (2-8 warps) owns one site and many CTAs share an SM, so that the serial part of a site (warp 0
+ *      comparing the allele sets) overlaps the sample loops of the other CTAs.  HBM sees every PL byte once: phase 1
+ *      leaves a byte-packed copy of the site (6 / 10 / 16 bytes per sample for 6 / 10 / 15 genotypes) in shared memory
+ *      and the sample's normaliser `sum` (8 bytes) in a per-CTA scratch row that never leaves L2, and phase 2 works
+ *      from those -- it neither re-fetches the int32 block nor repeats the G table look-ups per sample.
  *    - every WARP streams its own 64-sample tiles of the int32 block through a private ring of bulk copies
  *      (cp.async.bulk + mbarrier, SASS UBLKCP / SYNCS): no block barrier inside a phase; the first tiles of the CTA's
  *      NEXT site are issued when phase 2 starts, so they land while phase 2 computes.
  *    - each lane takes TWO ADJACENT samples per iteration (coefficient loads are shared, two dependency chains
  *      interleave, the pair's outputs leave in 64/128-bit stores).
- *    - phase 1 keeps ONE plain double product per allele set and thread (a thread multiplies at most 10 samples per site:
- *      every factor is >= 1e-27 for PL <= 255, so nothing underflows) -- 1 DMUL per set and sample instead of the
- *      exponent-tracked multiply; exponents are split off once, in the warp reduction.  Samples without data
- *      (PL = 0,..,0) are multiplied in like any other and divided out per site (their factor is a per-site constant).
- *    - samples with a missing / vector_end value or a PL >= 256 never enter the main loops: the lane puts its pair on a
- *      per-site list, warp 0 evaluates the list with the general per-sample code (sum of logs) before the allele sets
- *      are compared, and stores the FILLED bytes (mcall.c:495-527) so that phase 2 sees an ordinary sample.
+ *    - phase 1 keeps ONE plain double product per allele set and thread -- 1 DMUL per set and sample instead of the
+ *      exponent-tracked multiply (every factor is >= 1e-27 for PL <= 255, so ten samples cannot underflow); exponents
+ *      are split off every fifth iteration and in the warp reduction, which goes through a shared-memory transpose (one
+ *      lane per allele set multiplies the 32 partial products).  Samples without data (PL = 0,..,0) are multiplied in
+ *      like any other and divided out per site (their factor is a per-site constant).
+ *    - a sample with a missing / vector_end value or a PL >= 256 enters the main loop as a no-data sample and its int32
+ *      row goes on a per-site list; warp 0 evaluates the list with the general per-sample code (sum of logs) before
+ *      the allele sets are compared, and stores the FILLED bytes (mcall.c:495-527) so that phase 2 sees an ordinary sample.
  *    - phase 2 is straight-line code per site type: REF only / a pair {REF,b} / a triple {REF,b,c}, each keeping exactly
  *      the selected alleles.  Everything else (selected set without REF, unseen allele selected, PL >= 256 after the
  *      fill, list overflow) is appended to a fallback list that the general tiled kernel (mcall_kernels.cu) processes.
@@ -32,7 +35,8 @@
 
 namespace mcb {
 
-#define MM_ESC_CAP   128            /* samples per site that may take the general path (pairs: 64 special lanes) */
+#define MM_ESC_CAP   32             /* samples per site that may take the general path (one lane of warp 0 each) */
+#define MM_RENORM    5              /* iterations (pairs of samples per lane) between exponent splits of the running products */
 #define MM_MAX_NST   4              /* ring stages per warp */
 #ifndef MM_MINCTA3
 #define MM_MINCTA3 2
@@ -47,11 +51,18 @@ namespace mcb {
 template<int NALS> struct MMGeom
 {
     static constexpr int G  = Shape<NALS>::G;
-    static constexpr int RS = NALS<=3 ? 8 : (NALS==4 ? 12 : 16);       /* bytes per sample of the packed copy */
+    static constexpr int RS = NALS<=3 ? 6 : (NALS==4 ? 10 : 16);       /* bytes per sample of the packed copy */
     static constexpr int TILE_BYTES = 64*G*4;                           /* one warp tile: 64 samples of int32 PLs */
     static constexpr int NSET = Shape<NALS>::NPAIR + Shape<NALS>::NTRI;
     static constexpr int MINCTA = NALS==3 ? MM_MINCTA3 : (NALS==4 ? MM_MINCTA4 : MM_MINCTA5);    /* CTAs of 256 threads per SM */
+    static constexpr int NACC = NSET + 1;
+    static constexpr int RED_BYTES = NACC*32*12;                        /* warp reduction: one (mantissa, exponent) per lane and product */
 };
+/*  per-warp shared-memory region: the bulk-copy ring, reused for the warp reduction while no copy is in flight  */
+__host__ __device__ constexpr int mm_warp_region(int tile_bytes, int red_bytes, int nst)
+{
+    return ((nst*tile_bytes > red_bytes ? nst*tile_bytes : red_bytes) + 127) & ~127;
+}
 
 /*  per-site set-up, double buffered: written by warp 1 for the NEXT site while warp 0 evaluates the current one  */
 template<int NALS> struct __align__(16) MMSetup
@@ -78,12 +89,13 @@ template<int NALS, int BLOCK> struct MMShared
     double   red_M[NW][NACC];
     int      red_E[NW][NACC];
     int      red_pls[NW][NALS];
-    int      red_cnt[NW][2];
-    /* samples that take the general path */
+    int      red_cnt[NW];               /* samples without data that went through the main loop (PL = 0,..,0 and the listed ones) */
+    /* samples that take the general path: index and int32 row */
     int      nesc;
     unsigned short esc[MM_ESC_CAP];
+    int      esc_pl[MM_ESC_CAP][S::G];
     /* site decision record (written by warp 0, read by everybody in phase 2 and by thread 0 at the next site's start) */
-    double   max_qual, lk_sum, ref_lk, gap;
+    double   max_qual, lk_sum, ref_lk, gap, lse;     /* lse = logsumexp2(lk_sum, ref_lk) */
     double   q[3];
     uint32_t als_new, flags;
     int      path;                      /* 0 nothing to do, 1 REF only, 2 pair {REF,b}, 3 triple {REF,b,c} */
@@ -98,6 +110,10 @@ template<int NALS, int BLOCK> struct MMShared
 __device__ __forceinline__ void mm_lds_f64x2(uint32_t a, double &x, double &y)
 {
     asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(x), "=d"(y) : "r"(a));
+}
+__device__ __forceinline__ void mm_ldg_f64x2(const double *p, double &x, double &y)       /* L2 only: the row is rewritten every site */
+{
+    asm volatile("ld.global.cg.v2.f64 {%0,%1}, [%2];" : "=d"(x), "=d"(y) : "l"(p) : "memory");
 }
 __device__ __forceinline__ int2 mm_lds64i(uint32_t a)
 {
@@ -122,12 +138,6 @@ __device__ __forceinline__ uint32_t mm_pack4(int a, int b, int c, int d) { retur
 
 static __device__ __noinline__ double mm_log(double x) { return log(x); }
 static __device__ __noinline__ double mm_exp(double x) { return exp(x); }
-__device__ __forceinline__ double mm_logsumexp2(double a, double b)       /* mcall.c:573-579 */
-{
-    const double hi = a>b ? a : b, lo = a>b ? b : a;
-    return mm_log(1 + mm_exp(lo - hi)) + hi;
-}
-
 /*  set_pdg's missing-value fill (mcall.c:495-527) on a local copy of one sample's PL vector; returns 0 for "no data"
  *  (same rules as fix_missing in mcall_kernels.cu, including the values it leaves behind when it gives up)  */
 static __device__ __noinline__ int mm_fix_missing(int *pl, int nals, int unseen)
@@ -167,18 +177,18 @@ template<int NALS> struct MMSlow
     uint32_t punt;
 };
 
-/*  One sample on the general path: loads the int32 row from global memory, applies the fill, and -- when the sample has
- *  data and every value fits a byte -- adds its terms to `acc` and stores the filled packed row and the normaliser, so
- *  that phase 2 treats it like any other sample.  No data: packed zeros; sum = -1 when the row still holds sentinels
- *  (phase 2 then re-derives the output row from the int32 values), +G otherwise.  */
+/*  One sample on the general path: takes the int32 row the owning lane left on the list, applies the fill, and -- when the
+ *  sample has data and every value fits a byte -- adds its terms to `acc` and stores the filled packed row and the
+ *  normaliser, so that phase 2 treats it like any other sample.  No data: packed zeros; sum = -1 when the row still holds
+ *  sentinels (phase 2 then re-derives the output row from the int32 values), +G otherwise.  */
 template<int NALS>
-static __device__ __noinline__ void mm_slow_sample(const int32_t *grow, const MMSetup<NALS> *su, uint32_t pl2p_s, uint32_t row_s, uint32_t sum_s, MMSlow<NALS> *acc)
+static __device__ __noinline__ void mm_slow_sample(const int *row, const MMSetup<NALS> *su, uint32_t pl2p_s, uint32_t row_s, double *sum_g, MMSlow<NALS> *acc)
 {
     using S = Shape<NALS>;
     constexpr int G = S::G, RS = MMGeom<NALS>::RS;
     int pl[G]; double p[G];
     int orv = 0;
-    for (int j=0; j<G; j++) { pl[j] = __ldg(grow + j); orv |= pl[j]; }
+    for (int j=0; j<G; j++) { pl[j] = row[j]; orv |= pl[j]; }
     bool data = orv != 0, raw = false;
     if ( orv < 0 )
     {
@@ -187,11 +197,10 @@ static __device__ __noinline__ void mm_slow_sample(const int32_t *grow, const MM
         if ( data ) { orv = 0; for (int j=0; j<G; j++) orv |= pl[j]; data = orv > 0; }
     }
     if ( data && (unsigned)orv > 255u ) { acc->punt = 1; data = false; }    /* PL >= 256: the general kernel owns this site */
-    uint32_t w[4] = {0,0,0,0};
     double sum = raw ? -1.0 : (double)G;
     if ( data )
     {
-        for (int j=0; j<G; j++) { p[j] = lds64(pl2p_s + 8u*(uint32_t)pl[j]); w[j>>2] |= (uint32_t)pl[j] << (8*(j&3)); }
+        for (int j=0; j<G; j++) p[j] = lds64(pl2p_s + 8u*(uint32_t)pl[j]);
         sum = p[0];
         for (int j=1; j<G; j++) sum = __dadd_rn(sum, p[j]);
         acc->ndata++;
@@ -222,8 +231,9 @@ static __device__ __noinline__ void mm_slow_sample(const int32_t *grow, const MM
                         acc->lk[k] += mm_log(val);
                     }
     }
-    for (int j=0; j<RS; j+=4) mm_sts32(row_s + (uint32_t)j, w[j>>2]);
-    mm_sts_f64(sum_s, sum);
+    for (int j=0; j<RS; j++)
+        asm volatile("st.shared.u8 [%0], %1;" :: "r"(row_s + (uint32_t)j), "r"((data && j<G) ? pl[j] : 0) : "memory");
+    asm volatile("st.global.cg.f64 [%0], %1;" :: "l"(sum_g), "d"(sum) : "memory");
 }
 
 /*  qsum (mcall.c:1454-1464), -F prior (1507-1527), normalisation (1530-1535) by lane 0, then the allele-set
@@ -340,7 +350,7 @@ static __device__ __noinline__ void mm_finalize(MMShared<NALS,BLOCK> *shp, const
     if ( !sh.ref_gt && !nAC && (a.flag & MCB_CALL_VARONLY) ) ret = 0;      /* mcall.c:1618 */
     float qual;
     if ( nAC ) qual = (float)sh.max_qual;
-    else if ( sh.lk_sum != -CUDART_INF ) qual = (float)(-4.343*(sh.lk_sum - mm_logsumexp2(sh.lk_sum, sh.ref_lk)));
+    else if ( sh.lk_sum != -CUDART_INF ) qual = (float)(-4.343*(sh.lk_sum - sh.lse));
     else if ( sh.ac[0] ) qual = a.theta ? (float)(-4.343*a.theta) : 0.f;
     else qual = __uint_as_float(MCB_FLOAT_MISSING_BITS);
     a.ret[site] = ret;
@@ -357,12 +367,13 @@ static __device__ __noinline__ void mm_finalize(MMShared<NALS,BLOCK> *shp, const
  *  order (mcall.c:600-700), the group's best set, QUAL candidates, trimming maps and the phase-2 constants.  */
 template<int NALS, int BLOCK>
 static __device__ __noinline__ void mm_epilogue(MMShared<NALS,BLOCK> *shp, const MMSetup<NALS> *su, const KArgs &a, int lane,
-                                                uint32_t pl2p_s, uint32_t pack_s, uint32_t sums_s)
+                                                uint32_t pl2p_s, uint32_t pack_s, double *sums_g)
 {
     using S = Shape<NALS>;
     using GE = MMGeom<NALS>;
     constexpr int G = S::G, NPAIR = S::NPAIR, NSUB = S::NSUB, NSET = GE::NSET, NW = BLOCK/32, RS = GE::RS;
     constexpr double LN2 = 0.693147180559945309417232121458, LN10_10 = 0.2302585092994045684017991454684;
+    constexpr double LOG_G = G==6 ? 1.791759469228055000812477358381 : (G==10 ? 2.302585092994045684017991454684 : 2.708050201102210065996004570148);   /* ln 6, ln 10, ln 15 */
     MMShared<NALS,BLOCK> &sh = *shp;
     const int site = su->site, unseen = su->unseen, nsmpl = a.nsmpl;
     const uint32_t live = su->live;
@@ -375,15 +386,10 @@ static __device__ __noinline__ void mm_epilogue(MMShared<NALS,BLOCK> *shp, const
     const int nesc_raw = sh.nesc;
     const int nesc = min(nesc_raw, MM_ESC_CAP);
     if ( nesc_raw > MM_ESC_CAP ) sl.punt = 1;
-    else
+    else if ( lane < nesc )
     {
-        const int32_t *site_pl = reinterpret_cast<const int32_t*>(a.pl) + su->pl_off;
-        #pragma unroll 1
-        for (int e=lane; e<nesc; e+=32)
-        {
-            const int s = sh.esc[e];
-            mm_slow_sample<NALS>(site_pl + (size_t)s*G, su, pl2p_s, pack_s + (uint32_t)(s*RS), sums_s + 8u*(uint32_t)s, &sl);
-        }
+        const int s = sh.esc[lane];
+        mm_slow_sample<NALS>(sh.esc_pl[lane], su, pl2p_s, pack_s + (uint32_t)(s*RS), sums_g + s, &sl);
     }
     if ( __any_sync(0xffffffffu, nesc>0) )
     {
@@ -413,10 +419,10 @@ static __device__ __noinline__ void mm_epilogue(MMShared<NALS,BLOCK> *shp, const
     const bool punt_esc = __any_sync(0xffffffffu, sl.punt != 0);
 
     /* ---- totals ---- */
-    int n_fast = 0, n0 = 0;
+    int n0 = 0;
     #pragma unroll
-    for (int w=0; w<NW; w++) { n_fast += sh.red_cnt[w][0]; n0 += sh.red_cnt[w][1]; }
-    const int n_all = n_fast + sl.ndata;                /* samples with data */
+    for (int w=0; w<NW; w++) n0 += sh.red_cnt[w];
+    const int n_all = nsmpl - n0 + sl.ndata;            /* samples with data: every sample went through the main loop, n0 of them as no-data samples */
     auto total_log = [&](int k) -> double               /* log of the product over all fast-path samples */
     {
         double M = 1.0; int E = 0;
@@ -424,10 +430,14 @@ static __device__ __noinline__ void mm_epilogue(MMShared<NALS,BLOCK> *shp, const
         for (int w=0; w<NW; w++) { M = __dmul_rn(M, sh.red_M[w][k]); E += sh.red_E[w][k]; }
         return mm_log(M) + (double)E*LN2;
     };
-    /* the normaliser: samples without data were multiplied in with sum = G exactly */
-    const double lnN_all = n_all ? total_log(NSET) - (double)n0*mm_log((double)G) + sl.lnN : 0.0;
-
+    /* the normaliser (lane 31, next to the allele sets of the other lanes): samples without data were multiplied in with sum = G exactly */
     double lk = 0; bool cand = false, in_sum = false; uint32_t mask = 0;
+    double tl = 0;
+    {
+        const bool set_lane = lane>=NALS && lane<NSUB && ((live >> (lane-NALS)) & 1u);
+        if ( n_all>0 && (lane==31 || set_lane) ) tl = total_log(lane==31 ? NSET : lane - NALS);
+    }
+    const double lnN_all = n_all ? __shfl_sync(0xffffffffu, tl, 31) - (double)n0*LOG_G + sl.lnN : 0.0;
     if ( lane < NALS )
     {
         long long ps = 0;
@@ -466,7 +476,7 @@ static __device__ __noinline__ void mm_epilogue(MMShared<NALS,BLOCK> *shp, const
         double slk = 0;
         #pragma unroll 1
         for (int j=0; j<NSET; j++) if ( j==k ) slk = sl.lk[j];
-        lk = set ? (total_log(k) - (double)n0*su->logv0[k] + slk) - lnN_all : 0.0;
+        lk = set ? (tl - (double)n0*su->logv0[k] + slk) - lnN_all : 0.0;
         for (int j=0; j<nonref; j++) lk += a.theta;
         cand = set; in_sum = set;
     }
@@ -482,15 +492,26 @@ static __device__ __noinline__ void mm_epilogue(MMShared<NALS,BLOCK> *shp, const
     double second = (cand && lane!=best_lane) ? lk : -CUDART_INF;
     #pragma unroll
     for (int off=16; off; off>>=1) second = fmax(second, __shfl_xor_sync(0xffffffffu, second, off));
-    /* lk_sum = log sum exp over every evaluated set except {REF} (mcall.c:584, 614) */
+    /* lk_sum = log sum exp over every evaluated set except {REF} (mcall.c:584, 614), and with it
+     *     lse = logsumexp2(lk_sum, ref_lk) = log(1 + exp(lo - hi)) + hi          (mcall.c:573-579, 1554, 1640)
+     * With term = sum exp(lk - mx) and R = exp(ref_lk - mx) from the same round of exp(): exp(lo - hi) = min(term/R, R/term),
+     * so lanes 0 and 1 take log(term) and log(1 + e) side by side: three transcendental latencies on this warp's critical
+     * path (log of the products, exp, log) instead of five.  */
     double mx = in_sum ? lk : -CUDART_INF;
     #pragma unroll
     for (int off=16; off; off>>=1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, off));
-    double term = in_sum ? mm_exp(lk - mx) : 0.0;
+    const bool have_sum = mx > -CUDART_INF;
+    const double ex = (cand && have_sum) ? mm_exp(lk - mx) : 0.0;
+    double term = in_sum ? ex : 0.0;
     #pragma unroll
     for (int off=16; off; off>>=1) term += __shfl_xor_sync(0xffffffffu, term, off);
-    const double grp_lk_sum = mx > -CUDART_INF ? mx + mm_log(term) : -CUDART_INF;
+    const double R = __shfl_sync(0xffffffffu, ex, 0);                   /* lane 0 = {REF} */
+    const double e = have_sum ? (term > R ? __ddiv_rn(R, term) : __ddiv_rn(term, R)) : 0.0;
+    double lg = 0;
+    if ( lane < 2 ) lg = mm_log(lane==0 ? term : __dadd_rn(1.0, e));
+    const double grp_lk_sum = have_sum ? mx + __shfl_sync(0xffffffffu, lg, 0) : -CUDART_INF;
     const double grp_ref_lk = __shfl_sync(0xffffffffu, lk, 0);
+    const double grp_lse = __shfl_sync(0xffffffffu, lg, 1) + (grp_lk_sum > grp_ref_lk ? grp_lk_sum : grp_ref_lk);
     const uint32_t grp_als = __shfl_sync(0xffffffffu, mask, best_lane & 31);
 
     if ( lane==0 )
@@ -501,7 +522,7 @@ static __device__ __noinline__ void mm_epilogue(MMShared<NALS,BLOCK> *shp, const
         double max_qual = -CUDART_INF, lk_sum = -CUDART_INF, ref_lk = -CUDART_INF;
         if ( any )          /* mcall.c:1553-1560 */
         {
-            max_qual = -4.343*(grp_ref_lk - mm_logsumexp2(grp_lk_sum, grp_ref_lk));
+            max_qual = -4.343*(grp_ref_lk - grp_lse);
             lk_sum = grp_lk_sum; ref_lk = grp_ref_lk;
         }
         const double gap = any ? best - second : CUDART_INF;
@@ -543,6 +564,7 @@ static __device__ __noinline__ void mm_epilogue(MMShared<NALS,BLOCK> *shp, const
         {
             a.ret[site] = 0;
             if ( a.site_flags ) a.site_flags[site] = flags;
+            if ( a.pl_off_out ) a.pl_off_out[site] = -1;
             sh.path = 0;
         }
         else
@@ -559,7 +581,7 @@ static __device__ __noinline__ void mm_epilogue(MMShared<NALS,BLOCK> *shp, const
             if ( ref_gt ) flags |= MCB_SITE_REF_GT;
             sh.path = path; sh.out_off = off; sh.site = site;
             sh.als_new = als_new; sh.nals_new = nals_new; sh.ref_gt = ref_gt; sh.flags = flags;
-            sh.max_qual = max_qual; sh.lk_sum = lk_sum; sh.ref_lk = ref_lk; sh.gap = gap;
+            sh.max_qual = max_qual; sh.lk_sum = lk_sum; sh.ref_lk = ref_lk; sh.gap = gap; sh.lse = grp_lse;
             /* selected alleles in ascending order and the genotypes they span: slot k = new genotype k */
             int sel[3] = {0,0,0}, ns = 0;
             #pragma unroll
@@ -637,13 +659,14 @@ static __device__ __noinline__ void mm_raw_pl_row(const int32_t *grow, int unsee
 }
 
 template<int NALS, int BLOCK>
-__global__ void __launch_bounds__(BLOCK, (BLOCK>=512 ? (MMGeom<NALS>::MINCTA+1)/2 : (BLOCK<=128 ? 2*MMGeom<NALS>::MINCTA : MMGeom<NALS>::MINCTA))) mcall_multi_kernel(const KArgs a)
+__global__ void __launch_bounds__(BLOCK, (MMGeom<NALS>::MINCTA*(256/BLOCK))) mcall_multi_kernel(const KArgs a)
 {
     using S = Shape<NALS>;
     using GE = MMGeom<NALS>;
     using SH = MMShared<NALS,BLOCK>;
-    constexpr int G = S::G, NPAIR = S::NPAIR, NTRI = S::NTRI, NSET = GE::NSET, NACC = NSET + 1, NW = BLOCK/32, RS = GE::RS;
+    constexpr int G = S::G, NPAIR = S::NPAIR, NTRI = S::NTRI, NSET = GE::NSET, NACC = GE::NACC, NW = BLOCK/32, RS = GE::RS;
     constexpr int TILE_BYTES = GE::TILE_BYTES;
+    static_assert(NACC <= 31 && NW >= 2, "one lane per product in the warp reduction; warp 1 prepares the next site");
     constexpr bool CF_REG = NALS<=3;            /* coefficients of the small shape live in registers */
 
     SH &sh = *reinterpret_cast<SH*>(mcb_smem);
@@ -652,9 +675,10 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK>=512 ? (MMGeom<NALS>::MINCTA+1)/
     const int ntw = warp < ntiles ? (ntiles - warp + NW - 1)/NW : 0;       /* tiles of this warp: warp, warp+NW, ... */
     const uint32_t sbase = smem_base();
     const uint32_t dyn_s = sbase + (uint32_t)align128(sizeof(SH));
-    const uint32_t ring_s = dyn_s + (uint32_t)(warp*nst*TILE_BYTES);
-    const uint32_t pack_s = dyn_s + (uint32_t)(NW*nst*TILE_BYTES);
-    const uint32_t sums_s = pack_s + (uint32_t)align128((size_t)spad*RS);
+    const int wreg = mm_warp_region(TILE_BYTES, GE::RED_BYTES, nst);       /* per-warp region: bulk-copy ring / warp-reduction scratch */
+    const uint32_t ring_s = dyn_s + (uint32_t)(warp*wreg);
+    const uint32_t pack_s = dyn_s + (uint32_t)(NW*wreg);
+    double *sums_g = a.mm_sums + (size_t)blockIdx.x*spad;                    /* per-CTA row of normalisers: rewritten every site, lives in L2 */
     const uint32_t bars_s = sbase + (uint32_t)offsetof(SH, bars) + (uint32_t)(warp*MM_MAX_NST*8);
     const uint32_t pl2p_s = sbase + (uint32_t)offsetof(SH, pl2p), thr_s = sbase + (uint32_t)offsetof(SH, gq_thr);
     const uint32_t slot_s = sbase + (uint32_t)offsetof(SH, slot_out);
@@ -677,23 +701,26 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK>=512 ? (MMGeom<NALS>::MINCTA+1)/
     __syncthreads();
     if ( warp==1 ) mm_setup<NALS>(&sh.setup[0], a, lane, nsites);
 
+    const uint32_t lane_row_s = ring_s + (uint32_t)(lane*2*G*4);
     int par = 0;
     /* the ring position of the next tile this warp consumes: the c-th tile a warp pushes through its ring uses stage
        c % nst and completes phase (c / nst) & 1 of that stage's barrier; kept incrementally, across sites */
     uint32_t stage = 0, parity = 0;
     bool prefetched = false;
 
+    /* every tile is 64 samples except the site's last one, which belongs to warp (ntiles-1) % NW as its tile number ntw-1 */
+    const uint32_t last_bytes = ((uint32_t)((nsmpl - (ntiles-1)*64)*G*4) + 15u) & ~15u;
+    const int j_short = ((ntiles-1) % NW)==warp ? ntw-1 : -1;
     auto issue = [&](const int32_t *site_pl, int j, uint32_t stg)      /* lane 0: tile j of this warp into ring stage stg */
     {
-        const int t = warp + j*NW;
-        const int n = min(64, nsmpl - t*64);
-        const uint32_t bytes = ((uint32_t)(n*G*4) + 15u) & ~15u;
+        const uint32_t bytes = j==j_short ? last_bytes : (uint32_t)TILE_BYTES;
         mbar_expect_tx(bars_s + 8*stg, bytes);
-        bulk_g2s(ring_s + stg*TILE_BYTES, site_pl + (size_t)t*64*G, bytes, bars_s + 8*stg);
+        bulk_g2s(ring_s + stg*TILE_BYTES, site_pl + (size_t)(warp + j*NW)*(64*G), bytes, bars_s + 8*stg);
     };
     auto issue_first = [&](const int32_t *site_pl)                      /* lane 0: the first tiles of a site, from the current ring position */
     {
         uint32_t stg = stage;
+        fence_proxy_async();                    /* the region was written through the generic proxy by the warp reduction */
         for (int j=0; j<nst && j<ntw; j++) { issue(site_pl, j, stg); if ( ++stg==(uint32_t)nst ) stg = 0; }
     };
 
@@ -711,11 +738,11 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK>=512 ? (MMGeom<NALS>::MINCTA+1)/
         if ( !prefetched && lane==0 ) issue_first(site_pl);
 
         /* =========================== phase 1: site reduction ==================================== */
-        double accM[NACC];
+        double accM[NACC]; int accE[NACC];
         int plsum[NALS];
-        int ndata = 0, n0 = 0;
+        int n0 = 0, since = 0;
         #pragma unroll
-        for (int k=0; k<NACC; k++) accM[k] = 1.0;
+        for (int k=0; k<NACC; k++) { accM[k] = 1.0; accE[k] = 0; }
         #pragma unroll
         for (int k=0; k<NALS; k++) plsum[k] = 0;
         double cfr[CF_REG ? NPAIR*3 + NTRI*6 : 1];
@@ -737,7 +764,7 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK>=512 ? (MMGeom<NALS>::MINCTA+1)/
             mbar_wait(bars_s + 8*stage, parity);
             const int sA = (warp + j*NW)*64 + 2*lane;           /* this lane's samples: sA, sA+1 */
             const bool valid = sA < nsmpl;
-            const uint32_t row_s = ring_s + stage*TILE_BYTES + (uint32_t)(lane*2*G*4);
+            const uint32_t row_s = lane_row_s + stage*TILE_BYTES;
             int x[2*G];
             if ( valid )
             {
@@ -767,10 +794,34 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK>=512 ? (MMGeom<NALS>::MINCTA+1)/
             for (int i=0; i<G; i++) { orA |= x[i]; orB |= x[G+i]; }
             if ( (unsigned)(orA | orB) > 255u )
             {
-                /* a missing / vector_end value or a PL >= 256 in this pair: both samples go to warp 0's list */
-                const int pos = atomicAdd(&sh.nesc, 2);
-                if ( pos + 1 < MM_ESC_CAP ) { sh.esc[pos] = (unsigned short)sA; sh.esc[pos+1] = (unsigned short)(sA+1); }
-                continue;
+                /* a missing / vector_end value or a PL >= 256: the int32 row goes on warp 0's list and the sample enters the
+                   loop below as a no-data sample (its constant factor is divided out with the other no-data samples) */
+                if ( (unsigned)orA > 255u )
+                {
+                    const int pos = atomicAdd(&sh.nesc, 1);
+                    if ( pos < MM_ESC_CAP )
+                    {
+                        sh.esc[pos] = (unsigned short)sA;
+                        #pragma unroll
+                        for (int i=0; i<G; i++) sh.esc_pl[pos][i] = x[i];
+                    }
+                    #pragma unroll
+                    for (int i=0; i<G; i++) asm volatile("mov.s32 %0, 0;" : "+r"(x[i]));      /* in place: the common path keeps its registers */
+                    orA = 0;
+                }
+                if ( (unsigned)orB > 255u )
+                {
+                    const int pos = atomicAdd(&sh.nesc, 1);
+                    if ( pos < MM_ESC_CAP )
+                    {
+                        sh.esc[pos] = (unsigned short)(sA+1);
+                        #pragma unroll
+                        for (int i=0; i<G; i++) sh.esc_pl[pos][i] = x[G+i];
+                    }
+                    #pragma unroll
+                    for (int i=0; i<G; i++) asm volatile("mov.s32 %0, 0;" : "+r"(x[G+i]));
+                    orB = 0;
+                }
             }
             double pA[G], pB[G];
             #pragma unroll
@@ -780,7 +831,6 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK>=512 ? (MMGeom<NALS>::MINCTA+1)/
             for (int i=1; i<G; i++) { sumA = __dadd_rn(sumA, pA[i]); sumB = __dadd_rn(sumB, pB[i]); }
             /* PL = 0,..,0: no data (mcall.c:529-537).  Such a sample is multiplied in like any other (its factor is a per-site
                constant that warp 0 divides out) and adds nothing to the integer sums. */
-            ndata += (orA!=0) + (orB!=0);
             n0 += (orA==0) + (orB==0);
             #pragma unroll
             for (int k=0; k<NALS; k++) plsum[k] += x[hom_idx(k)] + x[G+hom_idx(k)];    /* mcall.c:607-611 */
@@ -832,37 +882,75 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK>=512 ? (MMGeom<NALS>::MINCTA+1)/
             /* the byte-packed copy and the normalisers, for phase 2 */
             const uint32_t prow_s = pack_s + (uint32_t)(sA*RS);
             if constexpr ( NALS<=3 )
-                mm_sts128(prow_s, mm_pack4(x[0],x[1],x[2],x[3]), mm_pack4(x[4],x[5],0,0), mm_pack4(x[6],x[7],x[8],x[9]), mm_pack4(x[10],x[11],0,0));
+            {
+                mm_sts32(prow_s,      mm_pack4(x[0],x[1],x[2],x[3]));
+                mm_sts32(prow_s + 4u, mm_pack4(x[4],x[5],x[6],x[7]));
+                mm_sts32(prow_s + 8u, mm_pack4(x[8],x[9],x[10],x[11]));
+            }
             else if constexpr ( NALS==4 )
             {
-                mm_sts64(prow_s,       mm_pack4(x[0],x[1],x[2],x[3]),     mm_pack4(x[4],x[5],x[6],x[7]));
-                mm_sts64(prow_s + 8u,  mm_pack4(x[8],x[9],0,0),           mm_pack4(x[10],x[11],x[12],x[13]));
-                mm_sts64(prow_s + 16u, mm_pack4(x[14],x[15],x[16],x[17]), mm_pack4(x[18],x[19],0,0));
+                mm_sts32(prow_s,       mm_pack4(x[0],x[1],x[2],x[3]));
+                mm_sts32(prow_s + 4u,  mm_pack4(x[4],x[5],x[6],x[7]));
+                mm_sts32(prow_s + 8u,  mm_pack4(x[8],x[9],x[10],x[11]));
+                mm_sts32(prow_s + 12u, mm_pack4(x[12],x[13],x[14],x[15]));
+                mm_sts32(prow_s + 16u, mm_pack4(x[16],x[17],x[18],x[19]));
             }
             else
             {
                 mm_sts128(prow_s,       mm_pack4(x[0],x[1],x[2],x[3]),     mm_pack4(x[4],x[5],x[6],x[7]),     mm_pack4(x[8],x[9],x[10],x[11]),   mm_pack4(x[12],x[13],x[14],0));
                 mm_sts128(prow_s + 16u, mm_pack4(x[15],x[16],x[17],x[18]), mm_pack4(x[19],x[20],x[21],x[22]), mm_pack4(x[23],x[24],x[25],x[26]), mm_pack4(x[27],x[28],x[29],0));
             }
-            mm_sts_f64x2(sums_s + 8u*(uint32_t)sA, sumA, sumB);
+            asm volatile("st.global.cg.v2.f64 [%0], {%1,%2};" :: "l"(sums_g + sA), "d"(sumA), "d"(sumB) : "memory");
+            if ( ++since == MM_RENORM )         /* ten more samples in every product: split the exponents off before anything can underflow */
+            {
+                #pragma unroll
+                for (int k=0; k<NACC; k++) acc_renorm(accM[k], accE[k]);
+                since = 0;
+            }
         }
         prefetched = false;
 
-        /* ---- warp reduction: exponents are split off here, once (mantissa multiply, exponent add) */
+        /* ---- warp reduction through a shared-memory transpose (the warp's ring is idle: every tile was consumed, none is in
+                flight): lane k multiplies the 32 partial products of accumulator k (mantissa multiply, exponent add) */
         {
+            const uint32_t redM_s = ring_s, redE_s = ring_s + (uint32_t)(NACC*256);
             #pragma unroll
             for (int k=0; k<NACC; k++)
             {
-                double M = accM[k]; int E = 0;
-                acc_renorm(M, E);
+                acc_renorm(accM[k], accE[k]);
+                mm_sts_f64(redM_s + (uint32_t)(k*256 + lane*8), accM[k]);
+                mm_sts32(redE_s + (uint32_t)(k*128 + lane*4), (uint32_t)accE[k]);
+            }
+            __syncwarp();
+            {
+                /* lane (k, seg): accumulator k = lane % KPAD, partials [seg*KPAD, (seg+1)*KPAD) -- rotated by k so that the lanes of a
+                   segment start in different banks; the 32/KPAD segments are then combined with shuffles */
+                constexpr int KPAD = NACC<=8 ? 8 : (NACC<=16 ? 16 : 32);
+                const int k = lane & (KPAD-1), seg = lane / KPAD;
+                double M0 = 1.0, M1 = 1.0; int E = 0;
+                if ( k < NACC )
+                {
+                    #pragma unroll
+                    for (int i=0; i<KPAD; i+=2)
+                    {
+                        const int c0 = seg*KPAD + ((i + k) & (KPAD-1)), c1 = seg*KPAD + ((i + 1 + k) & (KPAD-1));
+                        M0 = __dmul_rn(M0, lds64(redM_s + (uint32_t)((k*32 + c0)*8)));
+                        M1 = __dmul_rn(M1, lds64(redM_s + (uint32_t)((k*32 + c1)*8)));
+                        E += lds32(redE_s + (uint32_t)((k*32 + c0)*4)) + lds32(redE_s + (uint32_t)((k*32 + c1)*4));
+                    }
+                }
+                double M = __dmul_rn(M0, M1);           /* at most 32 mantissas in [1,2) meet in one product: < 2^32 */
                 #pragma unroll
-                for (int off=16; off; off>>=1)
+                for (int off=KPAD; off<32; off<<=1)
                 {
                     M = __dmul_rn(M, __shfl_xor_sync(0xffffffffu, M, off));
                     E += __shfl_xor_sync(0xffffffffu, E, off);
                 }
-                acc_renorm(M, E);
-                if ( lane==0 ) { sh.red_M[warp][k] = M; sh.red_E[warp][k] = E; }
+                if ( lane < NACC )
+                {
+                    acc_renorm(M, E);
+                    sh.red_M[warp][lane] = M; sh.red_E[warp][lane] = E;
+                }
             }
             #pragma unroll
             for (int k=0; k<NALS; k++)
@@ -873,12 +961,12 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK>=512 ? (MMGeom<NALS>::MINCTA+1)/
                 if ( lane==0 ) sh.red_pls[warp][k] = v;
             }
             #pragma unroll
-            for (int off=16; off; off>>=1) { ndata += __shfl_xor_sync(0xffffffffu, ndata, off); n0 += __shfl_xor_sync(0xffffffffu, n0, off); }
-            if ( lane==0 ) { sh.red_cnt[warp][0] = ndata; sh.red_cnt[warp][1] = n0; }
+            for (int off=16; off; off>>=1) n0 += __shfl_xor_sync(0xffffffffu, n0, off);
+            if ( lane==0 ) sh.red_cnt[warp] = n0;
         }
         __syncthreads();            /* [B] */
 
-        if ( warp==0 ) mm_epilogue<NALS,BLOCK>(&sh, &su, a, lane, pl2p_s, pack_s, sums_s);
+        if ( warp==0 ) mm_epilogue<NALS,BLOCK>(&sh, &su, a, lane, pl2p_s, pack_s, sums_g);
         else if ( warp==1 )
         {
             if ( lane==0 ) sh.setup[par^1].isite = atomicAdd(a.work_counter, 1);
@@ -903,11 +991,13 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK>=512 ? (MMGeom<NALS>::MINCTA+1)/
             int2 *out_gt = reinterpret_cast<int2*>(a.gt) + (size_t)sh.site*nsmpl;
             int32_t *out_gq = a.gq + (size_t)sh.site*nsmpl;
             int called = 0;
+            double ns0 = 0, ns1 = 0;            /* the normalisers of the next iteration are fetched (from L2) one iteration ahead */
+            if ( tid < npair ) mm_ldg_f64x2(sums_g + 2*tid, ns0, ns1);
             #pragma unroll 1
             for (int pr=tid; pr<npair; pr+=BLOCK)
             {
-                double s0, s1;
-                mm_lds_f64x2(sums_s + 16u*(uint32_t)pr, s0, s1);
+                const double s0 = ns0, s1 = ns1;
+                if ( pr + BLOCK < npair ) mm_ldg_f64x2(sums_g + 2*(pr + BLOCK), ns0, ns1);
                 const bool has0 = s0 > 0 && s0 != (double)G, has1 = s1 > 0 && s1 != (double)G;
                 const int g0 = has0 ? MCB_GT_UNPHASED(0) : MCB_GT_MISSING, g1 = has1 ? MCB_GT_UNPHASED(0) : MCB_GT_MISSING;
                 called += (int)has0 + (int)has1;
@@ -926,12 +1016,14 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK>=512 ? (MMGeom<NALS>::MINCTA+1)/
             const double q0 = sh.q[0], q1 = sh.q[1], q1x2 = __dmul_rn(2.0, q1);
             const uint32_t j0 = (uint32_t)sh.jgt[0], j1 = (uint32_t)sh.jgt[1], j2 = (uint32_t)sh.jgt[2];
             int f_alt = 0, f_called = 0;
+            double ns0 = 0, ns1 = 0;
+            if ( tid < npair ) mm_ldg_f64x2(sums_g + 2*tid, ns0, ns1);
             #pragma unroll 1
             for (int pr=tid; pr<npair; pr+=BLOCK)
             {
                 const uint32_t rA = pack_s + (uint32_t)(pr*2*RS), rB = rA + RS;
-                double s0, s1;
-                mm_lds_f64x2(sums_s + 16u*(uint32_t)pr, s0, s1);
+                const double s0 = ns0, s1 = ns1;
+                if ( pr + BLOCK < npair ) mm_ldg_f64x2(sums_g + 2*(pr + BLOCK), ns0, ns1);
                 const uint32_t a0 = mm_ldsu8(rA + j0), b0 = mm_ldsu8(rA + j1), c0 = mm_ldsu8(rA + j2);
                 const uint32_t a1 = mm_ldsu8(rB + j0), b1 = mm_ldsu8(rB + j1), c1 = mm_ldsu8(rB + j2);
                 int k0, k1, g0, g1;
@@ -966,13 +1058,15 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK>=512 ? (MMGeom<NALS>::MINCTA+1)/
             uint32_t jg[6];
             #pragma unroll
             for (int k=0; k<6; k++) jg[k] = (uint32_t)sh.jgt[k];
-            unsigned long long acc = 0;     /* AC: 12-bit counters, new allele j at bits [12j,12j+12); <= 2*10 per thread */
+            unsigned long long acc = 0;     /* AC: 12-bit counters, new allele j at bits [12j,12j+12); the launcher keeps samples per thread <= 40 */
+            double ns0 = 0, ns1 = 0;
+            if ( tid < npair ) mm_ldg_f64x2(sums_g + 2*tid, ns0, ns1);
             #pragma unroll 1
             for (int pr=tid; pr<npair; pr+=BLOCK)
             {
                 const uint32_t rA = pack_s + (uint32_t)(pr*2*RS), rB = rA + RS;
-                double s0, s1;
-                mm_lds_f64x2(sums_s + 16u*(uint32_t)pr, s0, s1);
+                const double s0 = ns0, s1 = ns1;
+                if ( pr + BLOCK < npair ) mm_ldg_f64x2(sums_g + 2*(pr + BLOCK), ns0, ns1);
                 uint32_t vA[6], vB[6];
                 #pragma unroll
                 for (int k=0; k<6; k++) { vA[k] = mm_ldsu8(rA + jg[k]); vB[k] = mm_ldsu8(rB + jg[k]); }
@@ -1031,8 +1125,8 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK>=512 ? (MMGeom<NALS>::MINCTA+1)/
 template<int NALS, int BLOCK> static size_t mm_smem(int nsmpl, int nst)
 {
     const int ntiles = (nsmpl + 63) >> 6, spad = ntiles*64;
-    return align128(sizeof(MMShared<NALS,BLOCK>)) + (size_t)(BLOCK/32)*nst*MMGeom<NALS>::TILE_BYTES
-         + align128((size_t)spad*MMGeom<NALS>::RS) + (size_t)spad*8;
+    return align128(sizeof(MMShared<NALS,BLOCK>)) + (size_t)(BLOCK/32)*mm_warp_region(MMGeom<NALS>::TILE_BYTES, MMGeom<NALS>::RED_BYTES, nst)
+         + align128((size_t)spad*MMGeom<NALS>::RS);
 }
 template<int NALS, int BLOCK> static cudaError_t mm_launch(const KArgs *a, int nsmpl, int nst, int grid, cudaStream_t st, size_t *smem_out, int *nb)
 {
@@ -1050,9 +1144,9 @@ template<int NALS> static cudaError_t mm_dispatch(int block, const KArgs *a, int
 {
     switch ( block )
     {
+        case 64:  return mm_launch<NALS,64>(a, nsmpl, nst, grid, st, smem_out, nb);
         case 128: return mm_launch<NALS,128>(a, nsmpl, nst, grid, st, smem_out, nb);
         case 256: return mm_launch<NALS,256>(a, nsmpl, nst, grid, st, smem_out, nb);
-        case 512: return mm_launch<NALS,512>(a, nsmpl, nst, grid, st, smem_out, nb);
     }
     return cudaErrorInvalidValue;
 }
@@ -1067,15 +1161,14 @@ static cudaError_t mm_dispatch_nals(int nals, int block, const KArgs *a, int nsm
     return cudaErrorInvalidValue;
 }
 
-/*  CTA size for a sample count: a thread multiplies at most 10 samples into its plain products (see the header),
- *  i.e. 5 pairs of samples per lane.  0: the sample count is out of this kernel's range.  */
+/*  Smallest CTA size for a sample count: the 12-bit allele counters of phase 2 allow 40 samples per thread.  0: the sample
+ *  count is out of this kernel's range (odd, too small to fill two warps, too large for the shared-memory copy).  */
 int multi_block_for(int nsmpl)
 {
-    if ( nsmpl & 1 ) return 0;
-    if ( nsmpl < 256 ) return 0;
-    if ( nsmpl <= 1280 ) return 128;
-    if ( nsmpl <= 2560 ) return 256;
-    if ( nsmpl <= 5120 ) return 512;
+    if ( (nsmpl & 1) || nsmpl < 128 ) return 0;
+    if ( nsmpl <= 2560 ) return 64;
+    if ( nsmpl <= 5120 ) return 128;
+    if ( nsmpl <= 10240 ) return 256;
     return 0;
 }
 size_t multi_smem_bytes(int nals, int block, int nsmpl, int nst)
@@ -1084,6 +1177,7 @@ size_t multi_smem_bytes(int nals, int block, int nsmpl, int nst)
     if ( mm_dispatch_nals(nals, block, nullptr, nsmpl, nst, 0, nullptr, &smem, nullptr)!=cudaSuccess ) return 0;
     return smem;
 }
+size_t multi_scratch_bytes(int nsmpl, int grid) { return (size_t)grid*(size_t)(((nsmpl + 63) >> 6)*64)*sizeof(double); }
 cudaError_t multi_kernel_occupancy(int nals, int block, int nsmpl, int nst, int *blocks_per_sm)
 {
     return mm_dispatch_nals(nals, block, nullptr, nsmpl, nst, 0, nullptr, nullptr, blocks_per_sm);

@@ -12,7 +12,7 @@ class B200Call(C.Structure):
                 ("ploidy", C.c_void_p), ("unseen", C.c_uint8), ("nsmpl_grp", C.c_int),
                 ("grp_off", C.c_void_p), ("grp_smpl", C.c_void_p), ("use_prior", C.c_int),
                 ("max_records", C.c_int), ("max_nals", C.c_int), ("device", C.c_int), ("bcf_typed", C.c_int),
-                ("batcher", C.c_void_p)]
+                ("async_flush", C.c_int), ("batcher", C.c_void_p)]
 
 
 class B200Rec(C.Structure):
@@ -29,8 +29,8 @@ class B200Out(C.Structure):
                 ("gts8", C.POINTER(C.c_int8)), ("GQs8", C.POINTER(C.c_int8)), ("PLs16", C.POINTER(C.c_int16))]
 
 
-HOST_EXPORTS = ["b200_mcall_init", "b200_mcall", "b200_mcall_flush", "b200_mcall_result", "b200_mcall_destroy",
-                "b200_set_error_handler"]
+HOST_EXPORTS = ["b200_mcall_init", "b200_mcall", "b200_mcall_flush", "b200_mcall_flush_async", "b200_mcall_wait", "b200_mcall_result",
+                "b200_mcall_n_ploidy", "b200_mcall_destroy", "b200_set_error_handler"]
 
 
 def _lib():
@@ -39,8 +39,9 @@ def _lib():
     L.b200_mcall_init.restype = None
     L.b200_mcall.argtypes = [C.POINTER(B200Call), C.POINTER(B200Rec)]
     L.b200_mcall.restype = C.c_int
-    L.b200_mcall_flush.argtypes = [C.POINTER(B200Call)]
-    L.b200_mcall_flush.restype = C.c_int
+    for f in (L.b200_mcall_flush, L.b200_mcall_flush_async, L.b200_mcall_wait, L.b200_mcall_n_ploidy):
+        f.argtypes = [C.POINTER(B200Call)]
+        f.restype = C.c_int
     L.b200_mcall_result.argtypes = [C.POINTER(B200Call), C.c_int, C.POINTER(B200Out)]
     L.b200_mcall_result.restype = C.c_int
     L.b200_mcall_destroy.argtypes = [C.POINTER(B200Call)]
@@ -56,7 +57,7 @@ def _widen(a, bits):
     return o
 
 
-def replay(params, batch, ploidy_tab=None, max_records=64, typed=False):
+def replay(params, batch, ploidy_tab=None, max_records=64, typed=False, async_flush=False, stats=None):
     """Feed a HostBatch record by record through b200_mcall (like vcfcall.c:1089-1148 feeds mcall) and collect the
     results into an abi.HostResult laid out like the C-ABI's, so that the usual comparison helpers apply.
     typed=True: b200_call_t.bcf_typed -- PL goes in as the int8/int16 typed vector a BCF record would hold (int8 when
@@ -73,6 +74,7 @@ def replay(params, batch, ploidy_tab=None, max_records=64, typed=False):
         call.grp_off, call.grp_smpl = params.grp_off.ctypes.data, params.grp_smpl.ctypes.data
     call.use_prior, call.max_records, call.max_nals, call.device = int(params.use_prior), max_records, params.max_nals, params.device
     call.bcf_typed = int(typed)
+    call.async_flush = int(async_flush)
     L.b200_mcall_init(C.byref(call))
     res = abi.HostResult(batch, want_gp=bool(params.output_tags & abi.CALL_FMT_GP))
     done = [0]
@@ -145,9 +147,13 @@ def replay(params, batch, ploidy_tab=None, max_records=64, typed=False):
             n = L.b200_mcall(C.byref(call), C.byref(rec))
             if n:
                 collect(n)
-        n = L.b200_mcall_flush(C.byref(call))
-        if n:
+        while True:         # drains the batch in flight (async) and the partial last batch
+            n = L.b200_mcall_flush(C.byref(call))
+            if n <= 0:
+                break
             collect(n)
+        if stats is not None:
+            stats["n_ploidy"] = L.b200_mcall_n_ploidy(C.byref(call))
     finally:
         L.b200_mcall_destroy(C.byref(call))
     assert done[0] == batch.nsites

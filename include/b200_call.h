@@ -43,6 +43,8 @@ typedef struct
     int      bcf_typed;         /* 1: BCF typed vectors both ways: FORMAT/PL is handed over as the record's own
                                    int8/int16 vector (b200_rec_t.PL_typed, e.g. bcf_fmt_t.p or b200_bcf_fmt_t.p) and GT / GQ / PL
                                    come back as int8 / int8 / int16 vectors (b200_out_t.gts8 / GQs8 / PLs16); pooled calling only */
+    int      async_flush;       /* 1: a full batch is handed to the GPU in the background and b200_mcall keeps queuing into the second
+                                   slab set; the results it then reports are those of the PREVIOUS batch (see b200_mcall_flush_async) */
     /* ---- owned by this layer ---- */
     b200_batcher_t *batcher;
 }
@@ -88,10 +90,22 @@ void b200_set_error_handler(void (*handler)(const char *msg));
 
 void b200_mcall_init(b200_call_t *call);                            /* = mcall_init, vcfcall.c:697-698 */
 /*  = mcall(), vcfcall.c:1136-1137, batched: queues the record.  Returns the number of results that became
- *  available (0 while the batch is filling, the batch size after an automatic flush).                     */
+ *  available: 0 while the batch is filling; after an automatic flush the size of the batch just run (async_flush = 0)
+ *  or of the batch that was in flight before it (async_flush = 1, 0 the first time).  Results stay valid until the
+ *  next call that returns results.                                                                               */
 int  b200_mcall(b200_call_t *call, const b200_rec_t *rec);
-int  b200_mcall_flush(b200_call_t *call);                           /* run the partial batch; returns results available */
-int  b200_mcall_result(b200_call_t *call, int i, b200_out_t *out);  /* i-th result of the last flush, in input order */
+/*  Two slab sets: one batch runs on the GPU (a worker thread inside this layer drives mcb_call_host) while the driver
+ *  fills the other, the way vcfcall.c:1089-1148 keeps reading while earlier records are written.
+ *    b200_mcall_flush_async  waits for the batch in flight (if any; its results become current and their number is
+ *                            returned, else 0), then starts the queued records in the background and returns at once.
+ *    b200_mcall_wait         waits for the batch in flight; returns the number of its results (0: nothing was in flight).
+ *    b200_mcall_flush        = flush_async, then wait if that returned nothing.  `while ((n = b200_mcall_flush(c)) > 0) consume(n);`
+ *                            drains everything in either mode; with async_flush = 0 it is the old synchronous flush.        */
+int  b200_mcall_flush_async(b200_call_t *call);
+int  b200_mcall_wait(b200_call_t *call);
+int  b200_mcall_flush(b200_call_t *call);
+int  b200_mcall_result(b200_call_t *call, int i, b200_out_t *out);  /* i-th current result, in input order */
+int  b200_mcall_n_ploidy(const b200_call_t *call);                  /* distinct ploidy vectors registered so far (id 0 = all diploid included) */
 void b200_mcall_destroy(b200_call_t *call);                         /* = mcall_destroy, vcfcall.c:722-723 */
 
 #ifdef __cplusplus

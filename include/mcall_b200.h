@@ -63,10 +63,12 @@ extern "C" {
 #define MCB_SITE_NO_QS        (1u<<4)   /* nqs<=0: reference would error() out (mcall.c:1457) */
 #define MCB_SITE_PL_RANGE      (1u<<6)   /* a PL > 2500 was seen: likelihoods underflow, parity with the reference not guaranteed */
 #define MCB_SITE_BAD_PRIOR     (1u<<7)   /* -F: AN < sum(AC); the reference error()s out (mcall.c:1523) */
-#define MCB_SITE_UNSUPPORTED   (1u<<8)   /* site shape not covered by the device kernels (n_allele==0) */
+#define MCB_SITE_UNSUPPORTED   (1u<<8)   /* site shape not covered by the device kernels (n_allele==0, n_allele > max_nals, > 5 alleles with int16 PLs) */
 #define MCB_SITE_REF_GT       (1u<<5)   /* genotypes come from mcall_set_ref_genotypes (mcall.c:1582,1587): no GQ/GP written */
 
-typedef struct mcb_ctx mcb_ctx;     /* opaque; one per GPU, used from one host thread (like call_t) */
+typedef struct mcb_ctx mcb_ctx;     /* opaque; one per GPU, used from one host thread (like call_t).  Calls on one context
+                                       must be stream-ordered: mcb_call_device shares work lists and scratch between calls,
+                                       so two calls on different streams need an event (or a sync) between them */
 
 /*  What mcall_init() reads from call_t (mcall.c:361-417).  */
 typedef struct mcb_params
@@ -91,7 +93,11 @@ mcb_params;
  *  G_i = A_i(A_i+1)/2 diploid genotypes; its PL block is pl + pl_off[i], laid out
  *  [nsmpl][G_i] row-major exactly as bcf_get_format_int32 returns it (mcall.c:1444),
  *  short vectors padded with MCB_INT32_VECTOR_END.  pl_off[i] must be a multiple of 4
- *  (16-byte alignment for bulk copies); the tail padding is never read.               */
+ *  (16-byte alignment for bulk copies), and the bytes between the end of a site's block and
+ *  the next 16-byte boundary must be READABLE (bulk copies round a tile up to 16 bytes;
+ *  their content is ignored) -- also behind the last site of the slab.
+ *  nals[i] must not exceed params.max_nals: mcb_call_host returns MCB_EINVAL, mcb_call_device
+ *  reports the site as skipped with MCB_SITE_UNSUPPORTED.                               */
 typedef struct mcb_batch
 {
     int32_t  nsites;
@@ -151,7 +157,9 @@ void mcb_destroy(mcb_ctx *ctx);
 
 /*  Register a ploidy vector (values 0/1/2): what set_ploidy() writes into call->ploidy
  *  (vcfcall.c:807-825).  Few distinct vectors exist (one per ploidy region), sites refer
- *  to them by id.  id 0 defaults to all-diploid.                                        */
+ *  to them by id.  id 0 defaults to all-diploid.  Registering a NEW id uploads that one row and
+ *  does not wait for work in flight; re-defining an id that earlier batches used synchronises
+ *  the device first.                                                                    */
 int  mcb_set_ploidy(mcb_ctx *ctx, int id, const uint8_t *ploidy);
 
 /* ---- the hot path (mcall) -------------------------------------------------------------------

@@ -1,6 +1,6 @@
 """Dump per-instruction executed counts of one kernel from an .ncu-rep and summarise basic blocks."""
 import csv, subprocess, sys, io
-rep, kidx = sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else 0
+rep, kidx = sys.argv[1], (sys.argv[2] if len(sys.argv) > 2 else '0')
 out = sys.argv[3] if len(sys.argv) > 3 else "/tmp/sass.txt"
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
@@ -12,7 +12,8 @@ for r in rows:
         cur['hdr'] = r; continue
     if cur is not None and 'hdr' in cur and len(r) >= len(cur['hdr']) - 2:
         cur['rows'].append(r)
-s = sections[kidx]
+sections = [x for x in sections if 'hdr' in x and x['rows']]
+s = sections[int(kidx)] if kidx.isdigit() else [x for x in sections if kidx in x['name']][0]
 idx = {h: i for i, h in enumerate(s['hdr'])}
 lines = []
 with open(out, "w") as fh:

@@ -342,13 +342,13 @@ def test_bcf_typed_outputs(compact, int16_in, oracle_built):
 
 
 @pytest.mark.parametrize("flag", [0, abi.CALL_VARONLY])
-@pytest.mark.parametrize("S", [256, 300, 1000, 1280, 1282, 2504, 2560, 4000])
+@pytest.mark.parametrize("S", [128, 130, 300, 1000, 1280, 1282, 2504, 2560, 4000, 6000])
 def test_multi_allelic_kernel(S, flag, oracle_built):
     """The CTA-per-site kernel of the 3-5 allele classes (mcall_multi.cu): sample counts around its 64-sample warp tiles
-    and its three CTA sizes (128 / 256 / 512 threads), adversarial PLs -- missing and partially missing rows (the list
-    warp 0 evaluates), zero QS entries (dead allele sets), unseen alleles and PL >= 256 (sites handed back to the general
-    kernel through the fallback list) -- compacted and in-place PL output, every ring depth; compared with the oracle
-    and with the general tiled kernel."""
+    and its three CTA sizes (64 / 128 / 256 threads), adversarial PLs -- missing and partially missing rows (the list
+    warp 0 evaluates; more than 32 of them hand the site back to the general kernel through the fallback list), zero QS
+    entries (dead allele sets), unseen alleles and PL >= 256 (fallback list again) -- compacted and in-place PL output,
+    every ring depth; compared with the oracle and with the general tiled kernel."""
     from bcftools_b200 import mcall
     rng = np.random.default_rng([S, flag, 23])
     R = 60 if S > 1500 else 120
@@ -356,6 +356,13 @@ def test_multi_allelic_kernel(S, flag, oracle_built):
     for i in range(0, R, 5):            # PL >= 256 on some sites
         blk = batch.site_pl(i)
         blk[rng.integers(0, S, 3), rng.integers(0, blk.shape[1], 3)] = 300
+    for i in range(3, R, 4):            # a handful of special rows per site (the bench workload's shape): the list stays below its 32 entries
+        blk = batch.site_pl(i)
+        sp = (blk < 0).any(1)
+        keep = rng.choice(np.where(sp)[0], size=min(int(sp.sum()), 7), replace=False) if sp.any() else []
+        fix = sp.copy(); fix[keep] = False
+        blk[fix] = rng.integers(0, 256, (int(fix.sum()), blk.shape[1]))
+        blk[fix, 0] = 0
     for i in range(1, R, 4):            # clean sites: every pair on the fast path, every allele live
         blk = batch.site_pl(i)
         blk[...] = rng.integers(0, 256, blk.shape)
@@ -376,7 +383,8 @@ def test_multi_allelic_kernel(S, flag, oracle_built):
         batch.unseen[i] = 0
     params = abi.CallParams(S, 5, flag=flag, output_tags=abi.CALL_FMT_GQ)
     exp, _ = oracle_built.call("port", params, batch, None)     # PL >= 256 next to missing values: undefined in the reference (mcall.c:522)
-    for opts, compact in (({}, False), ({"mm_nst": 1}, True), ({"mm_nst": 4}, False), ({"multi": 0}, True)):
+    for opts, compact in (({}, False), ({"mm_nst": 1, "mm_block": 64}, True), ({"mm_nst": 3, "mm_block": 256}, False), ({"mm_nst": 4, "mm_block": 128}, True),
+                          ({"multi": 0}, True)):
         with mcall.MCaller(params, options=opts) as mc:
             got = mc.call_host(batch, compact=compact)
         st = parity.compare(got, exp, params)
