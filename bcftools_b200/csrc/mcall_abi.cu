@@ -576,17 +576,16 @@ static int enqueue(mcb_ctx *ctx, const mcb_batch *b, const mcb_result *r, int32_
         if ( fork ) CK(cudaStreamWaitEvent(cs, ctx->cev_fork, 0));
         /*  3-5 alleles, int32 PLs, every sample diploid, GT + GQ + PL requested: the CTA-per-site kernel of mcall_multi.cu.
          *  Sites it has no straight-line code for come back on a fallback list, which the general kernel below walks.  */
-        bool multi = false;
         if ( nals>=3 && ctx->opt_multi && !ctx->opt_block && !ctx->opt_block_c[nals] && pl_es==4 && !ploidy && !gpk && a.gt && a.gq && a.out_pl && !(a.flag & MCB_CALL_KEEPALT)
              && (a.output_tags & (MCB_CALL_FMT_GQ|MCB_CALL_FMT_GP))
              && !((reinterpret_cast<uintptr_t>(a.gt) | reinterpret_cast<uintptr_t>(a.gq) | reinterpret_cast<uintptr_t>(a.out_pl)) & 15) )
         {
             /* CTA size: explicit option, else the class default (sweeps in profiles/), never below what the 12-bit allele counters allow */
             const int minblock = multi_block_for(a.nsmpl);
-            int mblock = ctx->opt_mm_block_c[nals] ? (int)ctx->opt_mm_block_c[nals] : (ctx->opt_mm_block ? (int)ctx->opt_mm_block : (nals==3 ? 64 : 128));
+            int mblock = ctx->opt_mm_block_c[nals] ? (int)ctx->opt_mm_block_c[nals] : (ctx->opt_mm_block ? (int)ctx->opt_mm_block : 128);
             if ( !minblock ) mblock = 0;
             else mblock = std::max(mblock, minblock);
-            int nst = ctx->opt_mm_nst_c[nals] ? (int)ctx->opt_mm_nst_c[nals] : (ctx->opt_mm_nst ? (int)ctx->opt_mm_nst : (nals==5 ? 1 : 2));
+            int nst = ctx->opt_mm_nst_c[nals] ? (int)ctx->opt_mm_nst_c[nals] : (ctx->opt_mm_nst ? (int)ctx->opt_mm_nst : (nals==4 ? 1 : 2));
             const size_t cap = 227u*1024u;
             while ( mblock && nst>1 && multi_smem_bytes(nals, mblock, a.nsmpl, nst) > cap ) nst--;
             if ( mblock && multi_smem_bytes(nals, mblock, a.nsmpl, nst) <= cap )
@@ -620,7 +619,6 @@ static int enqueue(mcb_ctx *ctx, const mcb_batch *b, const mcb_result *r, int32_
                         return cuda_fail(ctx, le, what);
                     }
                     launches++;
-                    multi = true;
                     /* the general kernel now walks the fallback list only */
                     a.site_list = am.fb_list; a.site_count = am.fb_count;
                     a.work_counter = counts + NCLASS + 16 + nals;

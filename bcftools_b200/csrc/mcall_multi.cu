@@ -38,14 +38,15 @@ namespace mcb {
 #define MM_ESC_CAP   32             /* samples per site that may take the general path (one lane of warp 0 each) */
 #define MM_RENORM    5              /* iterations (pairs of samples per lane) between exponent splits of the running products */
 #define MM_MAX_NST   4              /* ring stages per warp */
-#ifndef MM_MINCTA3
-#define MM_MINCTA3 2
+/*  resident threads per SM each instance is compiled for (the register cap is 65536 / threads)  */
+#ifndef MM_THREADS3
+#define MM_THREADS3 512
 #endif
-#ifndef MM_MINCTA4
-#define MM_MINCTA4 2
+#ifndef MM_THREADS4
+#define MM_THREADS4 512
 #endif
-#ifndef MM_MINCTA5
-#define MM_MINCTA5 1
+#ifndef MM_THREADS5
+#define MM_THREADS5 256
 #endif
 
 template<int NALS> struct MMGeom
@@ -54,7 +55,7 @@ template<int NALS> struct MMGeom
     static constexpr int RS = NALS<=3 ? 6 : (NALS==4 ? 10 : 16);       /* bytes per sample of the packed copy */
     static constexpr int TILE_BYTES = 64*G*4;                           /* one warp tile: 64 samples of int32 PLs */
     static constexpr int NSET = Shape<NALS>::NPAIR + Shape<NALS>::NTRI;
-    static constexpr int MINCTA = NALS==3 ? MM_MINCTA3 : (NALS==4 ? MM_MINCTA4 : MM_MINCTA5);    /* CTAs of 256 threads per SM */
+    static constexpr int THREADS = NALS==3 ? MM_THREADS3 : (NALS==4 ? MM_THREADS4 : MM_THREADS5);
     static constexpr int NACC = NSET + 1;
     static constexpr int RED_BYTES = NACC*32*12;                        /* warp reduction: one (mantissa, exponent) per lane and product */
 };
@@ -111,9 +112,22 @@ __device__ __forceinline__ void mm_lds_f64x2(uint32_t a, double &x, double &y)
 {
     asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(x), "=d"(y) : "r"(a));
 }
-__device__ __forceinline__ void mm_ldg_f64x2(const double *p, double &x, double &y)       /* L2 only: the row is rewritten every site */
+/*  The per-CTA row of normalisers is rewritten every site and read back ~50 us later, while PL blocks and results stream through
+ *  L2 at several TB/s: without a hint the row is evicted before its reuse (ncu: its reads all went to DRAM).  evict_last keeps it.  */
+__device__ __forceinline__ uint64_t mm_policy_evict_last() { uint64_t p; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p; }
+__device__ __forceinline__ uint64_t mm_policy_evict_first() { uint64_t p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p; }
+__device__ __forceinline__ void mm_ldg_f64x2(const double *p, double &x, double &y, uint64_t pol)
 {
-    asm volatile("ld.global.cg.v2.f64 {%0,%1}, [%2];" : "=d"(x), "=d"(y) : "l"(p) : "memory");
+    asm volatile("ld.global.cg.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;" : "=d"(x), "=d"(y) : "l"(p), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void mm_stg_f64x2(double *p, double x, double y, uint64_t pol)
+{
+    asm volatile("st.global.cg.L2::cache_hint.v2.f64 [%0], {%1,%2}, %3;" :: "l"(p), "d"(x), "d"(y), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void mm_bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar, uint64_t pol)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 :: "r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(pol) : "memory");
 }
 __device__ __forceinline__ int2 mm_lds64i(uint32_t a)
 {
@@ -130,10 +144,10 @@ __device__ __forceinline__ void mm_sts_f64(uint32_t a, double x) { asm volatile(
 __device__ __forceinline__ uint32_t mm_ldsu8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ void mm_stg128(void *p, int x, int y, int z, int w)
 {
-    asm volatile("st.global.v4.s32 [%0], {%1,%2,%3,%4};" :: "l"(p), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+    asm volatile("st.global.cs.v4.s32 [%0], {%1,%2,%3,%4};" :: "l"(p), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");     /* results stream out: evict first */
 }
-__device__ __forceinline__ void mm_stg64(void *p, int x, int y) { asm volatile("st.global.v2.s32 [%0], {%1,%2};" :: "l"(p), "r"(x), "r"(y) : "memory"); }
-__device__ __forceinline__ void mm_stg32(void *p, int x) { asm volatile("st.global.s32 [%0], %1;" :: "l"(p), "r"(x) : "memory"); }
+__device__ __forceinline__ void mm_stg64(void *p, int x, int y) { asm volatile("st.global.cs.v2.s32 [%0], {%1,%2};" :: "l"(p), "r"(x), "r"(y) : "memory"); }
+__device__ __forceinline__ void mm_stg32(void *p, int x) { asm volatile("st.global.cs.s32 [%0], %1;" :: "l"(p), "r"(x) : "memory"); }
 __device__ __forceinline__ uint32_t mm_pack4(int a, int b, int c, int d) { return (uint32_t)a | (uint32_t)b<<8 | (uint32_t)c<<16 | (uint32_t)d<<24; }
 
 static __device__ __noinline__ double mm_log(double x) { return log(x); }
@@ -233,7 +247,7 @@ static __device__ __noinline__ void mm_slow_sample(const int *row, const MMSetup
     }
     for (int j=0; j<RS; j++)
         asm volatile("st.shared.u8 [%0], %1;" :: "r"(row_s + (uint32_t)j), "r"((data && j<G) ? pl[j] : 0) : "memory");
-    asm volatile("st.global.cg.f64 [%0], %1;" :: "l"(sum_g), "d"(sum) : "memory");
+    asm volatile("st.global.cg.L2::cache_hint.f64 [%0], %1, %2;" :: "l"(sum_g), "d"(sum), "l"(mm_policy_evict_last()) : "memory");
 }
 
 /*  qsum (mcall.c:1454-1464), -F prior (1507-1527), normalisation (1530-1535) by lane 0, then the allele-set
@@ -659,7 +673,7 @@ static __device__ __noinline__ void mm_raw_pl_row(const int32_t *grow, int unsee
 }
 
 template<int NALS, int BLOCK>
-__global__ void __launch_bounds__(BLOCK, (MMGeom<NALS>::MINCTA*(256/BLOCK))) mcall_multi_kernel(const KArgs a)
+__global__ void __launch_bounds__(BLOCK, (MMGeom<NALS>::THREADS/BLOCK > 0 ? MMGeom<NALS>::THREADS/BLOCK : 1)) mcall_multi_kernel(const KArgs a)
 {
     using S = Shape<NALS>;
     using GE = MMGeom<NALS>;
@@ -702,6 +716,7 @@ __global__ void __launch_bounds__(BLOCK, (MMGeom<NALS>::MINCTA*(256/BLOCK))) mca
     if ( warp==1 ) mm_setup<NALS>(&sh.setup[0], a, lane, nsites);
 
     const uint32_t lane_row_s = ring_s + (uint32_t)(lane*2*G*4);
+    const uint64_t pol_last = mm_policy_evict_last(), pol_first = mm_policy_evict_first();
     int par = 0;
     /* the ring position of the next tile this warp consumes: the c-th tile a warp pushes through its ring uses stage
        c % nst and completes phase (c / nst) & 1 of that stage's barrier; kept incrementally, across sites */
@@ -715,7 +730,7 @@ __global__ void __launch_bounds__(BLOCK, (MMGeom<NALS>::MINCTA*(256/BLOCK))) mca
     {
         const uint32_t bytes = j==j_short ? last_bytes : (uint32_t)TILE_BYTES;
         mbar_expect_tx(bars_s + 8*stg, bytes);
-        bulk_g2s(ring_s + stg*TILE_BYTES, site_pl + (size_t)(warp + j*NW)*(64*G), bytes, bars_s + 8*stg);
+        mm_bulk_g2s(ring_s + stg*TILE_BYTES, site_pl + (size_t)(warp + j*NW)*(64*G), bytes, bars_s + 8*stg, pol_first);     /* PL blocks are read once */
     };
     auto issue_first = [&](const int32_t *site_pl)                      /* lane 0: the first tiles of a site, from the current ring position */
     {
@@ -900,7 +915,7 @@ __global__ void __launch_bounds__(BLOCK, (MMGeom<NALS>::MINCTA*(256/BLOCK))) mca
                 mm_sts128(prow_s,       mm_pack4(x[0],x[1],x[2],x[3]),     mm_pack4(x[4],x[5],x[6],x[7]),     mm_pack4(x[8],x[9],x[10],x[11]),   mm_pack4(x[12],x[13],x[14],0));
                 mm_sts128(prow_s + 16u, mm_pack4(x[15],x[16],x[17],x[18]), mm_pack4(x[19],x[20],x[21],x[22]), mm_pack4(x[23],x[24],x[25],x[26]), mm_pack4(x[27],x[28],x[29],0));
             }
-            asm volatile("st.global.cg.v2.f64 [%0], {%1,%2};" :: "l"(sums_g + sA), "d"(sumA), "d"(sumB) : "memory");
+            mm_stg_f64x2(sums_g + sA, sumA, sumB, pol_last);
             if ( ++since == MM_RENORM )         /* ten more samples in every product: split the exponents off before anything can underflow */
             {
                 #pragma unroll
@@ -992,12 +1007,12 @@ __global__ void __launch_bounds__(BLOCK, (MMGeom<NALS>::MINCTA*(256/BLOCK))) mca
             int32_t *out_gq = a.gq + (size_t)sh.site*nsmpl;
             int called = 0;
             double ns0 = 0, ns1 = 0;            /* the normalisers of the next iteration are fetched (from L2) one iteration ahead */
-            if ( tid < npair ) mm_ldg_f64x2(sums_g + 2*tid, ns0, ns1);
+            if ( tid < npair ) mm_ldg_f64x2(sums_g + 2*tid, ns0, ns1, pol_last);
             #pragma unroll 1
             for (int pr=tid; pr<npair; pr+=BLOCK)
             {
                 const double s0 = ns0, s1 = ns1;
-                if ( pr + BLOCK < npair ) mm_ldg_f64x2(sums_g + 2*(pr + BLOCK), ns0, ns1);
+                if ( pr + BLOCK < npair ) mm_ldg_f64x2(sums_g + 2*(pr + BLOCK), ns0, ns1, pol_last);
                 const bool has0 = s0 > 0 && s0 != (double)G, has1 = s1 > 0 && s1 != (double)G;
                 const int g0 = has0 ? MCB_GT_UNPHASED(0) : MCB_GT_MISSING, g1 = has1 ? MCB_GT_UNPHASED(0) : MCB_GT_MISSING;
                 called += (int)has0 + (int)has1;
@@ -1017,13 +1032,13 @@ __global__ void __launch_bounds__(BLOCK, (MMGeom<NALS>::MINCTA*(256/BLOCK))) mca
             const uint32_t j0 = (uint32_t)sh.jgt[0], j1 = (uint32_t)sh.jgt[1], j2 = (uint32_t)sh.jgt[2];
             int f_alt = 0, f_called = 0;
             double ns0 = 0, ns1 = 0;
-            if ( tid < npair ) mm_ldg_f64x2(sums_g + 2*tid, ns0, ns1);
+            if ( tid < npair ) mm_ldg_f64x2(sums_g + 2*tid, ns0, ns1, pol_last);
             #pragma unroll 1
             for (int pr=tid; pr<npair; pr+=BLOCK)
             {
                 const uint32_t rA = pack_s + (uint32_t)(pr*2*RS), rB = rA + RS;
                 const double s0 = ns0, s1 = ns1;
-                if ( pr + BLOCK < npair ) mm_ldg_f64x2(sums_g + 2*(pr + BLOCK), ns0, ns1);
+                if ( pr + BLOCK < npair ) mm_ldg_f64x2(sums_g + 2*(pr + BLOCK), ns0, ns1, pol_last);
                 const uint32_t a0 = mm_ldsu8(rA + j0), b0 = mm_ldsu8(rA + j1), c0 = mm_ldsu8(rA + j2);
                 const uint32_t a1 = mm_ldsu8(rB + j0), b1 = mm_ldsu8(rB + j1), c1 = mm_ldsu8(rB + j2);
                 int k0, k1, g0, g1;
@@ -1060,13 +1075,13 @@ __global__ void __launch_bounds__(BLOCK, (MMGeom<NALS>::MINCTA*(256/BLOCK))) mca
             for (int k=0; k<6; k++) jg[k] = (uint32_t)sh.jgt[k];
             unsigned long long acc = 0;     /* AC: 12-bit counters, new allele j at bits [12j,12j+12); the launcher keeps samples per thread <= 40 */
             double ns0 = 0, ns1 = 0;
-            if ( tid < npair ) mm_ldg_f64x2(sums_g + 2*tid, ns0, ns1);
+            if ( tid < npair ) mm_ldg_f64x2(sums_g + 2*tid, ns0, ns1, pol_last);
             #pragma unroll 1
             for (int pr=tid; pr<npair; pr+=BLOCK)
             {
                 const uint32_t rA = pack_s + (uint32_t)(pr*2*RS), rB = rA + RS;
                 const double s0 = ns0, s1 = ns1;
-                if ( pr + BLOCK < npair ) mm_ldg_f64x2(sums_g + 2*(pr + BLOCK), ns0, ns1);
+                if ( pr + BLOCK < npair ) mm_ldg_f64x2(sums_g + 2*(pr + BLOCK), ns0, ns1, pol_last);
                 uint32_t vA[6], vB[6];
                 #pragma unroll
                 for (int k=0; k<6; k++) { vA[k] = mm_ldsu8(rA + jg[k]); vB[k] = mm_ldsu8(rB + jg[k]); }
