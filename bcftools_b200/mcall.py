@@ -19,6 +19,10 @@ EXPORTS = ["mcb_init", "mcb_destroy", "mcb_set_ploidy", "mcb_call_device", "mcb_
            "mcb_set_option", "mcb_version", "mcb_selftest_div", "mcb_get_kernel_times"]
 
 
+JOB_EXPORTS = ["mcb_job_init", "mcb_job_destroy", "mcb_job_ndevices", "mcb_job_set_ploidy", "mcb_job_set_option",
+               "mcb_job_call_host", "mcb_job_partition", "mcb_job_last_error"]
+
+
 class McallError(RuntimeError):
     pass
 
@@ -62,8 +66,83 @@ def lib():
         L.mcb_get_kernel_times.argtypes = [C.c_void_p, C.c_void_p]
         L.mcb_selftest_div.restype = C.c_int
         L.mcb_selftest_div.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64)]
+        L.mcb_job_init.restype = C.c_int
+        L.mcb_job_init.argtypes = [C.POINTER(C.c_void_p), C.POINTER(abi.McbParams), C.POINTER(C.c_int), C.c_int]
+        L.mcb_job_destroy.restype = None
+        L.mcb_job_destroy.argtypes = [C.c_void_p]
+        L.mcb_job_ndevices.restype = C.c_int
+        L.mcb_job_ndevices.argtypes = [C.c_void_p]
+        L.mcb_job_set_ploidy.restype = C.c_int
+        L.mcb_job_set_ploidy.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.mcb_job_set_option.restype = C.c_int
+        L.mcb_job_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int64]
+        L.mcb_job_call_host.restype = C.c_int
+        L.mcb_job_call_host.argtypes = [C.c_void_p, C.POINTER(abi.McbBatch), C.POINTER(abi.McbResult), C.c_void_p]
+        L.mcb_job_partition.restype = C.c_int
+        L.mcb_job_partition.argtypes = [C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
+        L.mcb_job_last_error.restype = C.c_char_p
+        L.mcb_job_last_error.argtypes = [C.c_void_p]
         _lib = L
     return _lib
+
+
+def partition(nsmpl, nals, nparts):
+    """mcb_job_partition: contiguous site ranges of about equal PL volume (host arithmetic of the product library)."""
+    nals = np.ascontiguousarray(nals, np.uint8)
+    first = np.zeros(nparts + 1, np.int32)
+    rc = lib().mcb_job_partition(int(nsmpl), nals.ctypes.data, len(nals), int(nparts), first.ctypes.data)
+    if rc != 0:
+        raise McallError(f"mcb_job_partition failed: {rc}")
+    return first
+
+
+class MJob:
+    """mcall_job.h: one job over several devices (contiguous site ranges, ordered results)."""
+
+    def __init__(self, params, devices, ploidy_tab=None, options=None):
+        self.params = params
+        self._job = C.c_void_p()
+        L = lib()
+        p = params.c_struct()
+        devs = (C.c_int * len(devices))(*[int(d) for d in devices])
+        rc = L.mcb_job_init(C.byref(self._job), C.byref(p), devs, len(devices))
+        if rc != 0:
+            msg = L.mcb_strerror(rc).decode()
+            if self._job:
+                msg += " / " + L.mcb_job_last_error(self._job).decode()
+                L.mcb_job_destroy(self._job)
+                self._job = C.c_void_p()
+            raise McallError(f"mcb_job_init failed: {msg}")
+        if ploidy_tab is not None:
+            tab = np.ascontiguousarray(ploidy_tab, np.uint8).reshape(-1, params.nsmpl)
+            for i in range(tab.shape[0]):
+                self._check(L.mcb_job_set_ploidy(self._job, i, tab[i].ctypes.data), "mcb_job_set_ploidy")
+        for k, v in (options or {}).items():
+            self._check(L.mcb_job_set_option(self._job, k.encode(), int(v)), f"mcb_job_set_option({k})")
+
+    def _check(self, rc, what):
+        if rc != 0:
+            L = lib()
+            raise McallError(f"{what} failed: {L.mcb_strerror(rc).decode()} / {L.mcb_job_last_error(self._job).decode()}")
+
+    def call_host(self, batch, result=None, want_gp=False, compact=False, typed=False):
+        res = result if result is not None else abi.HostResult(batch, want_gp=want_gp, compact=compact, typed=typed)
+        b, r = batch.c_struct(), res.c_struct()
+        first = np.zeros(lib().mcb_job_ndevices(self._job) + 1, np.int32)
+        self._check(lib().mcb_job_call_host(self._job, C.byref(b), C.byref(r), first.ctypes.data), "mcb_job_call_host")
+        res.first_site = first
+        return res
+
+    def close(self):
+        if self._job:
+            lib().mcb_job_destroy(self._job)
+            self._job = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
 
 
 def pinned_empty(shape, dtype):

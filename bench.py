@@ -13,7 +13,11 @@ synthetic sites replicated x4 in HBM = 65,536 sites, 2.9 GB of PL; the 1M-site j
   value     device-resident throughput: inputs already in HBM, CUDA events on the launching stream, max over ranks
   e2e       the same metric through the C-ABI host entry point mcb_call_host with pinned HOST buffers:
             H2D of the PL slab + kernels + D2H of GT/GQ/PL/site records inside the timed region
-  roofline  dominant kernel (mcall_biallelic_warp_kernel, the two-allele class): algorithmic bytes of its sites / its own device time
+  roofline  dominant kernel (mcall_biallelic_warp_kernel, the two-allele class): algorithmic bytes of its sites / its own device time;
+            roofline.per_class has the same figures for every allele-count class, roofline.all_kernels for the whole step
+  sustained the same step repeated for >= --sustain seconds with its own clock samples (the headline region lasts ~50 ms)
+  secondary BASELINE config 5 (mixed ploidy) pooled and with 5 -G groups, device-resident
+  job       N > 1 only: ONE C4-shaped job over all N GPUs through mcb_job_call_host (strong scaling; rank 0 drives it)
   cpu_baseline  the CPU oracle on this box's host cores on a bounded sample of the same workload (rank 0, N=1)
 
 The reference arm times the reference's own CPU implementation of the path (oracle/_ref = the unmodified mcall.c
@@ -146,6 +150,17 @@ class OraclePool:
             p.join(timeout=10)
 
 
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.lower().startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    import platform
+    return platform.processor() or platform.machine()
+
+
 def run_reference(args, rank):
     """`--impl reference`: the reference's own CPU implementation of the path on the host cores (rank 0 only)."""
     if rank != 0:
@@ -171,7 +186,8 @@ def run_reference(args, rank):
                 data="synthetic", config=dict(workload=WORKLOAD, nsmpl=params.nsmpl, sites_per_step=sites,
                                               note="bounded sample of the same synthetic workload; reference arithmetic is single-threaded "
                                                    "(--threads n/a, vcfcall.c:692), parallelised as one process per core over site shards"),
-                cpu_baseline=dict(value=value, unit=UNIT, cores=ncores, kind=kind, sample=f"{sites} sites x {params.nsmpl} samples per step"),
+                cpu_baseline=dict(value=value, unit=UNIT, cores=ncores, cpu_model=cpu_model(), threads_flag="--threads n/a (output compression only, vcfcall.c:692)",
+                                  kind=kind, sample=f"{sites} sites x {params.nsmpl} samples per step"),
                 e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line), flush=True)
 
@@ -195,17 +211,34 @@ def bind_to_gpu_numa_node(gpu_index):
     return 0
 
 
+def kernel_source_hash():
+    """sha256 over the CUDA sources: the committed ncu capture is only quoted when it was taken from these very kernels."""
+    import glob
+    import hashlib
+    h = hashlib.sha256()
+    csrc = os.path.join(ROOT, "bcftools_b200", "csrc")
+    for f in sorted(glob.glob(os.path.join(csrc, "*.cu")) + glob.glob(os.path.join(csrc, "*.cuh"))):
+        h.update(os.path.basename(f).encode())
+        h.update(open(f, "rb").read())
+    return h.hexdigest()[:16]
+
+
 def ncu_traffic(sites_per_step):
-    """DRAM bytes (read + write) of one launch of the dominant kernel, from the committed `ncu --set full` capture of this
-    same command (profiles/r01_ncu_dominant_kernel.json); None when the capture was taken on another step size."""
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_ncu_dominant_kernel.json")
+    """DRAM bytes (read + write) per launch of every class kernel, from the committed `ncu --set full` capture of this same
+    command (profiles/r02_ncu_kernels.json, written by scripts/ncu_kernels_json.py).  The capture is refused -- loudly --
+    when it was taken from other kernel sources or another step size."""
+    path = os.path.join(ROOT, "profiles", "r02_ncu_kernels.json")
     try:
         d = json.load(open(path))
     except (OSError, ValueError):
-        return None, "no ncu capture committed"
+        return {}, "no ncu capture committed"
     if d.get("sites_per_step") != sites_per_step:
-        return None, "ncu capture is for %s sites per step" % d.get("sites_per_step")
-    return int(d["dram_bytes_read"] + d["dram_bytes_write"]), d.get("source", path)
+        return {}, "ncu capture is for %s sites per step" % d.get("sites_per_step")
+    if d.get("kernel_source_hash") != kernel_source_hash():
+        sys.stderr.write("bench.py: profiles/r02_ncu_kernels.json was captured from other kernel sources (%s, now %s): traffic not quoted\n"
+                         % (d.get("kernel_source_hash"), kernel_source_hash()))
+        return {}, "STALE: the ncu capture predates the current kernel sources"
+    return {int(k): int(v["dram_bytes_read"] + v["dram_bytes_write"]) for k, v in d.get("classes", {}).items()}, d.get("source", path)
 
 
 def main():
@@ -219,6 +252,10 @@ def main():
     ap.add_argument("--e2e-sites", type=int, default=8192)
     ap.add_argument("--ref-sites", type=int, default=8192)
     ap.add_argument("--cpu-sites", type=int, default=2048)
+    ap.add_argument("--sustain", type=float, default=2.0, help="seconds of a second, long timed region (clocks under sustained load); 0 = off")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the C5 (mixed ploidy, -G groups) secondary workload")
+    ap.add_argument("--secondary-sites", type=int, default=2048)
+    ap.add_argument("--job-sites-per-gpu", type=int, default=48, help="N>1: C4-shaped sites per GPU of the one-job strong-scaling leg (rank 0 drives all N GPUs)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -272,6 +309,28 @@ def main():
     barrier()
     dev_s = e0.elapsed_time(e1) * 1e-3
     launches = int(mc.stats()[0]) * args.steps
+    # ---- sustained leg: the timed region above lasts ~50 ms at boost clocks; these kernels are issue-bound, so a long job
+    # runs at whatever clock the power limit settles on.  Same step, >= --sustain seconds, its own clock samples.
+    sustained = None
+    if args.sustain > 0:
+        nsteps_s = max(args.steps, int(args.sustain / max(dev_s / args.steps, 1e-6)) + 1)
+        s_samp = ClockSampler(local_rank)
+        s_samp.start()
+        barrier()
+        e0.record()
+        for _ in range(nsteps_s):
+            mc.call_device(b, r, stream)
+        e1.record()
+        barrier()
+        s_samp.stop_flag = True
+        s_samp.join(timeout=2)
+        sus_s = e0.elapsed_time(e1) * 1e-3
+        if world > 1:
+            t = torch.tensor([sus_s], device=f"cuda:{local_rank}", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            sus_s = float(t.item())
+        sustained = dict(value=world * nsteps_s * calls_per_step / sus_s, unit=UNIT, steps=nsteps_s, seconds=sus_s,
+                         ms_per_step=1e3 * sus_s / nsteps_s, clocks=s_samp.summary())
     # per-class kernel times of untimed extra steps for the roofline of the dominant kernel: the library serialises the
     # class kernels on the caller's stream and brackets each with events (in the timed region they run on their own
     # streams and overlap at the tails of their persistent grids)
@@ -374,6 +433,52 @@ def main():
                                           h2d_bytes_per_step=int(sub16.pl.nbytes + h2d - sub.pl.nbytes), d2h_bytes_per_step=int(d2ht),
                                           types="in: PL int16 (BCF_BT_INT16 as stored in the record); out: GT int8, GQ int8, PL int16, narrowed on the device")
 
+    # ---- secondary workload (rank 0): BASELINE config 5 -- every 2nd sample haploid -- pooled and with 5 -G groups, device-resident
+    secondary = None
+    if rank == 0 and not args.no_secondary:
+        secondary = {}
+        for name, groups in (("C5_pooled", 0), ("C5_groups5", 5)):
+            p5, h5, t5 = synth.make_batch("C5", args.secondary_sites, with_groups=groups)
+            p5.device = local_rank
+            with mcall.MCaller(p5, ploidy_tab=t5) as m5:
+                d5 = device.DeviceBatch(h5, device=f"cuda:{local_rank}", replicate=args.replicate)
+                r5 = device.DeviceResult(d5)
+                b5, rr5 = d5.c_struct(), r5.c_struct()
+                for _ in range(3):
+                    m5.call_device(b5, rr5, stream)
+                torch.cuda.synchronize()
+                e0.record()
+                for _ in range(5):
+                    m5.call_device(b5, rr5, stream)
+                e1.record()
+                torch.cuda.synchronize()
+                s5 = e0.elapsed_time(e1) * 1e-3 / 5
+                secondary[name] = dict(value=d5.nsites * p5.nsmpl / s5, unit=UNIT, ms_per_step=1e3 * s5, sites_per_step=d5.nsites, nsmpl=p5.nsmpl,
+                                       groups=groups, ploidy="every 2nd sample haploid")
+            del d5, r5
+
+    # ---- N > 1: ONE job over the N GPUs of the box (mcall_job.h): BASELINE config 4 shape (100,000 samples), contiguous site
+    # ranges, host buffers, results concatenated in input order.  Rank 0 drives all devices while the other ranks wait.
+    job = None
+    if world > 1:
+        barrier()
+        if rank == 0:
+            pj, hj, tj = synth.make_batch("C4", args.job_sites_per_gpu * world)
+            hj = mcall.pin_batch(hj)
+            rj = mcall.pin_result(abi.HostResult(hj, compact=True))
+            job = dict(workload="C4", nsmpl=pj.nsmpl, sites=hj.nsites, scaling="strong: one job, contiguous site ranges balanced by PL volume, ordered concatenation",
+                       h2d_bytes=int(hj.pl.nbytes))
+            for ndev in sorted({1, world}):
+                with mcall.MJob(pj, list(range(ndev))) as jb:
+                    jb.call_host(hj, rj)
+                    t0 = time.perf_counter()
+                    for _ in range(3):
+                        jb.call_host(hj, rj)
+                    dtj = (time.perf_counter() - t0) / 3
+                job["devices_%d" % ndev] = dict(value=hj.nsites * pj.nsmpl / dtj, unit=UNIT, ms_per_call=1e3 * dtj)
+            job["speedup"] = job["devices_%d" % world]["value"] / job["devices_1"]["value"]
+        barrier()
+
     # ---- max over ranks of the device time
     if world > 1:
         t = torch.tensor([dev_s], device=f"cuda:{local_rank}", dtype=torch.float64)
@@ -381,24 +486,36 @@ def main():
         dev_s = float(t.item())
     if rank == 0:
         peak, peak_src = measured_peak()
-        # dominant kernel = the biallelic site kernel: its sites' algorithmic bytes / its own device time
-        is2 = hb.nals == 2
-        sub2 = hb.subset(np.where(is2)[0]) if is2.any() else None
+        # per allele-count class: its sites' algorithmic bytes / its own device time; the dominant kernel is the two-allele one
+        traffic, traffic_src = ncu_traffic(db.nsites)
+        kernel_names = {2: "mcall_biallelic_warp_kernel", 3: "mcall_multi_kernel<3>", 4: "mcall_multi_kernel<4>", 5: "mcall_multi_kernel<5>"}
+        per_class = {}
+        for k in range(2, 6):
+            isk = hb.nals == k
+            if not isk.any() or ktimes[k] <= 0:
+                continue
+            idx = np.where(isk)[0]
+            subk = hb.subset(idx)
+            resk = abi.HostResult(subk)
+            resk.ret[...] = res.ret[idx]
+            resk.site_flags[...] = res.site_flags[idx]
+            rdk, wrk = synth.algorithmic_bytes(subk, resk, params.output_tags)
+            bk = (rdk + wrk) * args.replicate
+            achk = bk / (ktimes[k] * 1e-3) / 1e9
+            per_class[str(k)] = dict(kernel=kernel_names[k], sites=int(isk.sum()) * args.replicate, algorithmic_bytes_per_launch=int(bk), kernel_ms=float(ktimes[k]),
+                                     achieved=achk, frac=achk / peak, calls_per_s=float(isk.sum() * args.replicate * params.nsmpl / (ktimes[k] * 1e-3)),
+                                     traffic=traffic.get(k), traffic_over_algorithmic=(traffic[k] / bk if k in traffic else None))
         roof = None
-        if sub2 is not None and ktimes[2] > 0:
-            res2 = abi.HostResult(sub2)
-            idx = np.where(is2)[0]
-            res2.ret[...] = res.ret[idx]
-            res2.site_flags[...] = res.site_flags[idx]
-            rd2, wr2 = synth.algorithmic_bytes(sub2, res2, params.output_tags)
-            bytes2 = (rd2 + wr2) * args.replicate
-            ach = bytes2 / (ktimes[2] * 1e-3) / 1e9
-            traffic, traffic_src = ncu_traffic(db.nsites)
-            roof = dict(bound="hbm", kernel="mcall_biallelic_warp_kernel (the two-allele class: 70 % of the sites of a step)", achieved=ach, peak=peak,
-                        unit="GB/s", frac=ach / peak, traffic=traffic, traffic_source=traffic_src, peak_source=peak_src,
-                        algorithmic_bytes_per_launch=int(bytes2),
+        if "2" in per_class:
+            c2 = per_class["2"]
+            roof = dict(bound="hbm", kernel="mcall_biallelic_warp_kernel (the two-allele class: 70 % of the sites of a step)", achieved=c2["achieved"], peak=peak,
+                        unit="GB/s", frac=c2["frac"], traffic=c2["traffic"], traffic_source=traffic_src, peak_source=peak_src,
+                        algorithmic_bytes_per_launch=c2["algorithmic_bytes_per_launch"],
                         kernel_ms=float(ktimes[2]), kernel_share_of_step=float(ktimes[2] / ktimes[0]),
+                        per_class=per_class,
                         all_kernels=dict(achieved=(rd_all + wr_all) * args.replicate / (ktimes[0] * 1e-3) / 1e9,
+                                         frac=(rd_all + wr_all) * args.replicate / (ktimes[0] * 1e-3) / 1e9 / peak,
+                                         frac_timed_region=(rd_all + wr_all) * args.replicate / (dev_s / args.steps) / 1e9 / peak,
                                          ms_per_class={str(k): float(ktimes[k]) for k in range(1, 6)}))
         value = world * args.steps * calls_per_step / dev_s
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(3, args.warmup),
@@ -408,7 +525,8 @@ def main():
                                 replicate=args.replicate, allele_mix="2:70%,3:20%,4:7%,5:3%", flags="call -m -a GQ",
                                 l2_policy="inputs larger than L2 (%.2f GB of PL per step)" % (db.pl_bytes() / 1e9),
                                 bytes_per_call=(rd_all + wr_all) / (hb.nsites * params.nsmpl), generator_version=synth.GENERATOR_VERSION),
-                    gpu_launches=launches, clocks=sampler.summary(), roofline=roof, cpu_baseline=cpu, e2e=e2e, parity=parity)
+                    gpu_launches=launches, clocks=sampler.summary(), roofline=roof, cpu_baseline=cpu, e2e=e2e, parity=parity,
+                    sustained=sustained, secondary=secondary, job=job)
         print(json.dumps(line, default=lambda o: o.item() if hasattr(o, 'item') else str(o)), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -35,6 +35,17 @@ def test_host_layer_symbols_are_exported():
     assert all(hasattr(L, s) for s in syms)
 
 
+def test_job_layer_symbols_are_exported():
+    """include/mcall_job.h: one job over N devices."""
+    from bcftools_b200 import mcall
+    hdr = open(os.path.join(ROOT, "include", "mcall_job.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    syms = sorted(set(re.findall(r"\b(mcb_job_[a-z0-9_]+)\s*\(", hdr)))
+    L = mcall.lib()
+    assert syms == sorted(mcall.JOB_EXPORTS), syms
+    assert all(hasattr(L, s) for s in syms)
+
+
 def test_struct_layouts_match_header():
     """ctypes mirrors must have the field order of the C structs (a mismatch would silently scramble pointers)."""
     from bcftools_b200 import abi

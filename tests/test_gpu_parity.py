@@ -458,3 +458,34 @@ def test_host_batcher_bcf_typed_replays_reference_goldens(name):
         pytest.skip("PL beyond int16")
     res = host_call.replay(params, batch, tab, max_records=16, typed=True)
     assert golden_util.check_against_expect(case, params, batch, res) == len(case["expect"])
+
+
+@pytest.mark.parametrize("name", golden_util.case_names())
+def test_async_host_batcher_replays_reference_goldens(name):
+    """b200_call_t.async_flush: two slab sets, the batch in flight runs on the batcher's worker thread while records are
+    queued into the other set; results arrive one batch late and must still come back complete and in input order."""
+    from bcftools_b200 import host_call
+    params, batch, tab, case = golden_util.load_case(name)
+    if any(s.get("qs") is None for s in case["sites"]) and params.ngroups <= 1:
+        pytest.skip("no QS")
+    res = host_call.replay(params, batch, tab, max_records=5, async_flush=True)
+    assert golden_util.check_against_expect(case, params, batch, res) == len(case["expect"])
+
+
+@pytest.mark.parametrize("async_flush", [False, True])
+def test_host_batcher_registers_each_distinct_ploidy_vector_once(async_flush, oracle_built):
+    """chrX-style alternation (PAR / non-PAR): 1,000 records switch between two ploidy vectors; the batcher must end with
+    two registered vectors (ids are looked up by content), and the calls must equal the oracle's."""
+    from bcftools_b200 import host_call
+    S = 24
+    rng = np.random.default_rng(77)
+    batch = parity.random_batch(rng, 1000, S, 3, minA=2, miss=False)
+    tab = np.full((2, S), 2, np.uint8)
+    tab[1, ::2] = 1
+    batch.ploidy_id = (np.arange(1000) % 2).astype(np.uint16)
+    params = abi.CallParams(S, 3, output_tags=abi.CALL_FMT_GQ)
+    exp, _ = oracle_built.call(ORACLE(oracle_built), params, batch, tab)
+    st = {}
+    res = host_call.replay(params, batch, tab, max_records=37, async_flush=async_flush, stats=st)
+    assert st["n_ploidy"] == 2, st
+    assert parity.compare(res, exp, params)["compared"] > 0
