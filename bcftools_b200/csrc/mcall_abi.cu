@@ -362,7 +362,7 @@ extern "C" int mcb_selftest_div(mcb_ctx *ctx, int mode, uint64_t n, uint64_t see
     unsigned long long *d = nullptr;
     CK(cudaMalloc(&d, 8));
     CK(cudaMemset(d, 0, 8));
-    if ( mode==0 ) n = 1ull<<24;
+    if ( mode==0 || mode==20 || mode==21 ) n = 1ull<<24;
     CK(launch_selftest_div(ctx->d_tab, mode, n, seed, d, 0));
     CK(cudaDeviceSynchronize());
     unsigned long long h = 0;

@@ -52,6 +52,7 @@ struct BWRec                            /* written by lane 0 after phase 1, read
     int4   hap_out[2];                  /* haploid call of selected allele x: {gt0, vector_end, AC[0] increment, AC[1] increment} */
     double q[2];                        /* (double)qsum of the selected alleles, mcall.c:797, 820 */
     double max_qual, lk_sum, ref_lk, gap;
+    float  scr_w[4];                    /* float32 screen of phase 2: weights of the slots 0/0, 0/1, 1/1; [3] != 0: the site stays on the literal path */
     float  qf[2];
     uint32_t flags, als_new;
     int    nsel, jgt0, inc_dip, inc_hap, nals_new, ret_early, pl_dropped, ref_gt;
@@ -61,12 +62,23 @@ struct BWRec                            /* written by lane 0 after phase 1, read
     unsigned short esc[BW_ESC_CAP];     /* their sample indices */
 };
 static_assert(sizeof(BWRec) <= BW_REC_BYTES, "BWRec grew past its slot");
+static_assert(offsetof(BWRec, scr_w) % 16 == 0, "scr_w is read with one 128-bit load");
 
 struct BWTables
 {
     double pl2p[256];
     double gq_thr[130];
+    ScreenTabs scr;                     /* float32 screen of phase 2 (mcall_device.cuh) */
 };
+
+/*  the literal FP64 call of one diploid sample of a pair site from its packed bytes: the samples the float32 screen does not accept  */
+static __device__ __noinline__ int bw_fast2_exact(uint32_t a, uint32_t b, uint32_t c, double q0, double q1, uint32_t pl2p_s, uint32_t thr_s)      /* slot | GQ << 8 */
+{
+    const double p0 = lds64c(pl2p_s + 8u*a), p1 = lds64c(pl2p_s + 8u*b), p2 = lds64c(pl2p_s + 8u*c);
+    int k, g;
+    fast2_call(p0, p1, p2, __dadd_rn(__dadd_rn(p0, p1), p2), q0, q1, __dmul_rn(2.0, q1), thr_s, k, g);
+    return k | g<<8;
+}
 
 /*  set_pdg's missing-value fill (mcall.c:495-527) on the 3 PLs of a biallelic sample; returns 0 for "no data"  */
 __device__ __noinline__ int fix_missing3(int *pl, int unseen)
@@ -176,6 +188,9 @@ __device__ __forceinline__ int4 bw_call_haploid(double pA, double pB, double sum
 }
 
 
+#ifndef BW_SCREEN
+#define BW_SCREEN    1                  /* 1: float32 screen in front of the literal FP64 call (0: every sample takes the literal path) */
+#endif
 #ifndef BW_FAST2
 #define BW_FAST2     1                  /* 1: straight-line phase 2 for the common variant site, two adjacent samples per lane */
 #endif
@@ -237,6 +252,9 @@ __global__ void __launch_bounds__(BW_MAXWARP*32, BW_MINCTA) mcall_biallelic_warp
 
     for (int i=tid; i<256; i+=blockDim.x) tb.pl2p[i] = a.tab->pl2p[i];
     for (int i=tid; i<130; i+=blockDim.x) tb.gq_thr[i] = i<128 ? a.tab->gq_thr[i] : -1.0;
+    screen_tabs_fill(&tb.scr, a.tab, tid, blockDim.x);
+    const uint32_t plf_s = sbase + (uint32_t)offsetof(BWTables, scr) + (uint32_t)offsetof(ScreenTabs, plf);
+    const uint32_t gqw_s = sbase + (uint32_t)offsetof(BWTables, scr) + (uint32_t)offsetof(ScreenTabs, gqw);
     __syncthreads();
 
     const int S = a.nsmpl;
@@ -578,6 +596,11 @@ __global__ void __launch_bounds__(BW_MAXWARP*32, BW_MINCTA) mcall_biallelic_warp
                     }
                 }
                 rec.inc_dip = inc_dip; rec.inc_hap = inc_hap;
+                {
+                    bool scr = ns==2 && BW_SCREEN;
+                    rec.scr_w[0] = screen_weight(rec.q[0], rec.q[0], 1.0, scr); rec.scr_w[1] = screen_weight(rec.q[1], rec.q[0], 2.0, scr);
+                    rec.scr_w[2] = screen_weight(rec.q[1], rec.q[1], 1.0, scr); rec.scr_w[3] = scr ? 0.f : 1.f;
+                }
                 rec.slot_out[3] = make_int4(MCB_GT_MISSING, MCB_GT_MISSING, 0, 0);
             }
         }
@@ -619,7 +642,11 @@ __global__ void __launch_bounds__(BW_MAXWARP*32, BW_MINCTA) mcall_biallelic_warp
             const bool fastp = PLOIDY && pair_ok && inc_hap==3;
             if ( fast2 )
             {
-                const double q1x2 = __dmul_rn(2.0, c.q1);
+                /* float32 screen (mcall_device.cuh): the arg max and the GQ of a sample far from every decision boundary need no
+                   double precision; the few samples it does not accept take the literal sequence */
+                float w0, w1, w2, wn;
+                asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(w0), "=f"(w1), "=f"(w2), "=f"(wn) : "r"(wbase_s + (uint32_t)offsetof(BWRec, scr_w)));
+                const bool noscr = wn != 0.f;
                 const int npair = S >> 1;
                 #pragma unroll 1
                 for (int pr=lane; pr<npair; pr+=32)
@@ -630,16 +657,12 @@ __global__ void __launch_bounds__(BW_MAXWARP*32, BW_MINCTA) mcall_biallelic_warp
                     int32_t *dpl = out_pl + 6*(size_t)pr;       /* escaped samples: placeholders, rewritten after the loop */
                     stg64(dpl, (int)pa0, (int)pb0); stg64(dpl + 2, (int)pc0, (int)pa1); stg64(dpl + 4, (int)pb1, (int)pc1);
                     int k0, k1, q0, q1;
-                    {
-                        const double p0 = lds64c(pl2p_s + 8u*pa0), p1 = lds64c(pl2p_s + 8u*pb0), p2 = lds64c(pl2p_s + 8u*pc0);
-                        fast2_call(p0, p1, p2, __dadd_rn(__dadd_rn(p0, p1), p2), c.q0, c.q1, q1x2, thr_s, k0, q0);
-                    }
-                    {
-                        const double p0 = lds64c(pl2p_s + 8u*pa1), p1 = lds64c(pl2p_s + 8u*pb1), p2 = lds64c(pl2p_s + 8u*pc1);
-                        fast2_call(p0, p1, p2, __dadd_rn(__dadd_rn(p0, p1), p2), c.q0, c.q1, q1x2, thr_s, k1, q1);
-                    }
+                    const bool ok0 = screen2_call(pa0, pb0, pc0, w0, w1, w2, plf_s, gqw_s, k0, q0);
+                    const bool ok1 = screen2_call(pa1, pb1, pc1, w0, w1, w2, plf_s, gqw_s, k1, q1);
                     const bool has0 = (pa0 | pb0 | pc0) != 0, has1 = (pa1 | pb1 | pc1) != 0;     /* PL=0,0,0: no data (mcall.c:529-537) */
                     const bool esc0 = (pa0 & pb0 & pc0) == 255u, esc1 = (pa1 & pb1 & pc1) == 255u;
+                    if ( (!ok0 || noscr) && has0 && !esc0 ) { const int e = bw_fast2_exact(pa0, pb0, pc0, c.q0, c.q1, pl2p_s, thr_s); k0 = e & 255; q0 = e >> 8; }
+                    if ( (!ok1 || noscr) && has1 && !esc1 ) { const int e = bw_fast2_exact(pa1, pb1, pc1, c.q0, c.q1, pl2p_s, thr_s); k1 = e & 255; q1 = e >> 8; }
                     const int4 o0 = lds128(c.slot_s + 16u*(uint32_t)((has0 && !esc0) ? k0 : 3));
                     const int4 o1 = lds128(c.slot_s + 16u*(uint32_t)((has1 && !esc1) ? k1 : 3));
                     ac0 += o0.z + o1.z; ac1 += o0.w + o1.w;

@@ -1141,8 +1141,68 @@ __global__ void selftest_div_kernel(const DevTables *tab, int mode, unsigned lon
     }
     if ( bad ) atomicAdd(mismatch, bad);
 }
+/*  float32 screen self-test (mcall_device.cuh): every accepted sample must carry the slot and GQ of the literal FP64 sequence.
+ *  mode 20/21: pair sites, all 256^3 PL triples, q1 = 10^(-seed/8), q0 = 1 - q1 (as floats): 20 counts accepted samples that
+ *  differ, 21 counts rejected ones.  mode 22/23: triple sites, n random PL sextuples, q1 and q2 from the seed.  */
+__global__ void selftest_screen_kernel(const DevTables *tab, int mode, unsigned long long n, unsigned long long seed, unsigned long long *count)
+{
+    __shared__ ScreenTabs st;
+    __shared__ double s_pl2p[256], s_thr[130];
+    for (int i=threadIdx.x; i<256; i+=blockDim.x) s_pl2p[i] = tab->pl2p[i];
+    for (int i=threadIdx.x; i<130; i+=blockDim.x) s_thr[i] = i<128 ? tab->gq_thr[i] : -1.0;
+    screen_tabs_fill(&st, tab, threadIdx.x, blockDim.x);
+    __syncthreads();
+    const uint32_t plf_s = smem_u32(st.plf), gqw_s = smem_u32(st.gqw), thr_s = smem_u32(s_thr);
+    const bool triple = mode >= 22;
+    const float q1f = (float)exp10(-(double)(seed & 63)/8.0), q2f = triple ? (float)exp10(-(double)((seed >> 6) & 63)/8.0) : 0.f;
+    float q0f = 1.f - q1f - q2f;
+    const float qs = q0f + q1f + q2f;
+    const double q0 = (double)(q0f/qs), q1 = (double)(q1f/qs), q2 = (double)(q2f/qs);
+    bool scr = true;
+    float w[6];
+    w[0] = screen_weight(q0, q0, 1.0, scr); w[1] = screen_weight(q1, q0, 2.0, scr); w[2] = screen_weight(q1, q1, 1.0, scr);
+    if ( triple ) { w[3] = screen_weight(q2, q0, 2.0, scr); w[4] = screen_weight(q2, q1, 2.0, scr); w[5] = screen_weight(q2, q2, 1.0, scr); }
+    unsigned long long bad = 0;
+    const unsigned long long stride = (unsigned long long)gridDim.x*blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x*blockDim.x + threadIdx.x; i<n; i += stride)
+    {
+        int ks, gs, ke, ge; bool ok;
+        if ( !triple )
+        {
+            const uint32_t a = i & 255, b = (i>>8) & 255, c = (i>>16) & 255;
+            ok = screen2_call(a, b, c, w[0], w[1], w[2], plf_s, gqw_s, ks, gs) && scr;
+            const double p0 = s_pl2p[a], p1 = s_pl2p[b], p2 = s_pl2p[c];
+            fast2_call(p0, p1, p2, __dadd_rn(__dadd_rn(p0, p1), p2), q0, q1, __dmul_rn(2.0, q1), thr_s, ke, ge);
+        }
+        else
+        {
+            unsigned long long x = (i + 1)*0x9E3779B97F4A7C15ull ^ (seed*0xD1B54A32D192ED03ull);
+            uint32_t v[6]; double p[6];
+            for (int j=0; j<6; j++)
+            {
+                x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull; x ^= x >> 27; x *= 0x94D049BB133111EBull; x ^= x >> 31;
+                v[j] = (x & 3) ? (uint32_t)((x>>8) & 255) : (uint32_t)((x>>8) & 15);
+                p[j] = s_pl2p[v[j]];
+            }
+            /* the normaliser of a multi-allelic sample also covers genotypes outside the triple */
+            double sum = p[0];
+            for (int j=1; j<6; j++) sum = __dadd_rn(sum, p[j]);
+            sum = __dadd_rn(sum, s_pl2p[(x>>40) & 255]);
+            ok = screen3_call(v, w, plf_s, gqw_s, ks, gs) && scr;
+            fast3_call(p, sum, q0, q1, q2, __dmul_rn(2.0, q1), __dmul_rn(2.0, q2), thr_s, ke, ge);
+        }
+        if ( mode & 1 ) bad += !ok;
+        else bad += ok && (ks != ke || gs != ge);
+    }
+    if ( bad ) atomicAdd(count, bad);
+}
 cudaError_t launch_selftest_div(const DevTables *tab, int mode, unsigned long long n, unsigned long long seed, unsigned long long *mismatch, cudaStream_t st)
 {
+    if ( mode >= 20 )
+    {
+        selftest_screen_kernel<<<148*8, 256, 0, st>>>(tab, mode, n, seed, mismatch);
+        return cudaGetLastError();
+    }
     selftest_div_kernel<<<148*8, 256, 0, st>>>(tab, mode, n, seed, mismatch);
     return cudaGetLastError();
 }

@@ -38,6 +38,9 @@ namespace mcb {
 #define MM_ESC_CAP   32             /* samples per site that may take the general path (one lane of warp 0 each) */
 #define MM_RENORM    5              /* iterations (pairs of samples per lane) between exponent splits of the running products */
 #define MM_MAX_NST   4              /* ring stages per warp */
+#ifndef MM_SCREEN
+#define MM_SCREEN    1              /* 1: float32 screen in front of the literal FP64 call of phase 2 (0: every sample takes the literal path) */
+#endif
 /*  resident threads per SM each instance is compiled for (the register cap is 65536 / threads)  */
 #ifndef MM_THREADS3
 #define MM_THREADS3 512
@@ -84,6 +87,8 @@ template<int NALS, int BLOCK> struct MMShared
     static constexpr int NW = BLOCK/32, NSET = MMGeom<NALS>::NSET, NACC = NSET + 1;
     double   pl2p[256];
     double   gq_thr[130];
+    ScreenTabs scr;                     /* float32 screen of phase 2 (mcall_device.cuh) */
+    float    scr_w[8];                  /* its weights of the slots 0..5; [6] != 0: this site stays on the literal path */
     uint64_t bars[NW][MM_MAX_NST];
     MMSetup<NALS> setup[2];
     /* phase-1 partials of every warp: products (mantissa, exponent), integer sums, counts */
@@ -615,49 +620,38 @@ static __device__ __noinline__ void mm_epilogue(MMShared<NALS,BLOCK> *shp, const
             }
             sh.slot_out[6] = make_int4(MCB_GT_MISSING, MCB_GT_MISSING, 0, 0);
             sh.slot_out[7] = make_int4(MCB_GT_MISSING, MCB_GT_MISSING, 0, 0);
+            if ( path>=2 )
+            {
+                bool scr = MM_SCREEN;
+                for (int x=0; x<3; x++)
+                    for (int y=0; y<=x; y++)
+                        sh.scr_w[x*(x+1)/2 + y] = x<path ? screen_weight(sh.q[x], sh.q[y], x==y ? 1.0 : 2.0, scr) : 0.f;
+                sh.scr_w[6] = scr ? 0.f : 1.f;
+            }
         }
         for (int j=0; j<8; j++) sh.ac[j] = 0;
         sh.nesc = 0;
     }
 }
 
-/*  mcall_call_genotypes + GQ (mcall.c:787-878) for one diploid sample of a site whose selected set is the triple
- *  {REF=s0, s1, s2} with exactly those alleles kept: the literal arithmetic of the general loop in mcall_kernels.cu
- *  (IEEE quotients through the shared reciprocal, products left to right, float32 round trip of every GP before max/sum),
- *  written without branches.  p[k] = pl2p[PL] of slot k = new genotype k: 0/0 0/1 1/1 0/2 1/2 2/2.  */
-__device__ __forceinline__ void fast3_call(const double (&p)[6], double sum, double q0, double q1, double q2, double q1x2, double q2x2,
-                                           uint32_t thr_s, int &bk, int &gq)
+/*  the literal FP64 call of one sample from its packed bytes and its normaliser: the samples the float32 screen does not accept.
+ *  q_s: shared address of the selected alleles' q[3].  Returns slot | GQ << 8.  */
+static __device__ __noinline__ int mm_fast2_exact(uint32_t a, uint32_t b, uint32_t c, double sum, uint32_t q_s, uint32_t pl2p_s, uint32_t thr_s)
 {
-    const double r = rcp_shared(sum);
-    const double g0 = __dmul_rn(__dmul_rn(div_shared(p[0], sum, r), q0), q0);
-    const double g2 = __dmul_rn(__dmul_rn(div_shared(p[2], sum, r), q1), q1);
-    const double g5 = __dmul_rn(__dmul_rn(div_shared(p[5], sum, r), q2), q2);
-    /* (2*pdg)*qa == pdg*(2*qa) bit for bit */
-    const double g1 = __dmul_rn(__dmul_rn(div_shared(p[1], sum, r), q1x2), q0);
-    const double g3 = __dmul_rn(__dmul_rn(div_shared(p[3], sum, r), q2x2), q0);
-    const double g4 = __dmul_rn(__dmul_rn(div_shared(p[4], sum, r), q2x2), q1);
-    /* homs in ascending allele order, then the hets (s1,s0), (s2,s0), (s2,s1); strict `<` (mcall.c:787-835) */
-    double best = 0.0 < g0 ? g0 : 0.0; int k = 0;
-    bool b;
-    b = best < g2; best = b ? g2 : best; k = b ? 2 : k;
-    b = best < g5; best = b ? g5 : best; k = b ? 5 : k;
-    b = best < g1; best = b ? g1 : best; k = b ? 1 : k;
-    b = best < g3; best = b ? g3 : best; k = b ? 3 : k;
-    b = best < g4; best = b ? g4 : best; k = b ? 4 : k;
-    bk = k;
-    /* mcall.c:843-878: max and sum over the float32 gps[] in new-genotype order */
-    const double f0 = (double)__double2float_rn(g0), f1 = (double)__double2float_rn(g1), f2 = (double)__double2float_rn(g2);
-    const double f3 = (double)__double2float_rn(g3), f4 = (double)__double2float_rn(g4), f5 = (double)__double2float_rn(g5);
-    const double gmax = (double)__double2float_rn(best);         /* float rounding is monotone */
-    const double gsum = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(f0, f1), f2), f3), f4), f5);
-    const double rs = rcp_shared(gsum);
-    const double xx = __dadd_rn(1.0, -div_shared(gmax, gsum, rs));
-    int kq = __float2int_rz(-3.0102999f*lg2_approx((float)xx));
-    kq = max(0, min(127, kq));
-    const double t0 = lds64c(thr_s + 8u*(uint32_t)kq), t1 = lds64c(thr_s + 8u*(uint32_t)kq + 8u);
-    kq += (xx <= t1) ? 1 : 0;
-    kq -= (xx > t0) ? 1 : 0;
-    gq = (xx==xx) ? kq : 127;           /* NaN (0/0): `max<=INT8_MAX` is false => INT8_MAX */
+    const double q0 = lds64(q_s), q1 = lds64(q_s + 8u);
+    int k, g;
+    fast2_call(lds64c(pl2p_s + 8u*a), lds64c(pl2p_s + 8u*b), lds64c(pl2p_s + 8u*c), sum, q0, q1, __dmul_rn(2.0, q1), thr_s, k, g);
+    return k | g<<8;
+}
+static __device__ __noinline__ int mm_fast3_exact(uint32_t row_s, uint32_t jgt_s, double sum, uint32_t q_s, uint32_t pl2p_s, uint32_t thr_s)
+{
+    const double q0 = lds64(q_s), q1 = lds64(q_s + 8u), q2 = lds64(q_s + 16u);
+    double p[6];
+    #pragma unroll
+    for (int k=0; k<6; k++) p[k] = lds64c(pl2p_s + 8u*mm_ldsu8(row_s + (uint32_t)lds32(jgt_s + 4u*k)));
+    int k, g;
+    fast3_call(p, sum, q0, q1, q2, __dmul_rn(2.0, q1), __dmul_rn(2.0, q2), thr_s, k, g);
+    return k | g<<8;
 }
 
 /*  phase 2, rare: the trimmed PL row of a sample whose int32 row holds sentinels and carries no data (mcall.c:1158-1194
@@ -680,6 +674,7 @@ __global__ void __launch_bounds__(BLOCK, (MMGeom<NALS>::THREADS/BLOCK > 0 ? MMGe
     using SH = MMShared<NALS,BLOCK>;
     constexpr int G = S::G, NPAIR = S::NPAIR, NTRI = S::NTRI, NSET = GE::NSET, NACC = GE::NACC, NW = BLOCK/32, RS = GE::RS;
     constexpr int TILE_BYTES = GE::TILE_BYTES;
+    static_assert(offsetof(SH, scr_w) % 16 == 0, "scr_w is read with 128-bit loads");
     static_assert(NACC <= 31 && NW >= 2, "one lane per product in the warp reduction; warp 1 prepares the next site");
     constexpr bool CF_REG = NALS<=3;            /* coefficients of the small shape live in registers */
 
@@ -700,6 +695,10 @@ __global__ void __launch_bounds__(BLOCK, (MMGeom<NALS>::THREADS/BLOCK > 0 ? MMGe
 
     for (int i=tid; i<256; i+=BLOCK) sh.pl2p[i] = a.tab->pl2p[i];
     for (int i=tid; i<130; i+=BLOCK) sh.gq_thr[i] = i<128 ? a.tab->gq_thr[i] : -1.0;
+    screen_tabs_fill(&sh.scr, a.tab, tid, BLOCK);
+    const uint32_t plf_s = sbase + (uint32_t)offsetof(SH, scr) + (uint32_t)offsetof(ScreenTabs, plf);
+    const uint32_t gqw_s = sbase + (uint32_t)offsetof(SH, scr) + (uint32_t)offsetof(ScreenTabs, gqw);
+    const uint32_t q_s = sbase + (uint32_t)offsetof(SH, q), jgt_s = sbase + (uint32_t)offsetof(SH, jgt), scrw_s = sbase + (uint32_t)offsetof(SH, scr_w);
     if ( lane==0 )
     {
         for (int i=0; i<MM_MAX_NST; i++) mbar_init(bars_s + 8*i, 1);
@@ -1028,7 +1027,10 @@ __global__ void __launch_bounds__(BLOCK, (MMGeom<NALS>::THREADS/BLOCK > 0 ? MMGe
             int2 *out_gt = reinterpret_cast<int2*>(a.gt) + (size_t)sh.site*nsmpl;
             int32_t *out_gq = a.gq + (size_t)sh.site*nsmpl;
             int32_t *out_pl = a.out_pl + sh.out_off;
-            const double q0 = sh.q[0], q1 = sh.q[1], q1x2 = __dmul_rn(2.0, q1);
+            float w0, w1, w2, wn;
+            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(w0), "=f"(w1), "=f"(w2), "=f"(wn) : "r"(scrw_s));
+            asm volatile("ld.shared.f32 %0, [%1+24];" : "=f"(wn) : "r"(scrw_s));
+            const bool noscr = wn != 0.f;
             const uint32_t j0 = (uint32_t)sh.jgt[0], j1 = (uint32_t)sh.jgt[1], j2 = (uint32_t)sh.jgt[2];
             int f_alt = 0, f_called = 0;
             double ns0 = 0, ns1 = 0;
@@ -1042,9 +1044,11 @@ __global__ void __launch_bounds__(BLOCK, (MMGeom<NALS>::THREADS/BLOCK > 0 ? MMGe
                 const uint32_t a0 = mm_ldsu8(rA + j0), b0 = mm_ldsu8(rA + j1), c0 = mm_ldsu8(rA + j2);
                 const uint32_t a1 = mm_ldsu8(rB + j0), b1 = mm_ldsu8(rB + j1), c1 = mm_ldsu8(rB + j2);
                 int k0, k1, g0, g1;
-                fast2_call(lds64c(pl2p_s + 8u*a0), lds64c(pl2p_s + 8u*b0), lds64c(pl2p_s + 8u*c0), s0, q0, q1, q1x2, thr_s, k0, g0);
-                fast2_call(lds64c(pl2p_s + 8u*a1), lds64c(pl2p_s + 8u*b1), lds64c(pl2p_s + 8u*c1), s1, q0, q1, q1x2, thr_s, k1, g1);
+                const bool ok0 = screen2_call(a0, b0, c0, w0, w1, w2, plf_s, gqw_s, k0, g0);
+                const bool ok1 = screen2_call(a1, b1, c1, w0, w1, w2, plf_s, gqw_s, k1, g1);
                 const bool has0 = s0 > 0 && s0 != (double)G, has1 = s1 > 0 && s1 != (double)G;     /* PL=0,..,0 / all missing: ./. and GQ 0 */
+                if ( (!ok0 || noscr) && has0 ) { const int e = mm_fast2_exact(a0, b0, c0, s0, q_s, pl2p_s, thr_s); k0 = e & 255; g0 = e >> 8; }
+                if ( (!ok1 || noscr) && has1 ) { const int e = mm_fast2_exact(a1, b1, c1, s1, q_s, pl2p_s, thr_s); k1 = e & 255; g1 = e >> 8; }
                 /* new alleles 0 and 1: GT codes 2 and 4, slot index = copies of allele 1 */
                 const int x0 = has0 ? (k0==2 ? 4 : 2) : 0, y0 = has0 ? (k0 ? 4 : 2) : 0;
                 const int x1 = has1 ? (k1==2 ? 4 : 2) : 0, y1 = has1 ? (k1 ? 4 : 2) : 0;
@@ -1069,7 +1073,11 @@ __global__ void __launch_bounds__(BLOCK, (MMGeom<NALS>::THREADS/BLOCK > 0 ? MMGe
             int2 *out_gt = reinterpret_cast<int2*>(a.gt) + (size_t)sh.site*nsmpl;
             int32_t *out_gq = a.gq + (size_t)sh.site*nsmpl;
             int32_t *out_pl = a.out_pl + sh.out_off;
-            const double q0 = sh.q[0], q1 = sh.q[1], q2 = sh.q[2], q1x2 = __dmul_rn(2.0, q1), q2x2 = __dmul_rn(2.0, q2);
+            float w[6], wn;
+            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(w[0]), "=f"(w[1]), "=f"(w[2]), "=f"(w[3]) : "r"(scrw_s));
+            asm volatile("ld.shared.v2.f32 {%0,%1}, [%2+16];" : "=f"(w[4]), "=f"(w[5]) : "r"(scrw_s));
+            asm volatile("ld.shared.f32 %0, [%1+24];" : "=f"(wn) : "r"(scrw_s));
+            const bool noscr = wn != 0.f;
             uint32_t jg[6];
             #pragma unroll
             for (int k=0; k<6; k++) jg[k] = (uint32_t)sh.jgt[k];
@@ -1090,19 +1098,11 @@ __global__ void __launch_bounds__(BLOCK, (MMGeom<NALS>::THREADS/BLOCK > 0 ? MMGe
                 mm_stg128(dst + 4, (int)vA[4], (int)vA[5], (int)vB[0], (int)vB[1]);
                 mm_stg128(dst + 8, (int)vB[2], (int)vB[3], (int)vB[4], (int)vB[5]);
                 int k0, k1, g0, g1;
-                {
-                    double p[6];
-                    #pragma unroll
-                    for (int k=0; k<6; k++) p[k] = lds64c(pl2p_s + 8u*vA[k]);
-                    fast3_call(p, s0, q0, q1, q2, q1x2, q2x2, thr_s, k0, g0);
-                }
-                {
-                    double p[6];
-                    #pragma unroll
-                    for (int k=0; k<6; k++) p[k] = lds64c(pl2p_s + 8u*vB[k]);
-                    fast3_call(p, s1, q0, q1, q2, q1x2, q2x2, thr_s, k1, g1);
-                }
+                const bool ok0 = screen3_call(vA, w, plf_s, gqw_s, k0, g0);
+                const bool ok1 = screen3_call(vB, w, plf_s, gqw_s, k1, g1);
                 const bool has0 = s0 > 0 && s0 != (double)G, has1 = s1 > 0 && s1 != (double)G;
+                if ( (!ok0 || noscr) && has0 ) { const int e = mm_fast3_exact(rA, jgt_s, s0, q_s, pl2p_s, thr_s); k0 = e & 255; g0 = e >> 8; }
+                if ( (!ok1 || noscr) && has1 ) { const int e = mm_fast3_exact(rB, jgt_s, s1, q_s, pl2p_s, thr_s); k1 = e & 255; g1 = e >> 8; }
                 const int4 o0 = lds128(slot_s + 16u*(uint32_t)(has0 ? k0 : 6));
                 const int4 o1 = lds128(slot_s + 16u*(uint32_t)(has1 ? k1 : 6));
                 acc += ((unsigned long long)(uint32_t)o0.z | ((unsigned long long)(uint32_t)o0.w << 32))

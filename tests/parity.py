@@ -51,7 +51,6 @@ def random_batch(rng, R, S, maxA, zq=True, miss=True, minA=1, pl_max=256):
 
 def compare(got, exp, params, exact_qual=False, check_flags=True):
     """Compare two HostResult objects.  Returns dict(compared=, near_ties=[...], qual_max_rel=)."""
-    assert (got.ret == exp.ret).all() or True
     near = []
     compared = 0
     qmax = 0.0
