@@ -46,6 +46,18 @@ def test_job_layer_symbols_are_exported():
     assert all(hasattr(L, s) for s in syms)
 
 
+def test_vcf_layer_symbols_are_exported():
+    """include/b200_vcf.h (text VCF model) and include/b200_vcfcall.h (the `call -m` driver)."""
+    from bcftools_b200 import vcfcall, mcall
+    L = mcall.lib()
+    for header, exports in (("b200_vcf.h", vcfcall.VCF_EXPORTS), ("b200_vcfcall.h", vcfcall.VCFCALL_EXPORTS)):
+        hdr = open(os.path.join(ROOT, "include", header)).read()
+        hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+        syms = sorted(set(re.findall(r"\b(b200_[a-z0-9_]+)\s*\(", hdr)))
+        assert syms == sorted(exports), (header, sorted(set(syms) ^ set(exports)))
+        assert all(hasattr(L, s) for s in syms), [s for s in syms if not hasattr(L, s)]
+
+
 def test_struct_layouts_match_header():
     """ctypes mirrors must have the field order of the C structs (a mismatch would silently scramble pointers)."""
     from bcftools_b200 import abi
