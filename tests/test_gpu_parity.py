@@ -409,6 +409,31 @@ def test_multi_allelic_kernel_on_the_bench_workload(cfg, nsites, oracle_built):
     assert st["compared"] > 0 and not st["near_ties"], st
 
 
+@pytest.mark.parametrize("cfg,nsites,groups", [("C2", 2048, None), ("C5", 2048, 0), ("C5", 2048, 5), ("C5", 2048, 26), ("C4", 64, None)])
+def test_baseline_configs_against_the_compiled_reference(cfg, nsites, groups, oracle_built):
+    """>= 2,048 sites of every BASELINE.json config (C3: the test above; C4, 100,000 samples: 64 sites) with the default
+    kernels against the reference's own mcall.c; C5 pooled, with 5 and with 26 -G groups."""
+    from bcftools_b200 import mcall
+    params, batch, tab = synth.make_batch(cfg, nsites, with_groups=groups)
+    exp, _ = oracle_built.call(ORACLE(oracle_built), params, batch, tab)
+    with mcall.MCaller(params, ploidy_tab=tab) as mc:
+        got = mc.call_host(batch, compact=True)
+    st = parity.compare(got, exp, params)
+    assert st["compared"] > 0 and not st["near_ties"], st
+
+
+def test_typed_end_to_end_path_on_the_bench_workload(oracle_built):
+    """The BCF typed transport both ways (int16 PL in; int8 GT, int8 GQ, int16 PL out, compacted) on 2,048 C3 sites
+    against the compiled reference."""
+    from bcftools_b200 import mcall
+    params, batch, tab = synth.make_batch("C3", 2048)
+    exp, _ = oracle_built.call(ORACLE(oracle_built), params, batch, tab)
+    with mcall.MCaller(params, ploidy_tab=tab) as mc:
+        got = mc.call_host(batch.to_int16(), compact=True, typed=True)
+    st = parity.compare(got.widen(), exp, params)
+    assert st["compared"] > 0 and not st["near_ties"], st
+
+
 def test_empty_batch():
     from bcftools_b200 import mcall
     params = abi.CallParams(8, 5)
