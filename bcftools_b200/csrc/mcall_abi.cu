@@ -73,6 +73,7 @@ struct mcb_ctx
     HostSlab slab[NSLAB];
     /* options */
     int64_t opt_tile_bytes = 0, opt_ring_bytes = 0, opt_blocks_per_sm = 0, opt_slab_bytes = 64ll<<20, opt_slab_min = 8ll<<20, opt_block = 0;     /* 0 = automatic */
+    int64_t opt_exact = 0;               /* 1: near-tie adjudication -- every site through the general kernel with the literal phase 1 (KArgs.exact_phase1) */
     int64_t opt_multi = 1;               /* 3-5 allele classes: the CTA-per-site kernel of mcall_multi.cu (0: the general tiled kernel) */
     int64_t opt_mm_nst = 0;              /* its ring stages per warp (0 = automatic) */
     int64_t opt_mm_nst_c[NCLASS] = {0,0,0,0,0,0};       /* ... per allele-count class */
@@ -180,6 +181,7 @@ extern "C" int mcb_set_option(mcb_ctx *ctx, const char *key, int64_t value)
     else if ( !strcmp(key,"concurrent") )    ctx->opt_concurrent = value;
     else if ( !strcmp(key,"order") )         ctx->opt_order = value;
     else if ( !strcmp(key,"multi") )         ctx->opt_multi = value;
+    else if ( !strcmp(key,"exact_phase1") )  { if ( value<0 || value>1 ) return MCB_EINVAL; ctx->opt_exact = value; }
     else if ( !strcmp(key,"mm_nst") )        { if ( value<0 || value>4 ) return MCB_EINVAL; ctx->opt_mm_nst = value; }
     else if ( !strncmp(key,"mm_nst_",7) && key[7]>='3' && key[7]<='5' && !key[8] ) { if ( value<0 || value>4 ) return MCB_EINVAL; ctx->opt_mm_nst_c[key[7]-'0'] = value; }
     else if ( !strcmp(key,"mm_block") )      { if ( value!=0 && value!=64 && value!=128 && value!=256 ) return MCB_EINVAL; ctx->opt_mm_block = value; }
@@ -456,6 +458,8 @@ static int enqueue(mcb_ctx *ctx, const mcb_batch *b, const mcb_result *r, int32_
     a.tab = ctx->d_tab; a.ploidy_tab = ctx->d_ploidy; a.nploidy = ctx->nploidy;
     a.nsmpl = ctx->p.nsmpl; a.max_nals = ctx->p.max_nals; a.flag = ctx->p.flag; a.output_tags = ctx->p.output_tags;
     a.theta = ctx->theta_log; a.tie_eps = ctx->p.tie_eps; a.use_prior = ctx->p.use_prior;
+    a.exact_phase1 = (int)ctx->opt_exact;
+    if ( ctx->opt_exact && ctx->ngroups > 1 ) return MCB_EINVAL;   /* the adjudication path covers pooled calling */
     const bool ploidy = ctx->any_nondiploid;
     const int pl_es = b->pl_type==2 ? 2 : 4;
     if ( b->pl_type!=0 && b->pl_type!=4 && b->pl_type!=2 ) return MCB_EINVAL;
@@ -536,7 +540,7 @@ static int enqueue(mcb_ctx *ctx, const mcb_batch *b, const mcb_result *r, int32_
         a.work_counter = counts + NCLASS + nals;    /* zeroed with the class counts: sites are claimed dynamically */
         /* two alleles, int32 PLs, no GP: one warp per site over a byte-packed shared-memory copy */
         int bw_warps = 0;
-        if ( nals==2 && pl_es==4 && !(a.gp && (a.output_tags & MCB_CALL_FMT_GP)) && ctx->opt_warp2!=0 && a.nsmpl<=8192 )
+        if ( nals==2 && pl_es==4 && !(a.gp && (a.output_tags & MCB_CALL_FMT_GP)) && ctx->opt_warp2!=0 && a.nsmpl<=8192 && !ctx->opt_exact )
         {
             const int ncta = biallelic_ctas_per_sm();
             const size_t per_cta = (size_t)(ctx->smem_per_sm/ncta) - 1024;  /* the kernel is compiled for ncta CTAs per SM */
@@ -576,7 +580,7 @@ static int enqueue(mcb_ctx *ctx, const mcb_batch *b, const mcb_result *r, int32_
         if ( fork ) CK(cudaStreamWaitEvent(cs, ctx->cev_fork, 0));
         /*  3-5 alleles, int32 PLs, every sample diploid, GT + GQ + PL requested: the CTA-per-site kernel of mcall_multi.cu.
          *  Sites it has no straight-line code for come back on a fallback list, which the general kernel below walks.  */
-        if ( nals>=3 && ctx->opt_multi && !ctx->opt_block && !ctx->opt_block_c[nals] && pl_es==4 && !ploidy && !gpk && a.gt && a.gq && a.out_pl && !(a.flag & MCB_CALL_KEEPALT)
+        if ( nals>=3 && ctx->opt_multi && !ctx->opt_exact && !ctx->opt_block && !ctx->opt_block_c[nals] && pl_es==4 && !ploidy && !gpk && a.gt && a.gq && a.out_pl && !(a.flag & MCB_CALL_KEEPALT)
              && (a.output_tags & (MCB_CALL_FMT_GQ|MCB_CALL_FMT_GP))
              && !((reinterpret_cast<uintptr_t>(a.gt) | reinterpret_cast<uintptr_t>(a.gq) | reinterpret_cast<uintptr_t>(a.out_pl)) & 15) )
         {

@@ -65,6 +65,7 @@ struct KArgs
     double theta, tie_eps;
     int use_prior;
     int tile_smpl, nstage;
+    int exact_phase1;                                           /* near-tie adjudication: literal sample-sequential sums of logs in the general kernel */
 };
 
 }   // namespace mcb

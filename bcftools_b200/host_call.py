@@ -12,7 +12,7 @@ class B200Call(C.Structure):
                 ("ploidy", C.c_void_p), ("unseen", C.c_uint8), ("nsmpl_grp", C.c_int),
                 ("grp_off", C.c_void_p), ("grp_smpl", C.c_void_p), ("use_prior", C.c_int),
                 ("max_records", C.c_int), ("max_nals", C.c_int), ("device", C.c_int), ("bcf_typed", C.c_int),
-                ("async_flush", C.c_int), ("batcher", C.c_void_p)]
+                ("async_flush", C.c_int), ("tie_eps", C.c_double), ("batcher", C.c_void_p)]
 
 
 class B200Rec(C.Structure):
@@ -57,7 +57,7 @@ def _widen(a, bits):
     return o
 
 
-def replay(params, batch, ploidy_tab=None, max_records=64, typed=False, async_flush=False, stats=None):
+def replay(params, batch, ploidy_tab=None, max_records=64, typed=False, async_flush=False, stats=None, tie_eps=0.0):
     """Feed a HostBatch record by record through b200_mcall (like vcfcall.c:1089-1148 feeds mcall) and collect the
     results into an abi.HostResult laid out like the C-ABI's, so that the usual comparison helpers apply.
     typed=True: b200_call_t.bcf_typed -- PL goes in as the int8/int16 typed vector a BCF record would hold (int8 when
@@ -75,6 +75,7 @@ def replay(params, batch, ploidy_tab=None, max_records=64, typed=False, async_fl
     call.use_prior, call.max_records, call.max_nals, call.device = int(params.use_prior), max_records, params.max_nals, params.device
     call.bcf_typed = int(typed)
     call.async_flush = int(async_flush)
+    call.tie_eps = float(tie_eps)
     L.b200_mcall_init(C.byref(call))
     res = abi.HostResult(batch, want_gp=bool(params.output_tags & abi.CALL_FMT_GP))
     done = [0]

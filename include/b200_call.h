@@ -21,6 +21,7 @@ extern "C" {
 #define CALL_VARONLY   (1<<1)
 #define CALL_FMT_GQ    (1<<6)
 #define CALL_FMT_GP    (1<<7)
+#define B200_SITE_ADJUDICATED (1u<<9)   /* b200_out_t.site_flags: the record's near tie was re-evaluated in the reference's summation order */
 
 typedef struct b200_batcher b200_batcher_t;
 
@@ -45,6 +46,9 @@ typedef struct
                                    come back as int8 / int8 / int16 vectors (b200_out_t.gts8 / GQs8 / PLs16); pooled calling only */
     int      async_flush;       /* 1: a full batch is handed to the GPU in the background and b200_mcall keeps queuing into the second
                                    slab set; the results it then reports are those of the PREVIOUS batch (see b200_mcall_flush_async) */
+    double   tie_eps;           /* allele sets closer than this in log-likelihood are near ties (0 = 1e-6): such records are called a second
+                                   time with the literal sample-sequential sums of logs (mcall.c:607-611, 635-645, 680-690) and come back
+                                   with MCB_SITE_NEAR_TIE | B200_SITE_ADJUDICATED in site_flags (pooled calling, int32 PLs) */
     /* ---- owned by this layer ---- */
     b200_batcher_t *batcher;
 }

@@ -434,6 +434,45 @@ def test_typed_end_to_end_path_on_the_bench_workload(oracle_built):
     assert st["compared"] > 0 and not st["near_ties"], st
 
 
+@pytest.mark.parametrize("S,maxA,flag", [(7, 5, 0), (40, 4, abi.CALL_VARONLY), (300, 5, 0), (64, 5, abi.CALL_KEEPALT)])
+def test_literal_phase1_for_near_tie_adjudication(S, maxA, flag, oracle_built):
+    """mcb_set_option("exact_phase1", 1): the literal sample-sequential sums of logs of mcall_find_best_alleles
+    (mcall.c:591-710) on the device must give the reference's calls on adversarial inputs, mixed ploidy included."""
+    from bcftools_b200 import mcall
+    rng = np.random.default_rng([S, maxA, flag, 99])
+    batch = parity.random_batch(rng, 80, S, maxA)
+    tab = np.full((3, S), 2, np.uint8)
+    tab[1, ::2] = 1
+    tab[2, ::3] = 1
+    tab[2, 1::5] = 0
+    batch.ploidy_id = rng.integers(0, 3, batch.nsites).astype(np.uint16)
+    params = abi.CallParams(S, maxA, flag=flag, output_tags=abi.CALL_FMT_GQ)
+    exp, _ = oracle_built.call(ORACLE(oracle_built), params, batch, tab)
+    with mcall.MCaller(params, ploidy_tab=tab, options={"exact_phase1": 1}) as mc:
+        got = mc.call_host(batch)
+    st = parity.compare(got, exp, params)
+    assert st["compared"] > 0 and not st["near_ties"], st
+
+
+def test_host_batcher_adjudicates_near_ties(oracle_built):
+    """With tie_eps so large that every record counts as a near tie, the batcher re-submits the whole batch through the
+    literal phase 1: results must still be the reference's and carry the ADJUDICATED flag."""
+    from bcftools_b200 import host_call
+    rng = np.random.default_rng(4242)
+    batch = parity.random_batch(rng, 150, 37, 5)
+    params = abi.CallParams(37, 5, output_tags=abi.CALL_FMT_GQ)
+    exp, _ = oracle_built.call(ORACLE(oracle_built), params, batch, None)
+    for async_flush in (False, True):
+        got = host_call.replay(params, batch, None, max_records=64, async_flush=async_flush, tie_eps=1e30)
+        called = got.ret > 0
+        tie, adj = (got.site_flags[called] & abi.SITE_NEAR_TIE) != 0, (got.site_flags[called] & (1 << 9)) != 0
+        assert (tie == adj).all() and adj.mean() > 0.5       # a site with a single candidate set has no runner-up: not a tie
+        st = parity.compare(got, exp, params)
+        assert st["compared"] > 0, st
+    plain = host_call.replay(params, batch, None, max_records=64)
+    assert not (plain.site_flags & (1 << 9)).any()
+
+
 def test_empty_batch():
     from bcftools_b200 import mcall
     params = abi.CallParams(8, 5)
