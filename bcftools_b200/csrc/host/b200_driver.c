@@ -256,18 +256,17 @@ static int ped_parse(const lines_t *in, lines_t *out)
     {
         char *str = dup_n(in->line[i], strlen(in->line[i]));
         if ( !str ) return B200_DRV_ENOMEM;
-        char *col[5], *tmp = str;
+        /* a PED line has at least six whitespace-separated fields (runs of blanks count once, leading blanks make an empty
+           first field): family, sample, father, mother, sex, ...; col[k] = field k+1, cut at its end */
+        char *col[5];
         int j = 0;
-        while ( *tmp && j<5 )
+        for (char *p = str; *p && j<5; )
         {
-            if ( isspace((unsigned char)*tmp) )
-            {
-                *tmp = 0; ++tmp;
-                while ( isspace((unsigned char)*tmp) ) tmp++;       /* allow multiple spaces */
-                col[j++] = tmp;                                     /* first character of column j+1 */
-                continue;
-            }
-            tmp++;
+            p += strcspn(p, " \t\n\v\f\r");            /* end of the current field */
+            if ( !*p ) break;
+            *p++ = 0;
+            p += strspn(p, " \t\n\v\f\r");             /* next field */
+            col[j++] = p;
         }
         if ( j!=5 ) { free(str); break; }
         /* columns: family, sample = col[0], father = col[1], mother = col[2], sex = col[3]; each ends at the next separator */
