@@ -278,6 +278,9 @@ def main():
     numa_cpus = bind_to_gpu_numa_node(local_rank) if world > 1 else 0
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    # a host-side group: ranks that only WAIT (the one-job leg below) must not park an NCCL kernel on their GPU -- rank 0 drives
+    # that GPU from its own context and would be time-sliced against the spinning barrier kernel
+    host_group = dist.new_group(backend="gloo") if world > 1 else None
 
     def barrier():
         if world > 1:
@@ -462,6 +465,7 @@ def main():
     job = None
     if world > 1:
         barrier()
+        dist.barrier(group=host_group)
         if rank == 0:
             pj, hj, tj = synth.make_batch("C4", args.job_sites_per_gpu * world)
             hj = mcall.pin_batch(hj)
@@ -477,6 +481,7 @@ def main():
                     dtj = (time.perf_counter() - t0) / 3
                 job["devices_%d" % ndev] = dict(value=hj.nsites * pj.nsmpl / dtj, unit=UNIT, ms_per_call=1e3 * dtj)
             job["speedup"] = job["devices_%d" % world]["value"] / job["devices_1"]["value"]
+        dist.barrier(group=host_group)      # the other ranks wait on the host, their GPUs idle
         barrier()
 
     # ---- max over ranks of the device time
