@@ -10,6 +10,7 @@
 #include <ctype.h>
 #include "b200_vcfcall.h"
 #include "b200_driver.h"
+#include "b200_bcfio.h"
 
 #define CF_INS_MISSED   (1<<4)      /* vcfcall.c:62-69 */
 #define CF_INDEL_ONLY   1
@@ -63,6 +64,7 @@ struct b200_vc
     int eof;
     gvcf_t *gvcf;
     int unseen;
+    int output_type;                /* 'v' text, 'z' BGZF-compressed text, 'b' BCF, 'u' uncompressed BCF (vcfcall.c:1003-1011) */
     b200_str_t out;
     char err[512];
 };
@@ -309,6 +311,7 @@ b200_vc_t *b200_vc_open(int argc, const char *const *argv, const char *vcf_text,
     #define OPEN_FAIL(...) do { vc_fail(vc, __VA_ARGS__); if ( err && errlen ) snprintf(err, errlen, "%s", vc->err); b200_vc_close(vc); return NULL; } while (0)
     vc->theta = 1.1e-3;
     vc->flag = CF_ACGT_ONLY;
+    vc->output_type = 'v';
     const char *samples_fname = NULL, *ploidy_alias = NULL, *ploidy_fname = NULL, *groups = NULL, *targets = NULL, *gvcf_arg = NULL;
     int samples_is_file = 0, mcall = 0;
     for (int i=0; i<argc; i++)
@@ -362,7 +365,7 @@ b200_vc_t *b200_vc_open(int argc, const char *const *argv, const char *vcf_text,
                 else if ( !strcasecmp(v, "indels") ) vc->flag |= CF_NO_INDEL;
                 else OPEN_FAIL("Unknown skip category \"%s\" (-S argument must be \"snps\" or \"indels\")\n", v);
             }
-            else if ( !strcmp(a, "--output-type") ) { NEED_ARG(v); if ( v[0]!='v' ) OPEN_FAIL("Only text VCF output (-O v) is part of this path\n"); }
+            else if ( !strcmp(a, "--output-type") ) { NEED_ARG(v); if ( !strchr("vzbu", v[0]) || !v[0] ) OPEN_FAIL("The output type \"%s\" not recognised\n", v); vc->output_type = v[0]; }
             else OPEN_FAIL("Unsupported option: %s\n", a);
             continue;
         }
@@ -400,7 +403,7 @@ b200_vc_t *b200_vc_open(int argc, const char *const *argv, const char *vcf_text,
                     break;
                 }
                 case 'g': gvcf_arg = v; break;
-                case 'O': if ( v[0]!='v' ) OPEN_FAIL("Only text VCF output (-O v) is part of this path\n"); break;
+                case 'O': if ( !strchr("vzbu", v[0]) || !v[0] ) OPEN_FAIL("The output type \"%s\" not recognised\n", v); vc->output_type = v[0]; break;
                 case 'C':
                     if ( !strcasecmp(v, "alleles") ) vc->aux_flag |= CALL_CONSTR_ALLELES;
                     else OPEN_FAIL("Unsupported argument to -C: \"%s\"\n", v);
@@ -588,6 +591,7 @@ void b200_vc_call_params(const b200_vc_t *vc, b200_call_t *call)
 }
 const uint8_t *b200_vc_ploidy(const b200_vc_t *vc) { return vc->ploidy_vec; }
 int b200_vc_unseen(const b200_vc_t *vc) { return vc->unseen; }
+int b200_vc_output_type(const b200_vc_t *vc) { return vc->output_type; }
 const char *b200_vc_output(const b200_vc_t *vc, size_t *len) { if ( len ) *len = vc->out.l; return vc->out.s ? vc->out.s : ""; }
 void b200_vc_output_clear(b200_vc_t *vc) { vc->out.l = 0; if ( vc->out.s ) vc->out.s[0] = 0; }
 
@@ -1076,6 +1080,14 @@ int b200_vcfcall_run(int argc, const char *const *argv, const char *in_path, con
     size_t len = 0;
     char *text = read_file(in_path, &len);
     if ( !text ) { if ( err ) snprintf(err, errlen, "Failed to read from %s\n", in_path); return -1; }
+    if ( len > 2 && (unsigned char)text[0]==31 && (unsigned char)text[1]==139 )     /* BGZF: compressed VCF or BCF (vcfcall.c:624: any htslib-readable input) */
+    {
+        b200_str_t raw = {0,0,0}, txt = {0,0,0};
+        int bad = b200_bgzf_decompress((const uint8_t*)text, len, &raw);
+        if ( !bad && raw.l >= 5 && !memcmp(raw.s, "BCF\2\2", 5) ) { bad = b200_bcf_to_vcf_text((const uint8_t*)text, len, &txt); free(raw.s); raw = txt; }
+        if ( bad ) { if ( err ) snprintf(err, errlen, "Failed to read from %s: not a BGZF / BCF2 file\n", in_path); free(raw.s); free(text); return -1; }
+        free(text); text = raw.s; len = raw.l;
+    }
     b200_vc_t *vc = b200_vc_open(argc, argv, text, len, err, errlen);
     if ( !vc ) { free(text); return -1; }
     FILE *fp = strcmp(out_path, "-") ? fopen(out_path, "wb") : stdout;
@@ -1091,8 +1103,9 @@ int b200_vcfcall_run(int argc, const char *const *argv, const char *in_path, con
     b200_mcall_init(&call);
     int rc = g_run_err[0] ? -1 : 0, nres;
     b200_vcrec_t *r; b200_rec_t in;
+    const int otype = b200_vc_output_type(vc);      /* text streams out batch by batch; the binary forms are encoded from the whole text at the end */
     #define DRAIN(n) do { for (int i_=0; i_<(n) && !rc; i_++) { b200_out_t o_; b200_mcall_result(&call, i_, &o_); if ( b200_vc_finish(vc, (b200_vcrec_t*)o_.user, &o_) ) rc = -1; } \
-                          size_t l_; const char *s_ = b200_vc_output(vc, &l_); if ( l_ ) { fwrite(s_, 1, l_, fp); b200_vc_output_clear(vc); } } while (0)
+                          size_t l_; const char *s_ = b200_vc_output(vc, &l_); if ( l_ && otype=='v' ) { fwrite(s_, 1, l_, fp); b200_vc_output_clear(vc); } } while (0)
     while ( !rc && (nres = b200_vc_next(vc, &r, &in)) > 0 )
     {
         call.unseen = (uint8_t) b200_vc_unseen(vc);     /* the ploidy vector is shared storage, rewritten in place by set_ploidy */
@@ -1110,7 +1123,21 @@ int b200_vcfcall_run(int argc, const char *const *argv, const char *in_path, con
     }
     #undef DRAIN
     if ( !rc && b200_vc_flush(vc) ) rc = -1;
-    if ( !rc ) { size_t l; const char *s = b200_vc_output(vc, &l); if ( l ) fwrite(s, 1, l, fp); }
+    if ( !rc )
+    {
+        size_t l; const char *s = b200_vc_output(vc, &l);
+        if ( otype=='v' ) { if ( l ) fwrite(s, 1, l, fp); }
+        else
+        {
+            b200_str_t bin = {0,0,0};
+            int bad;
+            if ( otype=='z' ) { bad = b200_bgzf_compress((const uint8_t*)s, l, 6, &bin); if ( !bad ) bad = b200_bgzf_finish(&bin); }
+            else bad = b200_vcf_text_to_bcf(s, l, otype=='b' ? 6 : 0, &bin);
+            if ( bad ) { rc = -1; snprintf(g_run_err, sizeof g_run_err, "Error: failed to encode the output\n"); }
+            else fwrite(bin.s, 1, bin.l, fp);
+            free(bin.s);
+        }
+    }
     if ( rc && err ) snprintf(err, errlen, "%s", g_run_err[0] ? g_run_err : b200_vc_error(vc));
     b200_mcall_destroy(&call);
     b200_set_error_handler(NULL);

@@ -28,7 +28,8 @@ class McallError(RuntimeError):
 
 
 def lib():
-    """Load libmcall_b200.so (building it in-tree if the sources are newer).  Raises if unavailable."""
+    """Load libmcall_b200.so; built in-tree when it is MISSING.  A stale library is not rebuilt here (file times do not survive the
+    copy to a GPU box): `python -m bcftools_b200.build` / `__graft_entry__.build()` rebuild what is older than its sources."""
     global _lib
     if _lib is None:
         if not os.path.exists(_LIB_PATH):

@@ -8,7 +8,7 @@ import numpy as np
 from . import abi, mcall
 from .host_call import B200Call, B200Rec, B200Out
 
-VCFCALL_EXPORTS = ["b200_vc_open", "b200_vc_close", "b200_vc_error", "b200_vc_call_params", "b200_vc_ploidy", "b200_vc_unseen",
+VCFCALL_EXPORTS = ["b200_vc_open", "b200_vc_close", "b200_vc_error", "b200_vc_call_params", "b200_vc_ploidy", "b200_vc_unseen", "b200_vc_output_type",
                    "b200_vc_next", "b200_vc_finish", "b200_vc_flush", "b200_vc_output", "b200_vc_output_clear",
                    "b200_vcfcall_run", "b200_pv4", "b200_vcmp_set_ref", "b200_vcmp_find_allele"]
 VCF_EXPORTS = ["b200_str_putsn", "b200_str_puts", "b200_str_putc", "b200_str_putw", "b200_str_putd",
@@ -17,6 +17,11 @@ VCF_EXPORTS = ["b200_str_putsn", "b200_str_puts", "b200_str_putc", "b200_str_put
                "b200_vrec_info_floats", "b200_vrec_info_ints", "b200_vrec_fmt_ints", "b200_vrec_fmt", "b200_vrec_set_info_ints",
                "b200_vrec_set_info_floats", "b200_vrec_set_info_text", "b200_vrec_set_fmt_ints", "b200_vrec_set_fmt_floats",
                "b200_vrec_set_genotypes", "b200_vrec_set_alleles"]
+
+
+BCFIO_EXPORTS = ["b200_bcfdict_build", "b200_bcfdict_destroy", "b200_bgzf_compress", "b200_bgzf_finish", "b200_bgzf_decompress",
+                 "b200_bcf_write_header", "b200_bcf_read_header", "b200_bcf_encode_rec", "b200_bcf_decode_rec",
+                 "b200_vcf_text_to_bcf", "b200_bcf_to_vcf_text"]
 
 
 class B200Str(C.Structure):
@@ -70,6 +75,25 @@ def pv4(i16):
     p = (C.c_float * 4)()
     tested = _lib().b200_pv4(a, p)
     return tested, [float(x) for x in p]
+
+
+def vcf_to_bcf(text, level=6):
+    """text VCF -> BCF2.2 bytes (BGZF, include/b200_bcfio.h)"""
+    L = _lib()
+    L.b200_vcf_text_to_bcf.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.POINTER(B200Str)]
+    out = B200Str(None, 0, 0)
+    if L.b200_vcf_text_to_bcf(text, len(text), level, C.byref(out)):
+        raise RuntimeError("b200_vcf_text_to_bcf failed")
+    return C.string_at(out.s, out.l)
+
+
+def bcf_to_vcf(data):
+    L = _lib()
+    L.b200_bcf_to_vcf_text.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(B200Str)]
+    out = B200Str(None, 0, 0)
+    if L.b200_bcf_to_vcf_text(data, len(data), C.byref(out)):
+        raise RuntimeError("b200_bcf_to_vcf_text failed")
+    return C.string_at(out.s, out.l)
 
 
 def format_float(x):

@@ -16,8 +16,9 @@
  *  b200_vcfcall_run() is the whole command with the CUDA batcher in between (records are retained while their batch
  *  is on the device: the record ring of vcfbuf.c:146-175); the two halves are also exported so that the host logic can
  *  be replayed against the reference's expected outputs without a GPU (tests/test_vcfcall_host.py feeds them results
- *  computed by the CPU oracle -- the product never does).  Output is text VCF (-O v) without the ##bcftools_ version
- *  lines (--no-version); -c, -C trio, -r/-R, -n, -p, --threads and compressed or BCF output are not part of this path.
+ *  computed by the CPU oracle -- the product never does).  Input may be text VCF, BGZF-compressed VCF or BCF; output is
+ *  -O v / z / b / u (include/b200_bcfio.h), without the ##bcftools_ version lines (--no-version); -c, -C trio, -r/-R, -n, -p
+ *  and --threads are not part of this path.
  *  Errors: functions return NULL / negative and leave a message in b200_vc_error(); nothing exits.
  */
 #ifndef B200_VCFCALL_H
@@ -49,6 +50,7 @@ const char *b200_vc_error(const b200_vc_t *vc);
 void b200_vc_call_params(const b200_vc_t *vc, b200_call_t *call);
 const uint8_t *b200_vc_ploidy(const b200_vc_t *vc);         /* the current per-sample ploidy vector (call->ploidy) */
 int  b200_vc_unseen(const b200_vc_t *vc);                   /* the current record's unseen allele (call->unseen) */
+int  b200_vc_output_type(const b200_vc_t *vc);              /* -O: 'v', 'z', 'b' or 'u' */
 
 /*  Next record that goes to the caller: 1 and *rec / *in filled (in's pointers stay valid until the record is finished),
  *  0 at the end of the input, -1 on error.  Records the driver writes without calling (too many alleles) or drops are

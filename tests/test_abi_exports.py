@@ -50,7 +50,7 @@ def test_vcf_layer_symbols_are_exported():
     """include/b200_vcf.h (text VCF model) and include/b200_vcfcall.h (the `call -m` driver)."""
     from bcftools_b200 import vcfcall, mcall
     L = mcall.lib()
-    for header, exports in (("b200_vcf.h", vcfcall.VCF_EXPORTS), ("b200_vcfcall.h", vcfcall.VCFCALL_EXPORTS)):
+    for header, exports in (("b200_vcf.h", vcfcall.VCF_EXPORTS), ("b200_vcfcall.h", vcfcall.VCFCALL_EXPORTS), ("b200_bcfio.h", vcfcall.BCFIO_EXPORTS)):
         hdr = open(os.path.join(ROOT, "include", header)).read()
         hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
         syms = sorted(set(re.findall(r"\b(b200_[a-z0-9_]+)\s*\(", hdr)))

@@ -22,3 +22,20 @@ def test_call_m_on_the_device_reproduces_the_reference_output_bytes(case, tmp_pa
         for k, (a, b) in enumerate(zip(g, e)):
             assert a == b, (case["id"], k, a[:300], b[:300])
         assert len(g) == len(e), (case["id"], len(g), len(e))
+
+
+@pytest.mark.parametrize("case_id,otype", [("mpileup.1", "b"), ("mpileup.2-gvcf", "u"), ("cAls.7", "b"), ("af-fixation.3", "z")])
+def test_bcf_in_and_out(case_id, otype, tmp_path):
+    """what test.pl's second command checks (`call -Ob ... | bcftools view`): BCF (or BGZF) input -> device -> -O b / u / z output,
+    decoded back to text, equals the expected output"""
+    import gzip
+    case = [c for c in vcf_cases.CASES if c["id"] == case_id][0]
+    inp, exp, args = vcf_cases.load(case)
+    src = str(tmp_path / "in.bcf")
+    with open(src, "wb") as fh:
+        fh.write(vcfcall.vcf_to_bcf(inp))
+    out = str(tmp_path / "out.bin")
+    vcfcall.run(args + ["-O", otype], src, out)
+    data = open(out, "rb").read()
+    got = gzip.decompress(data) if otype == "z" else vcfcall.bcf_to_vcf(data)
+    assert got == exp
