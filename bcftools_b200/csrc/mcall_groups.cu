@@ -19,6 +19,9 @@ namespace mcb {
 
 #define GBLOCK 128
 #define GNW    (GBLOCK/32)
+#ifndef GMINB
+#define GMINB 4          /* resident CTAs per SM the kernel is compiled for (register cap 65536 / (128 * GMINB)) */
+#endif
 #ifndef BIG_GROUP
 #define BIG_GROUP 64        /* groups of at least this many samples are reduced by the whole CTA, sample-parallel */
 #endif
@@ -76,7 +79,7 @@ __device__ __forceinline__ double pl_to_p_dev(const double *s_pl2p, const DevTab
 }
 
 template<int NALS>
-__global__ void __launch_bounds__(GBLOCK) mcall_groups_kernel(const KArgs a, GroupRec *scratch)
+__global__ void __launch_bounds__(GBLOCK, GMINB) mcall_groups_kernel(const KArgs a, GroupRec *scratch)
 {
     using S = Shape<NALS>;
     constexpr int G = S::G, NPAIR = S::NPAIR, NSUB = S::NSUB;
@@ -90,9 +93,9 @@ __global__ void __launch_bounds__(GBLOCK) mcall_groups_kernel(const KArgs a, Gro
     __shared__ unsigned char s_pld[GNW][32];
     /* block-wide path for big groups (>= BIG_GROUP samples): same data flow as phase 1 of the pooled kernel */
     constexpr int NTRI = S::NTRI, NACC = S::NACC;
-    __shared__ float  s_qf[NALS];
-    __shared__ double s_cfp[(NPAIR ? NPAIR : 1)*5], s_cft[(NTRI ? NTRI : 1)*9];
-    __shared__ uint32_t s_live;
+    __shared__ float  s_qf[GNW][NALS];
+    __shared__ double s_cfp[GNW][(NPAIR ? NPAIR : 1)*5], s_cft[GNW][(NTRI ? NTRI : 1)*9];
+    __shared__ uint32_t s_live[GNW];
     __shared__ double s_redM[GNW][NACC];
     __shared__ int    s_redE[GNW][NACC];
     __shared__ long long s_redP[GNW][NALS];
@@ -363,12 +366,16 @@ __global__ void __launch_bounds__(GBLOCK) mcall_groups_kernel(const KArgs a, Gro
         }
         __threadfence_block();
         __syncthreads();
-        /* =========================== phase A, big groups: the whole CTA, one lane per SAMPLE =========== */
-        for (int g=0; g<ngrp; g++)
+        /* =========================== phase A, big groups: one WARP per group, one lane per SAMPLE =======
+         *  Every warp takes its own groups from start to end -- quality sums, coefficients, the sample-parallel products,
+         *  the set comparison -- with warp-level synchronisation only.  (The first version ran the groups one after the
+         *  other on the whole CTA: warp 0's sequential AD sums and set comparisons were 40 % of all instructions and the
+         *  other three warps spent more than half of their time at the barriers behind them, profiles/r02_ncu_groups_*.)  */
+        for (int g=0, big_i=0; g<ngrp; g++)
         {
             const int beg = a.grp_off[g], end = a.grp_off[g+1], ng = end-beg;
             if ( ng < BIG_GROUP ) continue;
-            if ( warp==0 )
+            if ( (big_i++ % GNW) != warp ) continue;
             {
                 /* quality sums (float32, group order), -F prior, normalisation: as in the warp path above */
                 float qa = 0;
@@ -397,12 +404,12 @@ __global__ void __launch_bounds__(GBLOCK) mcall_groups_kernel(const KArgs a, Gro
                             }
                         }
                         #pragma unroll
-                        for (int j=0; j<5; j++) s_adc[0][lane][j] = frac[j];
+                        for (int j=0; j<5; j++) s_adc[warp][lane][j] = frac[j];
                         __syncwarp();
                         if ( lane<NALS )
                         {
                             const int n = min(32, end-base);
-                            for (int k=0; k<n; k++) qa = __fadd_rn(qa, s_adc[0][k][lane]);
+                            for (int k=0; k<n; k++) qa = __fadd_rn(qa, s_adc[warp][k][lane]);
                         }
                         __syncwarp();
                     }
@@ -441,7 +448,7 @@ __global__ void __launch_bounds__(GBLOCK) mcall_groups_kernel(const KArgs a, Gro
                 if ( lane==0 )
                 {
                     #pragma unroll
-                    for (int j=0; j<NALS; j++) { s_qf[j] = qf[j]; grec[g].q[j] = (double)qf[j]; }
+                    for (int j=0; j<NALS; j++) { s_qf[warp][j] = qf[j]; grec[g].q[j] = (double)qf[j]; }
                 }
                 __syncwarp();
                 /* allele-set coefficients, one lane per set (mcall.c:629-633, 671-677) */
@@ -450,8 +457,8 @@ __global__ void __launch_bounds__(GBLOCK) mcall_groups_kernel(const KArgs a, Gro
                 {
                     int aa = 1; while ( aa*(aa+1)/2 <= lane ) aa++;
                     int bb = lane - aa*(aa-1)/2;
-                    float fqa = s_qf[aa], fqb = s_qf[bb];
-                    double *cf = s_cfp + lane*5;
+                    float fqa = s_qf[warp][aa], fqb = s_qf[warp][bb];
+                    double *cf = s_cfp[warp] + lane*5;
                     if ( fqa!=0 && fqb!=0 )
                     {
                         float den = __fadd_rn(fqa,fqb);
@@ -469,8 +476,8 @@ __global__ void __launch_bounds__(GBLOCK) mcall_groups_kernel(const KArgs a, Gro
                     int r = k - aa*(aa-1)*(aa-2)/6;
                     int bb = 1; while ( bb*(bb+1)/2 <= r ) bb++;
                     int cc = r - bb*(bb-1)/2;
-                    float fqa = s_qf[aa], fqb = s_qf[bb], fqc = s_qf[cc];
-                    double *cf = s_cft + k*9;
+                    float fqa = s_qf[warp][aa], fqb = s_qf[warp][bb], fqc = s_qf[warp][cc];
+                    double *cf = s_cft[warp] + k*9;
                     if ( fqa!=0 && fqb!=0 && fqc!=0 )
                     {
                         float den = __fadd_rn(__fadd_rn(fqa,fqb),fqc);
@@ -484,10 +491,10 @@ __global__ void __launch_bounds__(GBLOCK) mcall_groups_kernel(const KArgs a, Gro
                 }
                 #pragma unroll
                 for (int off=16; off; off>>=1) live |= __shfl_xor_sync(0xffffffffu, live, off);
-                if ( lane==0 ) s_live = live;
+                if ( lane==0 ) s_live[warp] = live;
             }
-            __syncthreads();
-            const uint32_t live = s_live;
+            __syncwarp();
+            const uint32_t live = s_live[warp];
             /* ---- sample-parallel accumulation (pooled kernel, phase 1) over the group's sample list */
             double accM[NACC]; int accE[NACC]; long long plsum[NALS];
             int cnt_all = 0, cnt_called = 0, since = 0;
@@ -496,7 +503,7 @@ __global__ void __launch_bounds__(GBLOCK) mcall_groups_kernel(const KArgs a, Gro
             for (int k=0; k<NACC; k++) { accM[k] = 1.0; accE[k] = 0; }
             #pragma unroll
             for (int k=0; k<NALS; k++) plsum[k] = 0;
-            for (int i=tid; i<ng; i+=GBLOCK)
+            for (int i=lane; i<ng; i+=32)
             {
                 const int smp = a.grp_smpl[beg+i];
                 int pl[G]; double p[G];
@@ -538,7 +545,7 @@ __global__ void __launch_bounds__(GBLOCK) mcall_groups_kernel(const KArgs a, Gro
                             const int k = pair_idx(x,y);
                             if ( live & (1u<<k) )
                             {
-                                const double *cf = s_cfp + k*5;
+                                const double *cf = s_cfp[warp] + k*5;
                                 double val = fma(cf[2], p[gt_idx(x,y)], fma(cf[1], p[hom_idx(y)], cf[0]*p[hom_idx(x)]));
                                 acc_mul(accM[k], accE[k], val);
                             }
@@ -553,7 +560,7 @@ __global__ void __launch_bounds__(GBLOCK) mcall_groups_kernel(const KArgs a, Gro
                                 const int k = tri_idx(x,y,z);
                                 if ( live & (1u<<(NPAIR+k)) )
                                 {
-                                    const double *cf = s_cft + k*9;
+                                    const double *cf = s_cft[warp] + k*9;
                                     double val = fma(cf[5], p[gt_idx(y,z)], fma(cf[4], p[gt_idx(x,z)], fma(cf[3], p[gt_idx(x,y)],
                                                  fma(cf[2], p[hom_idx(z)], fma(cf[1], p[hom_idx(y)], cf[0]*p[hom_idx(x)])))));
                                     acc_mul(accM[NPAIR+k], accE[NPAIR+k], val);
@@ -570,7 +577,7 @@ __global__ void __launch_bounds__(GBLOCK) mcall_groups_kernel(const KArgs a, Gro
                             const int k = pair_idx(x,y);
                             if ( live & (1u<<k) )
                             {
-                                const double *cf = s_cfp + k*5;
+                                const double *cf = s_cfp[warp] + k*5;
                                 double val = fma(cf[4], p[hom_idx(y)], cf[3]*p[hom_idx(x)]);
                                 acc_mul(accM[k], accE[k], val);
                             }
@@ -585,7 +592,7 @@ __global__ void __launch_bounds__(GBLOCK) mcall_groups_kernel(const KArgs a, Gro
                                 const int k = tri_idx(x,y,z);
                                 if ( live & (1u<<(NPAIR+k)) )
                                 {
-                                    const double *cf = s_cft + k*9;
+                                    const double *cf = s_cft[warp] + k*9;
                                     double val = fma(cf[8], p[hom_idx(z)], fma(cf[7], p[hom_idx(y)], cf[6]*p[hom_idx(x)]));
                                     acc_mul(accM[NPAIR+k], accE[NPAIR+k], val);
                                 }
@@ -631,19 +638,18 @@ __global__ void __launch_bounds__(GBLOCK) mcall_groups_kernel(const KArgs a, Gro
                 s_redC[warp][0] = cnt_all; s_redC[warp][1] = cnt_called;
                 if ( bflags ) atomicOr(&st.flags, bflags);
             }
-            __syncthreads();
+            __syncwarp();
             /* ---- set totals and the group's best set: lane k <-> allele set k */
-            if ( warp==0 )
             {
                 constexpr double LN10_10 = 0.2302585092994045684017991454684;
                 int n_all = 0, n_called = 0;
                 #pragma unroll
-                for (int w=0; w<GNW; w++) { n_all += s_redC[w][0]; n_called += s_redC[w][1]; }
+                { const int w = warp; n_all += s_redC[w][0]; n_called += s_redC[w][1]; }
                 auto total_log = [&](int k, int n) -> double
                 {
                     double M = 1.0; int E = 0;
                     #pragma unroll
-                    for (int w=0; w<GNW; w++) { M = __dmul_rn(M, s_redM[w][k]); E += s_redE[w][k]; }
+                    { const int w = warp; M = __dmul_rn(M, s_redM[w][k]); E += s_redE[w][k]; }
                     return log(M) + (double)(E - 1023*n)*LN2;
                 };
                 const double lnN_all = n_all ? total_log(NACC-2, n_all) : 0.0;
@@ -653,7 +659,7 @@ __global__ void __launch_bounds__(GBLOCK) mcall_groups_kernel(const KArgs a, Gro
                 {
                     long long ps = 0;
                     #pragma unroll
-                    for (int w=0; w<GNW; w++) ps += s_redP[w][lane];
+                    ps += s_redP[warp][lane];
                     const bool set = n_all > 0;
                     lk = set ? -LN10_10*(double)ps - lnN_all : 0.0;
                     if ( lane>0 ) lk += a.theta;
@@ -717,7 +723,7 @@ __global__ void __launch_bounds__(GBLOCK) mcall_groups_kernel(const KArgs a, Gro
                     if ( any && best - second < a.tie_eps ) atomicOr(&st.flags, MCB_SITE_NEAR_TIE);
                 }
             }
-            __syncthreads();
+            __syncwarp();
         }
         __threadfence_block();
         __syncthreads();
