@@ -17,7 +17,9 @@
 
 namespace mcb {
 
+#ifndef GBLOCK
 #define GBLOCK 128
+#endif
 #define GNW    (GBLOCK/32)
 #ifndef GMINB
 #define GMINB 4          /* resident CTAs per SM the kernel is compiled for (register cap 65536 / (128 * GMINB)) */
