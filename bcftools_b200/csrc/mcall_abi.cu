@@ -66,6 +66,8 @@ struct mcb_ctx
     uint8_t  *d_ploidy = nullptr;  int nploidy = 0, ploidy_cap = 0;  bool any_nondiploid = false;
     std::vector<uint8_t> h_ploidy;
     uint32_t *d_grp_off = nullptr, *d_grp_smpl = nullptr, *d_smpl2grp = nullptr;  int ngroups = 1;
+    bool grp_sorted = false;             /* every group lists its members in ascending sample order (what mcall_biallelic_groups.cu walks) */
+    int64_t opt_bgroups = 0;             /* -G, two-allele class: the warp-per-site kernel of mcall_biallelic_groups.cu (0: mcall_groups.cu only) */
     KernelScratch scratch;              /* device path (mcb_call_device) */
     /* device-path scratch */
     int32_t *d_lists = nullptr, *d_counts = nullptr;  int list_cap = 0;
@@ -181,6 +183,7 @@ extern "C" int mcb_set_option(mcb_ctx *ctx, const char *key, int64_t value)
     else if ( !strcmp(key,"concurrent") )    ctx->opt_concurrent = value;
     else if ( !strcmp(key,"order") )         ctx->opt_order = value;
     else if ( !strcmp(key,"multi") )         ctx->opt_multi = value;
+    else if ( !strcmp(key,"bgroups") )       ctx->opt_bgroups = value;
     else if ( !strcmp(key,"exact_phase1") )  { if ( value<0 || value>1 ) return MCB_EINVAL; ctx->opt_exact = value; }
     else if ( !strcmp(key,"mm_nst") )        { if ( value<0 || value>4 ) return MCB_EINVAL; ctx->opt_mm_nst = value; }
     else if ( !strncmp(key,"mm_nst_",7) && key[7]>='3' && key[7]<='5' && !key[8] ) { if ( value<0 || value>4 ) return MCB_EINVAL; ctx->opt_mm_nst_c[key[7]-'0'] = value; }
@@ -266,6 +269,10 @@ extern "C" int mcb_init(mcb_ctx **out, const mcb_params *params)
                 s2g[smp] = g;
             }
         ctx->ngroups = Q;
+        ctx->grp_sorted = true;
+        for (int g=0; g<Q; g++)
+            for (uint32_t i=params->grp_off[g]+1; i<params->grp_off[g+1]; i++)
+                if ( params->grp_smpl[i] <= params->grp_smpl[i-1] ) ctx->grp_sorted = false;
         CK(cudaMalloc(&ctx->d_grp_off, sizeof(uint32_t)*(Q+1)));
         CK(cudaMalloc(&ctx->d_grp_smpl, sizeof(uint32_t)*S));
         CK(cudaMalloc(&ctx->d_smpl2grp, sizeof(uint32_t)*S));
@@ -441,6 +448,27 @@ static int enqueue_class0(mcb_ctx *ctx, KArgs &a, const mcb_batch *b, const mcb_
     return MCB_OK;
 }
 
+/*  one stream per allele-count class (their persistent grids overlap) + fork / join events, created on first use  */
+static int ensure_class_streams(mcb_ctx *ctx)
+{
+    if ( ctx->cev_fork ) return MCB_OK;
+    CK(cudaEventCreateWithFlags(&ctx->cev_fork, cudaEventDisableTiming));
+    /* concurrent=2: stream priorities in launch order (5 alleles first = highest), so that a later class only
+       fills the SMs the earlier one leaves idle in the tail of its persistent grid */
+    int plo = 0, phi = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&plo, &phi));       /* numerically lower = higher priority */
+    for (int i=1; i<NCLASS; i++)
+    {
+        int pos = 0; { int64_t v = ctx->opt_order; int d[5] = {5,4,3,2,1}; for (int k=4; k>=0 && v>0; k--, v/=10) d[k] = (int)(v%10); for (int k=0; k<5; k++) if ( d[k]==i ) pos = k; }
+        int prio = std::min(plo, phi + pos);
+        if ( ctx->opt_concurrent>=2 ) CK(cudaStreamCreateWithPriority(&ctx->cstream[i], cudaStreamNonBlocking, prio));
+        else
+        CK(cudaStreamCreateWithFlags(&ctx->cstream[i], cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&ctx->cev_join[i], cudaEventDisableTiming));
+    }
+    return MCB_OK;
+}
+
 static int enqueue(mcb_ctx *ctx, const mcb_batch *b, const mcb_result *r, int32_t *lists, int32_t *counts, int list_stride, unsigned long long *cursor, KernelScratch &sc, cudaStream_t st)
 {
     CK(cudaMemsetAsync(counts, 0, sizeof(int32_t)*NCOUNTS, st));
@@ -471,7 +499,7 @@ static int enqueue(mcb_ctx *ctx, const mcb_batch *b, const mcb_result *r, int32_
         int grid = std::min(b->nsites, ctx->nsm*8);
         const size_t per_cta = groups_scratch_bytes(1, ctx->ngroups);
         grid = (int)std::max<int64_t>(1, std::min<int64_t>(grid, (int64_t)(512ll<<20)/(int64_t)per_cta));
-        const size_t need = groups_scratch_bytes(grid, ctx->ngroups);
+        const size_t per_class = (groups_scratch_bytes(grid, ctx->ngroups) + 255) & ~(size_t)255, need = 5*per_class;
         if ( need > sc.grp_bytes )
         {
             CK(cudaStreamSynchronize(st));
@@ -479,11 +507,36 @@ static int enqueue(mcb_ctx *ctx, const mcb_batch *b, const mcb_result *r, int32_
             CK(cudaMalloc(&sc.grp, need));
             sc.grp_bytes = need;
         }
-        for (int nals=1; nals<=5; nals++)
+        /* the classes run on their own streams (each with its own stretch of the per-CTA group records): the multi-allelic
+           ones are a few hundred sites per batch, i.e. a single wave bound by the latency of one site */
+        const bool gfork = ctx->opt_concurrent != 0;
+        if ( gfork )
+        {
+            { int src = ensure_class_streams(ctx); if ( src ) return src; }
+            CK(cudaEventRecord(ctx->cev_fork, st));
+        }
+        for (int nals=5; nals>=1; nals--)
         {
             a.site_list = lists + (size_t)nals*list_stride; a.site_count = counts + nals;
             a.work_counter = counts + NCLASS + nals;
-            CK(launch_groups_kernel(nals, a, sc.grp, grid, st));
+            cudaStream_t cs = gfork ? ctx->cstream[nals] : st;
+            if ( gfork ) CK(cudaStreamWaitEvent(cs, ctx->cev_fork, 0));
+            /* two alleles, up to 32 groups with ascending member lists, no FORMAT/GP: the warp-per-site kernel; what it has no
+               code for comes back on a fallback list that the general grouped kernel walks */
+            if ( nals==2 && ctx->opt_bgroups && ctx->grp_sorted && biallelic_groups_ok(a.nsmpl, ctx->ngroups) && !(a.gp && (a.output_tags & MCB_CALL_FMT_GP)) )
+            {
+                KArgs ab = a;
+                ab.fb_list = lists + (size_t)(NCLASS + nals)*list_stride;
+                ab.fb_count = counts + NCLASS + 8 + nals;
+                const int w = biallelic_groups_warps();
+                const int bgrid = (int)std::min<int64_t>(((int64_t)b->nsites + w - 1)/w, (int64_t)ctx->nsm*biallelic_groups_ctas_per_sm());
+                cudaError_t le = launch_biallelic_groups_kernel(ab, std::max(1, bgrid), cs);
+                if ( le!=cudaSuccess ) return cuda_fail(ctx, le, "two-allele grouped kernel");
+                launches++;
+                a.site_list = ab.fb_list; a.site_count = ab.fb_count;
+            }
+            CK(launch_groups_kernel(nals, a, (char*)sc.grp + (size_t)(nals-1)*per_class, grid, cs));
+            if ( gfork ) { CK(cudaEventRecord(ctx->cev_join[nals], cs)); CK(cudaStreamWaitEvent(st, ctx->cev_join[nals], 0)); }
             launches++;
         }
         { int rc0 = enqueue_class0(ctx, a, b, r, lists, counts, pl_es, sc, st); if ( rc0 ) return rc0; }
@@ -503,23 +556,7 @@ static int enqueue(mcb_ctx *ctx, const mcb_batch *b, const mcb_result *r, int32_
     }
     if ( fork )
     {
-        if ( !ctx->cev_fork )
-        {
-            CK(cudaEventCreateWithFlags(&ctx->cev_fork, cudaEventDisableTiming));
-            /* concurrent=2: stream priorities in launch order (5 alleles first = highest), so that a later class only
-               fills the SMs the earlier one leaves idle in the tail of its persistent grid */
-            int plo = 0, phi = 0;
-            CK(cudaDeviceGetStreamPriorityRange(&plo, &phi));       /* numerically lower = higher priority */
-            for (int i=1; i<NCLASS; i++)
-            {
-                int pos = 0; { int64_t v = ctx->opt_order; int d[5] = {5,4,3,2,1}; for (int k=4; k>=0 && v>0; k--, v/=10) d[k] = (int)(v%10); for (int k=0; k<5; k++) if ( d[k]==i ) pos = k; }
-                int prio = std::min(plo, phi + pos);
-                if ( ctx->opt_concurrent>=2 ) CK(cudaStreamCreateWithPriority(&ctx->cstream[i], cudaStreamNonBlocking, prio));
-                else
-                CK(cudaStreamCreateWithFlags(&ctx->cstream[i], cudaStreamNonBlocking));
-                CK(cudaEventCreateWithFlags(&ctx->cev_join[i], cudaEventDisableTiming));
-            }
-        }
+        { int src = ensure_class_streams(ctx); if ( src ) return src; }
         CK(cudaEventRecord(ctx->cev_fork, st));
     }
     /* launch order of the allele-count classes: digits of opt_order, first digit first (timing mode: ascending) */

@@ -91,5 +91,10 @@ size_t multi_smem_bytes(int nals, int block, int nsmpl, int nst);
 size_t multi_scratch_bytes(int nsmpl, int grid);
 cudaError_t multi_kernel_occupancy(int nals, int block, int nsmpl, int nst, int *blocks_per_sm);
 cudaError_t launch_multi_kernel(int nals, int block, const KArgs &a, int grid, cudaStream_t st);
+/*  warp-per-site kernel for grouped calling (-G) of two-allele sites (mcall_biallelic_groups.cu)  */
+bool biallelic_groups_ok(int nsmpl, int ngroups);
+int biallelic_groups_warps();
+int biallelic_groups_ctas_per_sm();
+cudaError_t launch_biallelic_groups_kernel(const KArgs &a, int grid, cudaStream_t st);
 cudaError_t launch_selftest_div(const DevTables *tab, int mode, unsigned long long n, unsigned long long seed, unsigned long long *mismatch, cudaStream_t st);
 }

@@ -129,6 +129,48 @@ def test_sample_groups(S, maxA, mode, flag, oracle_built):
     assert st["compared"] > 0, st
 
 
+@pytest.mark.parametrize("S,ng,flag,prior", [(64, 2, 0, False), (333, 5, abi.CALL_VARONLY, False), (1000, 16, 0, True), (1000, 17, abi.CALL_KEEPALT, False),
+                                             (2504, 5, 0, False), (2504, 26, 0, True), (640, 32, 0, False)])
+def test_two_allele_grouped_kernel(S, ng, flag, prior, oracle_built):
+    """-G on two-allele sites: the warp-per-site kernel of mcall_biallelic_groups.cu (sequential float32 AD sums per group, one
+    pass per group over the packed copy, per-sample group records in phase 2) against the reference; ploidy 0 / 1 / 2, samples
+    without data (PL = 0,0,0 and first-value-missing vectors), -F priors, sites whose ALT is the unseen allele (fallback)."""
+    from bcftools_b200 import mcall
+    rng = np.random.default_rng([S, ng, flag, 5])
+    R = 96
+    batch = parity.random_batch(rng, R, S, 2, zq=False, miss=False, minA=2)
+    for i in range(R):                      # whole-vector missing samples: first value missing, the rest vector_end
+        blk = batch.site_pl(i)
+        m = rng.random(S) < 0.03
+        blk[m] = abi.INT32_VECTOR_END
+        blk[m, 0] = abi.INT32_MISSING
+        if i % 11 == 3:
+            blk[rng.integers(0, S)] = [255, 255, 255]       # a genuine all-255 vector: the general kernel's
+    batch.unseen = np.where(np.arange(R) % 13 == 5, 1, 0).astype(np.uint8)
+    groups = [list(range(k, S, ng)) for k in range(ng)]
+    tab = np.full((3, S), 2, np.uint8)
+    tab[1, ::2] = 1
+    tab[2, ::3] = 1
+    tab[2, 1::5] = 0
+    batch.ploidy_id = rng.integers(0, 3, R).astype(np.uint16)
+    if prior:
+        batch.prior_an = rng.integers(10, 400, R).astype(np.int32)
+        batch.prior_ac = np.full((R, 2), abi.INT32_VECTOR_END, np.int32)
+        batch.prior_ac[:, 0] = (batch.prior_an * rng.random(R) * 0.5).astype(np.int32)
+    params = abi.CallParams(S, 2, flag=flag, output_tags=abi.CALL_FMT_GQ, groups=groups, use_prior=prior)
+    exp, _ = oracle_built.call(ORACLE(oracle_built), params, batch, tab)
+    with mcall.MCaller(params, ploidy_tab=tab, options={"bgroups": 1}) as mc:
+        got = mc.call_host(batch)
+        n_new = int(mc.stats()[0])
+    with mcall.MCaller(params, ploidy_tab=tab, options={"bgroups": 0}) as mc:
+        old = mc.call_host(batch)
+        n_old = int(mc.stats()[0])
+    assert n_new == n_old + 1                # the extra launch is the warp-per-site kernel
+    st = parity.compare(got, exp, params)
+    assert st["compared"] > 0, st
+    assert parity.compare(old, exp, params)["compared"] == st["compared"]
+
+
 @pytest.mark.parametrize("S,maxA,groups,flag,tags", [(12, 8, None, 0, abi.CALL_FMT_GQ), (40, 7, None, abi.CALL_VARONLY, abi.CALL_FMT_GQ | abi.CALL_FMT_GP),
                                                      (25, 9, 3, abi.CALL_KEEPALT, abi.CALL_FMT_GQ), (6, 32, None, 0, abi.CALL_FMT_GQ),
                                                      (150, 6, None, 0, abi.CALL_FMT_GQ)])
