@@ -67,7 +67,7 @@ struct mcb_ctx
     std::vector<uint8_t> h_ploidy;
     uint32_t *d_grp_off = nullptr, *d_grp_smpl = nullptr, *d_smpl2grp = nullptr;  int ngroups = 1;
     bool grp_sorted = false;             /* every group lists its members in ascending sample order (what mcall_biallelic_groups.cu walks) */
-    int64_t opt_bgroups = 0;             /* -G, two-allele class: the warp-per-site kernel of mcall_biallelic_groups.cu (0: mcall_groups.cu only) */
+    int64_t opt_bgroups = 1;             /* -G, two-allele class: the warp-per-site kernel of mcall_biallelic_groups.cu (0: mcall_groups.cu only) */
     KernelScratch scratch;              /* device path (mcb_call_device) */
     /* device-path scratch */
     int32_t *d_lists = nullptr, *d_counts = nullptr;  int list_cap = 0;
