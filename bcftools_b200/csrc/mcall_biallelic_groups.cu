@@ -31,7 +31,8 @@ namespace mcb {
 
 struct __align__(16) BGGroup
 {
-    float    scr_w[4];              /* float32 screen: weights of 0/0, 0/1, 1/1; [3] != 0: literal path only */
+    float    scr_w[4];              /* float32 screen, diploid samples: weights of 0/0, 0/1, 1/1; [3] != 0: literal path only */
+    float    scr_h[4];              /* ... haploid samples: weights of allele 0, (none), allele 1; [3] != 0: literal path only */
     double   q[2];                  /* (double)(float) normalised qsum of REF, ALT (mcall.c:1530-1535) */
     double   cf[5];                 /* pair {ALT,REF}: fa2 (ALT/ALT), fb2 (REF/REF), 2 fa fb, fa, fb (mcall.c:629-633, 642-643) */
     double   accN, accC, accP;      /* products over the group's samples: sum (data), sum (called), val (called); mantissas */
@@ -178,19 +179,22 @@ __global__ void __launch_bounds__(BG_WARPS*32, BG_MINCTA) mcall_biallelic_groups
             const bool gvalid = g < NG;
             const int beg = gvalid ? (int)a.grp_off[g] : 0, end = gvalid ? (int)a.grp_off[g+1] : 0;
             int mi = beg;
-            int s_cur = mi<end ? (int)a.grp_smpl[mi] : 0x7fffffff;
             float q = 0;
             if ( site_ad && nad>0 )
                 for (int c0=0; c0<S; c0+=CH)
                 {
                     const int cend = min(S, c0 + CH);
                     /* every lane: the fractions AD[a]/sum of its samples of the chunk (independent per sample) */
+                    int nxt[5];
+                    #pragma unroll
+                    for (int j=0; j<5; j++) nxt[j] = (j<nad && c0+lane<cend) ? __ldg(site_ad + (size_t)(c0+lane)*nad + j) : I32_VEC_END;
                     for (int s=c0+lane; s<cend; s+=32)
                     {
-                        const int32_t *ptr = site_ad + (size_t)s*nad;
                         int adv[5]; float sum = 0; int e = nad<5 ? nad : 5;
                         #pragma unroll
-                        for (int j=0; j<5; j++) adv[j] = j<nad ? __ldg(ptr + j) : I32_VEC_END;
+                        for (int j=0; j<5; j++) adv[j] = nxt[j];
+                        #pragma unroll
+                        for (int j=0; j<5; j++) nxt[j] = (j<nad && s+32<cend) ? __ldg(site_ad + (size_t)(s+32)*nad + j) : I32_VEC_END;     /* the next sample's AD is on its way */
                         #pragma unroll
                         for (int j=0; j<5; j++)
                         {
@@ -208,12 +212,20 @@ __global__ void __launch_bounds__(BG_WARPS*32, BG_MINCTA) mcall_biallelic_groups
                     }
                     __syncwarp();
                     /* lane (g, a): the float32 running sum over the members of g inside the chunk, in group order (adding +0 is exact) */
-                    while ( s_cur < cend )
+                    for (;;)
                     {
-                        const int s = s_cur;
-                        mi++;
-                        s_cur = mi<end ? (int)a.grp_smpl[mi] : 0x7fffffff;     /* the next index is on its way while this one is added */
-                        q = __fadd_rn(q, bg_lds_f32(buf_s + 8u*(uint32_t)(s-c0) + 4u*(uint32_t)al));
+                        /* four member indices per round: their loads are independent, the float32 additions stay in order */
+                        const int i0 = mi  <end ? (int)__ldg(a.grp_smpl + mi)   : 0x7fffffff, i1 = mi+1<end ? (int)__ldg(a.grp_smpl + mi+1) : 0x7fffffff;
+                        const int i2 = mi+2<end ? (int)__ldg(a.grp_smpl + mi+2) : 0x7fffffff, i3 = mi+3<end ? (int)__ldg(a.grp_smpl + mi+3) : 0x7fffffff;
+                        const uint32_t fo = buf_s + 4u*(uint32_t)al - 8u*(uint32_t)c0;
+                        if ( i0 >= cend ) break;
+                        q = __fadd_rn(q, bg_lds_f32(fo + 8u*(uint32_t)i0)); mi++;
+                        if ( i1 >= cend ) break;
+                        q = __fadd_rn(q, bg_lds_f32(fo + 8u*(uint32_t)i1)); mi++;
+                        if ( i2 >= cend ) break;
+                        q = __fadd_rn(q, bg_lds_f32(fo + 8u*(uint32_t)i2)); mi++;
+                        if ( i3 >= cend ) break;
+                        q = __fadd_rn(q, bg_lds_f32(fo + 8u*(uint32_t)i3)); mi++;
                     }
                     __syncwarp();
                 }
@@ -326,10 +338,12 @@ __global__ void __launch_bounds__(BG_WARPS*32, BG_MINCTA) mcall_biallelic_groups
             const bool live = r.live != 0;
             double accN = 1.0, accC = 1.0, accP = 1.0; int eN = 0, eC = 0, eP = 0;
             int cnt = 0, cnt_called = 0, ps0 = 0, ps1 = 0;
+            int s_n = beg+lane<end ? (int)__ldg(a.grp_smpl + beg + lane) : 0;
             #pragma unroll 1
             for (int mi=beg+lane; mi<end; mi+=32)
             {
-                const int s = (int)a.grp_smpl[mi];
+                const int s = s_n;
+                if ( mi+32 < end ) s_n = (int)__ldg(a.grp_smpl + mi + 32);
                 const uint32_t ad = buf_s + 3u*(uint32_t)s;
                 const uint32_t pa = bg_ldsu8(ad), pb = bg_ldsu8(ad + 1u), pc = bg_ldsu8(ad + 2u);
                 const uint32_t tri = pa | pb<<8 | pc<<16;
@@ -440,6 +454,9 @@ __global__ void __launch_bounds__(BG_WARPS*32, BG_MINCTA) mcall_biallelic_groups
                 bool scr = r.als==3u;
                 r.scr_w[0] = screen_weight(r.q[0], r.q[0], 1.0, scr); r.scr_w[1] = screen_weight(r.q[1], r.q[0], 2.0, scr);
                 r.scr_w[2] = screen_weight(r.q[1], r.q[1], 1.0, scr); r.scr_w[3] = scr ? 0.f : 1.f;
+                bool scrh = r.als==3u;      /* haploid: lk = pdg*q over the two alleles (mcall.c:793-808): the same screen with no het term */
+                r.scr_h[0] = screen_weight(r.q[0], 1.0, 1.0, scrh); r.scr_h[1] = 0.f;
+                r.scr_h[2] = screen_weight(r.q[1], 1.0, 1.0, scrh); r.scr_h[3] = scrh ? 0.f : 1.f;
             }
         }
         #pragma unroll
@@ -505,14 +522,17 @@ __global__ void __launch_bounds__(BG_WARPS*32, BG_MINCTA) mcall_biallelic_groups
             int2 *out_gt = a.gt ? reinterpret_cast<int2*>(a.gt) + (size_t)site*S : nullptr;
             int32_t *out_gq = want_gq ? a.gq + (size_t)site*S : nullptr;
             const bool scr_site = nals_new==2 && map0==0 && map1==1 && want_gq;
+            int pld_n = lane<S ? (int)__ldg(ploidy + lane) : 0;
+            uint32_t gi_n = lane<S ? __ldg(a.smpl2grp + lane) : 0;
             #pragma unroll 1
             for (int s=lane; s<S; s+=32)
             {
                 const uint32_t ad = buf_s + 3u*(uint32_t)s;
                 const uint32_t pa = bg_ldsu8(ad), pb = bg_ldsu8(ad + 1u), pc = bg_ldsu8(ad + 2u);
                 const uint32_t tri = pa | pb<<8 | pc<<16;
-                const int pld = (int)__ldg(ploidy + s);
-                const uint32_t gi = __ldg(a.smpl2grp + s);
+                const int pld = pld_n;
+                const uint32_t gi = gi_n;
+                if ( s+32 < S ) { pld_n = (int)__ldg(ploidy + s + 32); gi_n = __ldg(a.smpl2grp + s + 32); }
                 const bool esc = tri==0xffffffu, has = !esc && tri!=0u;
                 int gt0, gt1, gq = 0;
                 if ( !pld ) { gt0 = MCB_GT_MISSING; gt1 = I32_VEC_END; }
@@ -520,12 +540,12 @@ __global__ void __launch_bounds__(BG_WARPS*32, BG_MINCTA) mcall_biallelic_groups
                 else if ( ref_gt ) { gt0 = MCB_GT_UNPHASED(0); gt1 = pld==2 ? MCB_GT_UNPHASED(0) : I32_VEC_END; ac0 += pld; }
                 else
                 {
-                    const uint32_t r_s = grp_s + gi*(uint32_t)sizeof(BGGroup);
+                    const uint32_t r_s = grp_s + gi*(uint32_t)sizeof(BGGroup) + (pld==2 ? 0u : 16u);       /* scr_w / scr_h */
                     float w0, w1, w2, wn;
                     asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(w0), "=f"(w1), "=f"(w2), "=f"(wn) : "r"(r_s));
                     int g0, g1;
                     bool done = false;
-                    if ( scr_site && pld==2 && wn==0.f )
+                    if ( scr_site && wn==0.f )
                     {
                         int k, q;
                         if ( screen2_call(pa, pb, pc, w0, w1, w2, plf_s, gqw_s, k, q) ) { g0 = k==2 ? 1 : 0; g1 = k ? 1 : 0; gq = q; done = true; }

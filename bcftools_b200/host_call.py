@@ -88,7 +88,8 @@ def replay(params, batch, ploidy_tab=None, max_records=64, typed=False, async_fl
             res.ret[i], res.site_flags[i] = out.ret, out.site_flags
             if out.ret <= 0:
                 continue
-            res.als_new[i], res.qual[i], res.an[i] = out.als_new, out.qual, out.an
+            res.als_new[i], res.an[i] = out.als_new, out.an
+            res.qual.view(np.uint32)[i] = C.c_uint32.from_buffer(out, B200Out.qual.offset).value      # the exact bits: missing QUAL is a signalling NaN pattern
             res.als_map[i] = np.ctypeslib.as_array(out.als_map, (params.max_nals,))
             res.ac[i] = np.ctypeslib.as_array(out.ac, (params.max_nals,))
             if typed:
