@@ -26,7 +26,7 @@ for l in dis.split("\n"):
     m = re.match(r"\s*\.section\s+\.text\.(\S+?),", l)
     if m:
         name = subprocess.run(["c++filt", m.group(1)], capture_output=True, text=True).stdout.strip()
-        norm = lambda t: re.sub(r"\((?:int|bool)\)|\s", "", t)
+        norm = lambda t: re.sub(r"\((?:int|bool)\)|\s", "", t).replace("<false>", "<0>").replace("<true>", "<1>")
         active = norm(kpat) in norm(name)
         continue
     if not active:
