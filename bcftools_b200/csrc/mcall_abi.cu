@@ -497,9 +497,9 @@ static int enqueue(mcb_ctx *ctx, const mcb_batch *b, const mcb_result *r, int32_
         if ( !b->ad || !b->ad_off || !b->nad ) return MCB_EQS;      /* mcall.c:1476 */
         a.grp_off = ctx->d_grp_off; a.grp_smpl = ctx->d_grp_smpl; a.smpl2grp = ctx->d_smpl2grp; a.ngroups = ctx->ngroups;
         int grid = std::min(b->nsites, ctx->nsm*8);
-        const size_t per_cta = groups_scratch_bytes(1, ctx->ngroups);
+        const size_t per_cta = groups_scratch_bytes(1, ctx->ngroups, a.nsmpl);
         grid = (int)std::max<int64_t>(1, std::min<int64_t>(grid, (int64_t)(512ll<<20)/(int64_t)per_cta));
-        const size_t per_class = (groups_scratch_bytes(grid, ctx->ngroups) + 255) & ~(size_t)255, need = 5*per_class;
+        const size_t per_class = (groups_scratch_bytes(grid, ctx->ngroups, a.nsmpl) + 255) & ~(size_t)255, need = 5*per_class;
         if ( need > sc.grp_bytes )
         {
             CK(cudaStreamSynchronize(st));
@@ -509,14 +509,22 @@ static int enqueue(mcb_ctx *ctx, const mcb_batch *b, const mcb_result *r, int32_
         }
         /* the classes run on their own streams (each with its own stretch of the per-CTA group records): the multi-allelic
            ones are a few hundred sites per batch, i.e. a single wave bound by the latency of one site */
-        const bool gfork = ctx->opt_concurrent != 0;
+        /* time_kernels=1: the classes one after the other on the caller's stream, in ascending order, an event after each */
+        const bool gtiming = ctx->opt_time_kernels && lists==ctx->d_lists;
+        const bool gfork = ctx->opt_concurrent != 0 && !gtiming;
         if ( gfork )
         {
             { int src = ensure_class_streams(ctx); if ( src ) return src; }
             CK(cudaEventRecord(ctx->cev_fork, st));
         }
-        for (int nals=5; nals>=1; nals--)
+        if ( gtiming )
         {
+            for (int i=0; i<=NCLASS; i++) if ( !ctx->kev[i] ) CK(cudaEventCreate(&ctx->kev[i]));
+            CK(cudaEventRecord(ctx->kev[0], st));
+        }
+        for (int step=0; step<5; step++)
+        {
+            const int nals = gtiming ? step+1 : 5-step;
             a.site_list = lists + (size_t)nals*list_stride; a.site_count = counts + nals;
             a.work_counter = counts + NCLASS + nals;
             cudaStream_t cs = gfork ? ctx->cstream[nals] : st;
@@ -537,12 +545,13 @@ static int enqueue(mcb_ctx *ctx, const mcb_batch *b, const mcb_result *r, int32_
             }
             CK(launch_groups_kernel(nals, a, (char*)sc.grp + (size_t)(nals-1)*per_class, grid, cs));
             if ( gfork ) { CK(cudaEventRecord(ctx->cev_join[nals], cs)); CK(cudaStreamWaitEvent(st, ctx->cev_join[nals], 0)); }
+            if ( gtiming ) CK(cudaEventRecord(ctx->kev[nals], st));
             launches++;
         }
         { int rc0 = enqueue_class0(ctx, a, b, r, lists, counts, pl_es, sc, st); if ( rc0 ) return rc0; }
         ctx->stats[0] += launches + 1;
         ctx->stats[1] += b->nsites;
-        ctx->kev_valid = false;
+        ctx->kev_valid = gtiming;
         return MCB_OK;
     }
     const bool timing = ctx->opt_time_kernels && lists==ctx->d_lists;

@@ -25,6 +25,9 @@
 namespace mcb {
 
 #define BG_WARPS     8
+#ifndef BG_AD_ASYNC
+#define BG_AD_ASYNC  1                  /* phase 0: FORMAT/AD chunks through cp.async when a site has two values per sample */
+#endif
 #define BG_MINCTA    3
 #define BG_MAXGRP    32
 #define BG_SITE_BYTES 128
@@ -61,6 +64,14 @@ __device__ __forceinline__ double bg_logsumexp2(double a, double b)
 }
 __device__ __forceinline__ uint32_t bg_ldsu8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ void bg_sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void bg_cp_async16(uint32_t dst, const void *src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(__cvta_generic_to_global(src)) : "memory");
+}
+__device__ __forceinline__ void bg_cp_async_wait_all()
+{
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
 __device__ __forceinline__ void bg_sts_f32x2(uint32_t a, float x, float y) { asm volatile("st.shared.v2.f32 [%0], {%1,%2};" :: "r"(a), "f"(x), "f"(y) : "memory"); }
 __device__ __forceinline__ float bg_lds_f32(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
 __device__ __forceinline__ void bg_stg64(void *p, int x, int y) { asm volatile("st.global.cs.v2.s32 [%0], {%1,%2};" :: "l"(p), "r"(x), "r"(y) : "memory"); }
@@ -152,7 +163,7 @@ __global__ void __launch_bounds__(BG_WARPS*32, BG_MINCTA) mcall_biallelic_groups
     __syncthreads();
 
     const int S = a.nsmpl, nsites = *a.site_count;
-    const int CH = buf_bytes >> 3;                  /* samples per chunk of phase 0: two float32 fractions each */
+    const int CH = (buf_bytes >> 4) << 1;           /* samples per chunk of phase 0: two float32 fractions each; even, so that chunks start on 16 bytes */
     const int want_gq = (a.gq && (a.output_tags & (MCB_CALL_FMT_GQ|MCB_CALL_FMT_GP))) ? 1 : 0;
 
     for (;;)
@@ -171,6 +182,7 @@ __global__ void __launch_bounds__(BG_WARPS*32, BG_MINCTA) mcall_biallelic_groups
         const int nad = a.nad ? a.nad[site] : 0;
         const int32_t *site_ad = a.ad ? a.ad + a.ad_off[site] : nullptr;
         uint32_t sflags = (site_ad && nad>0) ? 0 : MCB_SITE_NO_QS;
+        const bool ad_async = BG_AD_ASYNC && nad==2 && (reinterpret_cast<uintptr_t>(site_ad) & 15)==0;
 
         /* =========================== phase 0: the groups' quality sums ============================== */
         for (int gbase=0; gbase<NG; gbase+=16)
@@ -184,6 +196,43 @@ __global__ void __launch_bounds__(BG_WARPS*32, BG_MINCTA) mcall_biallelic_groups
                 for (int c0=0; c0<S; c0+=CH)
                 {
                     const int cend = min(S, c0 + CH);
+                    if ( ad_async )
+                    {
+                        /* two AD values per sample on a 16-byte boundary: the chunk's rows come in with asynchronous copies (one
+                           round trip per chunk, not per 32 samples) and are turned into fractions in place */
+                        const int n = cend - c0, n16 = n >> 1;
+                        const char *src = reinterpret_cast<const char*>(site_ad) + (size_t)c0*8;
+                        for (int i=lane; i<n16; i+=32) bg_cp_async16(buf_s + 16u*(uint32_t)i, src + 16*(size_t)i);
+                        if ( (n & 1) && lane==0 )
+                        {
+                            const int2 v = __ldg(reinterpret_cast<const int2*>(src) + (n-1));
+                            bg_sts_f32x2(buf_s + 8u*(uint32_t)(n-1), __int_as_float(v.x), __int_as_float(v.y));
+                        }
+                        bg_cp_async_wait_all();
+                        __syncwarp();
+                        for (int i=lane; i<n; i+=32)
+                        {
+                            const uint32_t ad_s = buf_s + 8u*(uint32_t)i;
+                            const int a0 = __float_as_int(bg_lds_f32(ad_s)), a1 = __float_as_int(bg_lds_f32(ad_s + 4u));
+                            float sum = 0; int e = 2;
+                            if ( a0==I32_VEC_END ) e = 0;
+                            else
+                            {
+                                if ( a0!=I32_MISSING ) sum = __fadd_rn(sum, (float)a0);
+                                if ( a1==I32_VEC_END ) e = 1;
+                                else if ( a1!=I32_MISSING ) sum = __fadd_rn(sum, (float)a1);
+                            }
+                            float f0 = 0, f1 = 0;
+                            if ( sum!=0 )
+                            {
+                                if ( 0<e && a0!=I32_MISSING ) f0 = __fdiv_rn((float)a0, sum);
+                                if ( 1<e && a1!=I32_MISSING ) f1 = __fdiv_rn((float)a1, sum);
+                            }
+                            bg_sts_f32x2(ad_s, f0, f1);
+                        }
+                    }
+                    else
+                    {
                     /* every lane: the fractions AD[a]/sum of its samples of the chunk (independent per sample) */
                     int nxt[5];
                     #pragma unroll
@@ -209,6 +258,7 @@ __global__ void __launch_bounds__(BG_WARPS*32, BG_MINCTA) mcall_biallelic_groups
                             if ( 1<e && adv[1]!=I32_MISSING ) f1 = __fdiv_rn((float)adv[1], sum);
                         }
                         bg_sts_f32x2(buf_s + 8u*(uint32_t)(s-c0), f0, f1);
+                    }
                     }
                     __syncwarp();
                     /* lane (g, a): the float32 running sum over the members of g inside the chunk, in group order (adding +0 is exact) */

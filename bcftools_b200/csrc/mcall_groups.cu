@@ -18,11 +18,19 @@
 namespace mcb {
 
 #ifndef GBLOCK
-#define GBLOCK 128
+#define GBLOCK 160          /* five warps: the five super-population groups of a 1000G-shaped call take one round of phase A */
 #endif
 #define GNW    (GBLOCK/32)
+/*  resident CTAs per SM the instances are compiled for (register cap 65536 / (GBLOCK * n)): up to three alleles 64 registers,
+ *  four alleles 96, five alleles 200 (no spills; a batch holds few such sites).  Sweeps: profiles/r02_groups_cta_regcap_sweep.log  */
 #ifndef GMINB
-#define GMINB 4          /* resident CTAs per SM the kernel is compiled for (register cap 65536 / (128 * GMINB)) */
+#define GMINB 2
+#endif
+#ifndef GMINB3
+#define GMINB3 6
+#endif
+#ifndef GMINB4
+#define GMINB4 4
 #endif
 #ifndef BIG_GROUP
 #define BIG_GROUP 64        /* groups of at least this many samples are reduced by the whole CTA, sample-parallel */
@@ -35,6 +43,11 @@ struct GroupRec
     uint32_t als;           /* grp->als */
     int nals, has_max, pad;
 };
+
+#define GS_NODATA  (-2.0)
+#define GS_GENERIC (-1.0)
+__host__ __device__ inline size_t groups_rec_bytes(int ngroups) { return ((size_t)ngroups*sizeof(GroupRec) + 15) & ~(size_t)15; }
+__host__ __device__ inline size_t groups_cta_bytes(int ngroups, int nsmpl) { return groups_rec_bytes(ngroups) + (((size_t)nsmpl*sizeof(double) + 15) & ~(size_t)15); }
 
 struct GSite                /* site decision record, shared memory */
 {
@@ -80,8 +93,21 @@ __device__ __forceinline__ double pl_to_p_dev(const double *s_pl2p, const DevTab
     return (unsigned)v < (unsigned)MCB_PL2P_BIG ? tab->pl2p_big[v] : 0.0;
 }
 
+/*  GQ from the largest and the sum of the genotype posteriors (mcall.c:843-878): phred of 1 - max/sum through the
+ *  threshold table, 127 when the ratio is not a number  */
+__device__ __forceinline__ int groups_gq(double gmax, double gsum, const double *s_thr)
+{
+    const double xx = __dadd_rn(1.0, -__ddiv_rn(gmax, gsum));
+    if ( !(xx==xx) ) return 127;
+    int k = __float2int_rz(-3.0102999f*lg2_approx((float)xx));
+    k = max(0, min(127, k));
+    if ( xx <= s_thr[k+1] ) { k++; while ( xx <= s_thr[k+1] ) k++; }
+    else while ( xx > s_thr[k] ) k--;
+    return k;
+}
+
 template<int NALS>
-__global__ void __launch_bounds__(GBLOCK, GMINB) mcall_groups_kernel(const KArgs a, GroupRec *scratch)
+__global__ void __launch_bounds__(GBLOCK, (NALS<=3 ? GMINB3 : (NALS==4 ? GMINB4 : GMINB))) mcall_groups_kernel(const KArgs a, GroupRec *scratch)
 {
     using S = Shape<NALS>;
     constexpr int G = S::G, NPAIR = S::NPAIR, NSUB = S::NSUB;
@@ -93,6 +119,7 @@ __global__ void __launch_bounds__(GBLOCK, GMINB) mcall_groups_kernel(const KArgs
     __shared__ int    s_chunk[GNW][32][16];     /* PL rows of 32 samples of the group, fetched together: one global round trip per 32 samples */
     __shared__ float  s_adc[GNW][32][5];        /* per-sample AD fractions of the chunk */
     __shared__ unsigned char s_pld[GNW][32];
+    __shared__ int    s_sid[GNW][32];
     /* block-wide path for big groups (>= BIG_GROUP samples): same data flow as phase 1 of the pooled kernel */
     constexpr int NTRI = S::NTRI, NACC = S::NACC;
     __shared__ float  s_qf[GNW][NALS];
@@ -106,7 +133,11 @@ __global__ void __launch_bounds__(GBLOCK, GMINB) mcall_groups_kernel(const KArgs
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nsmpl = a.nsmpl, ngrp = a.ngroups;
-    GroupRec *grec = scratch + (size_t)blockIdx.x*ngrp;
+    char *cta_scratch = reinterpret_cast<char*>(scratch) + (size_t)blockIdx.x*groups_cta_bytes(ngrp, nsmpl);
+    GroupRec *grec = reinterpret_cast<GroupRec*>(cta_scratch);
+    /* per-sample normaliser sum_j p[j] written by phase A and read by phase C (the site's samples are partitioned by the
+       groups, mcall_abi.cu checks it): > 0 the sum, GS_NODATA a row of zeros, GS_GENERIC a row with missing values */
+    double *ssum = reinterpret_cast<double*>(cta_scratch + groups_rec_bytes(ngrp));
 
     for (int i=tid; i<256; i+=GBLOCK) s_pl2p[i] = a.tab->pl2p[i];
     for (int i=tid; i<130; i+=GBLOCK) s_thr[i] = i<128 ? a.tab->gq_thr[i] : -1.0;
@@ -268,6 +299,7 @@ __global__ void __launch_bounds__(GBLOCK, GMINB) mcall_groups_kernel(const KArgs
                         #pragma unroll
                         for (int j=0; j<G; j++) s_chunk[warp][lane][j] = site_pl[(size_t)s*G + j];
                         s_pld[warp][lane] = ploidy[s];
+                        s_sid[warp][lane] = s;
                     }
                 }
                 __syncwarp();
@@ -277,7 +309,8 @@ __global__ void __launch_bounds__(GBLOCK, GMINB) mcall_groups_kernel(const KArgs
                     int *row = s_chunk[warp][k];
                     int v = lane<G ? row[lane] : 0;
                     bool data = true;
-                    if ( __any_sync(0xffffffffu, v<0) )
+                    const bool neg = __any_sync(0xffffffffu, v<0);
+                    if ( neg )
                     {
                         int ok = 0;
                         if ( lane==0 ) ok = fix_missing_local(row, NALS, unseen);
@@ -287,12 +320,14 @@ __global__ void __launch_bounds__(GBLOCK, GMINB) mcall_groups_kernel(const KArgs
                         data = ok && !__any_sync(0xffffffffu, v<0);
                     }
                     if ( !__any_sync(0xffffffffu, v!=0) ) data = false;      /* PL=0,..,0: no data (mcall.c:529-537) */
+                    if ( lane==0 && (neg || !data) ) ssum[s_sid[warp][k]] = neg ? GS_GENERIC : GS_NODATA;
                     if ( !data ) continue;
                     if ( lane<G ) s_p[warp][lane] = pl_to_p_dev(s_pl2p, a.tab, v, &wflags);
                     __syncwarp();
                     double sum = s_p[warp][0];
                     #pragma unroll
                     for (int j=1; j<G; j++) sum = __dadd_rn(sum, s_p[warp][j]);
+                    if ( lane==0 && !neg ) ssum[s_sid[warp][k]] = sum > 0 ? sum : GS_GENERIC;
                     const int pld = s_pld[warp][k];
                     if ( live && lane<NSUB )
                     {
@@ -512,8 +547,10 @@ __global__ void __launch_bounds__(GBLOCK, GMINB) mcall_groups_kernel(const KArgs
                 int orv = 0;
                 #pragma unroll
                 for (int j=0; j<G; j++) { pl[j] = site_pl[(size_t)smp*G + j]; orv |= pl[j]; }
-                if ( orv<0 )
+                const bool neg = orv<0;
+                if ( neg )
                 {
+                    ssum[smp] = GS_GENERIC;
                     int tmp[16];
                     #pragma unroll
                     for (int j=0; j<G; j++) tmp[j] = pl[j];
@@ -523,12 +560,13 @@ __global__ void __launch_bounds__(GBLOCK, GMINB) mcall_groups_kernel(const KArgs
                     for (int j=0; j<G; j++) { if ( ok ) pl[j] = tmp[j]; orv |= pl[j]; }
                     if ( !ok || orv<0 ) continue;
                 }
-                if ( orv==0 ) continue;
+                if ( orv==0 ) { if ( !neg ) ssum[smp] = GS_NODATA; continue; }
                 #pragma unroll
                 for (int j=0; j<G; j++) p[j] = pl_to_p_dev(s_pl2p, a.tab, pl[j], &bflags);
                 double sum = p[0];
                 #pragma unroll
                 for (int j=1; j<G; j++) sum = __dadd_rn(sum, p[j]);
+                if ( !neg ) ssum[smp] = sum > 0 ? sum : GS_GENERIC;
                 const int pld = ploidy[smp];
                 #pragma unroll
                 for (int k=0; k<NALS; k++) plsum[k] += pl[hom_idx(k)];
@@ -811,6 +849,98 @@ __global__ void __launch_bounds__(GBLOCK, GMINB) mcall_groups_kernel(const KArgs
                 const int s = sb + tid;
                 if ( s>=nsmpl ) continue;
                 const GroupRec &r = grec[a.smpl2grp[s]];
+                const int pld = ploidy[s];
+                /* ---- the common cases without the full row: phase A left the sample's normaliser, so only the PLs of the
+                        group's own genotypes (at most three alleles) and of the kept genotypes are fetched; same expressions
+                        in the same order as the general code below */
+                {
+                    const double sv = ssum[s];
+                    const int rn = r.nals;
+                    if ( !want_gp && pld<=2 && sv!=GS_GENERIC && (!pld || sv==GS_NODATA || ref_gt || (rn>=1 && rn<=3)) )
+                    {
+                        const int32_t *row = site_pl + (size_t)s*G;
+                        int gt0, gt1, gq = 0;
+                        if ( !pld ) { gt0 = MCB_GT_MISSING; gt1 = I32_VEC_END; }
+                        else if ( sv==GS_NODATA ) { gt0 = MCB_GT_MISSING; gt1 = pld==2 ? MCB_GT_MISSING : I32_VEC_END; }
+                        else if ( ref_gt )
+                        {
+                            gt0 = MCB_GT_UNPHASED(0); gt1 = pld==2 ? MCB_GT_UNPHASED(0) : I32_VEC_END;
+                            acc += (unsigned long long)pld;
+                        }
+                        else
+                        {
+                            uint32_t m = r.als;
+                            int al[3], nal[3]; double q[3];
+                            #pragma unroll
+                            for (int i=0; i<3; i++)
+                            {
+                                al[i] = m ? __ffs(m) - 1 : 0; m &= m - 1;
+                                nal[i] = st.als_map[al[i]]; q[i] = r.q[al[i]];
+                            }
+                            double lkh[3] = {0,0,0}, lkt[3] = {0,0,0};
+                            double best = 0; int g0 = 0, g1 = 0;
+                            #pragma unroll
+                            for (int x=0; x<3; x++)             /* homozygous / haploid (mcall.c:793-808) */
+                                if ( x<rn )
+                                {
+                                    const double pdg = __ddiv_rn(pl_to_p_dev(s_pl2p, a.tab, row[hom_idx(al[x])], &tflags), sv);
+                                    lkh[x] = pld==2 ? __dmul_rn(__dmul_rn(pdg, q[x]), q[x]) : __dmul_rn(pdg, q[x]);
+                                    if ( best < lkh[x] ) { best = lkh[x]; g0 = nal[x]; }
+                                }
+                            double gmax = 0, gsum = 0;
+                            auto post = [&](double lk) { const double gv = (double)__double2float_rn(lk); if ( gmax < gv ) gmax = gv; gsum = __dadd_rn(gsum, gv); };
+                            if ( pld==2 )
+                            {
+                                g1 = g0;
+                                #pragma unroll
+                                for (int x=1; x<3; x++)         /* heterozygous (mcall.c:812-834) */
+                                    #pragma unroll
+                                    for (int y=0; y<x; y++)
+                                        if ( x<rn )
+                                        {
+                                            const double pdg = __ddiv_rn(pl_to_p_dev(s_pl2p, a.tab, row[gt_idx(al[x],al[y])], &tflags), sv);
+                                            const double lk = __dmul_rn(__dmul_rn(__dmul_rn(2.0,pdg), q[x]), q[y]);
+                                            lkt[x*(x-1)/2 + y] = lk;
+                                            if ( best < lk ) { best = lk; g0 = nal[y]; g1 = nal[x]; }
+                                        }
+                                gt0 = MCB_GT_UNPHASED(g0); gt1 = MCB_GT_UNPHASED(g1);
+                                acc += (1ull << (12*min(g0,4))) + (1ull << (12*min(g1,4)));
+                                if ( want_gq )                  /* the posteriors in the order of the new genotypes: the kept alleles ascend */
+                                {
+                                    post(lkh[0]);
+                                    if ( rn>1 ) { post(lkt[0]); post(lkh[1]); }
+                                    if ( rn>2 ) { post(lkt[1]); post(lkt[2]); post(lkh[2]); }
+                                }
+                            }
+                            else
+                            {
+                                gt0 = MCB_GT_UNPHASED(g0); gt1 = I32_VEC_END;
+                                acc += 1ull << (12*min(g0,4));
+                                if ( want_gq )                  /* haploid: the first r.nals entries only (mcall.c:843-850) */
+                                {
+                                    #pragma unroll
+                                    for (int x=0; x<3; x++) if ( x<rn && nal[x]<rn ) post(lkh[x]);
+                                }
+                            }
+                            if ( want_gq ) gq = groups_gq(gmax, gsum, s_thr);
+                        }
+                        if ( out_gt ) out_gt[s] = make_int2(gt0, gt1);
+                        if ( out_gq ) out_gq[s] = gq;
+                        if ( out_pl )               /* mcall.c:1158-1194 */
+                        {
+                            int32_t *dst = out_pl + (size_t)s*ngt_new;
+                            for (int k=0; k<ngt_new; k++)
+                            {
+                                int v;
+                                if ( pld==2 ) v = row[st.pl_map[k]];
+                                else if ( pld==1 && k<nals_new ) v = row[st.pl_map[hom_idx(k)]];
+                                else v = (pld==0 && k==0) ? I32_MISSING : I32_VEC_END;
+                                dst[k] = v;
+                            }
+                        }
+                        continue;
+                    }
+                }
                 int pl[G]; double p[G];
                 int orv = 0;
                 #pragma unroll
@@ -837,7 +967,6 @@ __global__ void __launch_bounds__(GBLOCK, GMINB) mcall_groups_kernel(const KArgs
                     #pragma unroll
                     for (int j=1; j<G; j++) sum = __dadd_rn(sum, p[j]);
                 }
-                const int pld = ploidy[s];
                 int gt0, gt1, gq = 0;
                 bool called = false;
                 float gps[G];               /* FORMAT/GP scratch in the NEW genotype order, zeroed like mcall.c:1605 */
@@ -903,16 +1032,7 @@ __global__ void __launch_bounds__(GBLOCK, GMINB) mcall_groups_kernel(const KArgs
                                 if ( gmax < gv ) gmax = gv;
                                 gsum = __dadd_rn(gsum, gv);
                             }
-                        const double xx = __dadd_rn(1.0, -__ddiv_rn(gmax, gsum));
-                        if ( !(xx==xx) ) gq = 127;
-                        else
-                        {
-                            int k = __float2int_rz(-3.0102999f*lg2_approx((float)xx));
-                            k = max(0, min(127, k));
-                            if ( xx <= s_thr[k+1] ) { k++; while ( xx <= s_thr[k+1] ) k++; }
-                            else while ( xx > s_thr[k] ) k--;
-                            gq = k;
-                        }
+                        gq = groups_gq(gmax, gsum, s_thr);
                     }
                 }
                 if ( out_gt ) out_gt[s] = make_int2(gt0, gt1);
@@ -989,7 +1109,7 @@ __global__ void __launch_bounds__(GBLOCK, GMINB) mcall_groups_kernel(const KArgs
     }
 }
 
-size_t groups_scratch_bytes(int grid, int ngroups) { return (size_t)grid*ngroups*sizeof(GroupRec); }
+size_t groups_scratch_bytes(int grid, int ngroups, int nsmpl) { return (size_t)grid*groups_cta_bytes(ngroups, nsmpl); }
 
 cudaError_t launch_groups_kernel(int nals, const KArgs &a, void *scratch, int grid, cudaStream_t st)
 {

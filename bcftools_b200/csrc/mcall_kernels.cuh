@@ -76,7 +76,7 @@ cudaError_t launch_site_kernel(int nals, bool ploidy, bool gp, int block, int pl
 cudaError_t launch_classify(const uint8_t *nals, int nsites, int32_t *lists, int32_t *counts, int list_stride, int max_nals, int32_t *ret, uint32_t *site_flags, int64_t *pl_off_out, cudaStream_t st);
 cudaError_t launch_unsupported(const int32_t *list, const int32_t *count, int32_t *ret, uint32_t *site_flags, const uint8_t *nals, int64_t *pl_off_out, cudaStream_t st);
 cudaError_t site_kernel_occupancy(int nals, bool ploidy, bool gp, int block, int pl_es, size_t ring_bytes, int *blocks_per_sm);
-size_t groups_scratch_bytes(int grid, int ngroups);
+size_t groups_scratch_bytes(int grid, int ngroups, int nsmpl);
 cudaError_t launch_groups_kernel(int nals, const KArgs &a, void *scratch, int grid, cudaStream_t st);
 void generic_scratch_bytes(int grid, int ngroups, int nsmpl, size_t *grp, size_t *pl, size_t *sum);
 cudaError_t launch_generic_kernel(const KArgs &a, void *grp_scratch, void *pl_scratch, void *sum_scratch, int grid, cudaStream_t st);

@@ -18,7 +18,7 @@ s = [x for x in sections if re.sub(r'\((?:int|bool)\)|\s', '', kpat) in re.sub(r
 idx = {h: i for i, h in enumerate(s['hdr'])}
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(obj)], cwd=tmp, capture_output=True)
-dis = subprocess.run(["nvdisasm", "-g", "-c"] + glob.glob(os.path.join(tmp, "*.cubin")), capture_output=True, text=True).stdout
+dis = "\n".join(subprocess.run(["nvdisasm", "-g", "-c", c], capture_output=True, text=True).stdout for c in sorted(glob.glob(os.path.join(tmp, "*.cubin"))))
 # the kernel's section in the disassembly: mangled names differ from the demangled one; match by template digits
 want = re.sub(r"[^0-9A-Za-z]", "", kpat)
 lines, cur_line, active = [], 0, False
