@@ -106,7 +106,7 @@ def test_two_allele_kernel_under_ploidy_vectors(S, flag, oracle_built):
 
 
 @pytest.mark.parametrize("S,maxA,mode,flag", [(30, 5, 3, 0), (9, 4, "single", abi.CALL_VARONLY), (200, 5, 7, abi.CALL_KEEPALT), (64, 3, 2, 0),
-                                              (300, 5, "mixed", 0), (700, 4, 3, abi.CALL_VARONLY)])
+                                              (300, 5, "mixed", 0), (700, 4, 3, abi.CALL_VARONLY), (1000, 5, 5, 0), (1300, 5, 13, 0)])
 def test_sample_groups(S, maxA, mode, flag, oracle_built):
     """-G: per-group quality sums from FORMAT/AD (float32, group order), per-group allele sets, union of the sets,
     QUAL of the best group, per-sample genotypes with the sample's own group (mcall.c:1466-1504, 1546-1561, 1608-1614)."""
@@ -127,6 +127,26 @@ def test_sample_groups(S, maxA, mode, flag, oracle_built):
     params = abi.CallParams(S, maxA, flag=flag, output_tags=abi.CALL_FMT_GQ, groups=groups)
     st = _run(params, batch, tab, oracle_built)
     assert st["compared"] > 0, st
+
+
+def test_grouped_call_reports_per_class_times():
+    """time_kernels=1 in a grouped call: the classes run one after the other and every class with sites reports a duration
+    (what scripts/quick_bench.py --classes and the sweeps under profiles/r02_groups_* read)."""
+    from bcftools_b200 import mcall
+    import torch
+    rng = np.random.default_rng(77)
+    S = 320
+    batch = parity.random_batch(rng, 64, S, 5)
+    params = abi.CallParams(S, 5, output_tags=abi.CALL_FMT_GQ, groups=[list(range(k, S, 4)) for k in range(4)])
+    from bcftools_b200 import device
+    db = device.DeviceBatch(batch)
+    dr = device.DeviceResult(db)
+    with mcall.MCaller(params, options={"time_kernels": 1}) as mc:
+        mc.call_device(db.c_struct(), dr.c_struct(), torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        ms = mc.kernel_times_ms()
+    cnt = np.bincount(batch.nals, minlength=6)
+    assert ms[0] > 0 and all(ms[k] > 0 for k in range(1, 6) if cnt[k])
 
 
 @pytest.mark.parametrize("S,ng,flag,prior", [(64, 2, 0, False), (333, 5, abi.CALL_VARONLY, False), (1000, 16, 0, True), (1000, 17, abi.CALL_KEEPALT, False),
