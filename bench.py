@@ -255,7 +255,7 @@ def main():
     ap.add_argument("--sustain", type=float, default=2.0, help="seconds of a second, long timed region (clocks under sustained load); 0 = off")
     ap.add_argument("--no-secondary", action="store_true", help="skip the C5 (mixed ploidy, -G groups) secondary workload")
     ap.add_argument("--secondary-sites", type=int, default=2048)
-    ap.add_argument("--job-sites-per-gpu", type=int, default=48, help="N>1: C4-shaped sites per GPU of the one-job strong-scaling leg (rank 0 drives all N GPUs)")
+    ap.add_argument("--job-sites-per-gpu", type=int, default=192, help="N>1: C4-shaped sites per GPU of the one-job strong-scaling leg (rank 0 drives all N GPUs)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -5,8 +5,10 @@
  *  GPU, each range balanced by its FORMAT/PL bytes.  Every device has its own mcb_ctx (mcall_b200.h), its own host thread
  *  and its own slab pipeline; there is no collective and no NVLink traffic on the data path.  Results come back in input
  *  order: the per-site and per-sample arrays are indexed by site, and compacted trimmed-PL blocks (mcb_result.pl_off_out)
- *  are concatenated range after range before the call returns -- the "ordered concatenation before BCF re-encoding" of the
- *  north star, equivalent to `bcftools concat` of region shards.
+ *  stand range after range, in site order at ascending offsets, when the call returns -- the "ordered concatenation before
+ *  BCF re-encoding" of the north star, equivalent to `bcftools concat` of region shards.  Every range compacts into its own
+ *  stretch of the output, so a few unused elements may separate two ranges' blocks (pl_off_out[] says where each site's
+ *  block is); mcb_job_set_option(job, "pack", 1) closes these gaps with a host-side move of the later ranges.
  *
  *  The same device may be listed more than once (two contexts on one GPU): that is how the single-GPU tests exercise the
  *  sharding logic.
@@ -25,7 +27,7 @@ int  mcb_job_init(mcb_job **job, const mcb_params *params, const int *devices, i
 void mcb_job_destroy(mcb_job *job);
 int  mcb_job_ndevices(const mcb_job *job);
 
-/*  mcb_set_ploidy / mcb_set_option on every context of the job  */
+/*  mcb_set_ploidy / mcb_set_option on every context of the job; the job's own option: "pack" (see above, default 0)  */
 int  mcb_job_set_ploidy(mcb_job *job, int id, const uint8_t *ploidy);
 int  mcb_job_set_option(mcb_job *job, const char *key, int64_t value);
 

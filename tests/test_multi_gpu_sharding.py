@@ -98,8 +98,8 @@ def test_job_over_several_contexts_equals_one_context(compact, typed):
     params, batch, tab = synth.make_batch("C3", 96, flag=abi.CALL_VARONLY)
     with mcall.MCaller(params, ploidy_tab=tab, options={"slab_bytes": 2 << 20}) as mc:
         one = mc.call_host(batch, compact=compact, typed=typed)
-    for devs in (devices, [0, 0, 0]):
-        with mcall.MJob(params, devs, ploidy_tab=tab, options={"slab_bytes": 2 << 20}) as job:
+    for devs, pack in ((devices, 0), ([0, 0, 0], 0), ([0, 0, 0], 1)):     # pack=1: the gaps between the ranges' blocks closed on the host
+        with mcall.MJob(params, devs, ploidy_tab=tab, options={"slab_bytes": 2 << 20, "pack": pack}) as job:
             got = job.call_host(batch, compact=compact, typed=typed)
         assert got.first_site[0] == 0 and got.first_site[-1] == batch.nsites and len(got.first_site) == len(devs) + 1
         for name in ("ret", "als_new", "als_map", "ac", "an", "site_flags"):
@@ -111,7 +111,7 @@ def test_job_over_several_contexts_equals_one_context(compact, typed):
         for i in range(batch.nsites):
             if one.ret[i] > 0 and not (one.site_flags[i] & abi.SITE_PL_DROPPED):
                 assert (got.site_pl(i) == one.site_pl(i)).all(), i
-        if compact:     # gap-free, range after range: the blocks of range k lie behind those of range k-1
+        if compact:     # range after range: the blocks of range k lie behind those of range k-1
             offs = got.pl_off_out
             for k in range(len(devs) - 1):
                 a = offs[got.first_site[k]:got.first_site[k + 1]]
