@@ -249,7 +249,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--sites", type=int, default=16384, help="unique synthetic sites generated per rank")
     ap.add_argument("--replicate", type=int, default=4, help="HBM copies of the unique sites forming one step")
-    ap.add_argument("--e2e-sites", type=int, default=8192)
+    ap.add_argument("--e2e-sites", type=int, default=16384, help="sites per mcb_call_host step of the e2e leg (default: every unique site of the synthetic batch)")
     ap.add_argument("--ref-sites", type=int, default=8192)
     ap.add_argument("--cpu-sites", type=int, default=2048)
     ap.add_argument("--sustain", type=float, default=2.0, help="seconds of a second, long timed region (clocks under sustained load); 0 = off")
