@@ -185,13 +185,17 @@ __global__ void __launch_bounds__(BG_WARPS*32, BG_MINCTA) mcall_biallelic_groups
         const bool ad_async = BG_AD_ASYNC && nad==2 && (reinterpret_cast<uintptr_t>(site_ad) & 15)==0;
 
         /* =========================== phase 0: the groups' quality sums ============================== */
-        for (int gbase=0; gbase<NG; gbase+=16)
+        /*  lane (g, allele) for 16 groups at a time: with more than 16 groups every lane carries two running sums, so that a chunk
+            of fractions is staged once and walked by both halves  */
+        const int al = lane & 1, NP = NG > 16 ? 2 : 1;
+        int mi2[2], end2[2]; float q2[2] = {0.f, 0.f};
+        #pragma unroll
+        for (int p=0; p<2; p++)
         {
-            const int g = gbase + (lane>>1), al = lane & 1;
-            const bool gvalid = g < NG;
-            const int beg = gvalid ? (int)a.grp_off[g] : 0, end = gvalid ? (int)a.grp_off[g+1] : 0;
-            int mi = beg;
-            float q = 0;
+            const int g = p*16 + (lane>>1);
+            mi2[p] = g<NG ? (int)a.grp_off[g] : 0; end2[p] = g<NG ? (int)a.grp_off[g+1] : 0;
+        }
+        {
             if ( site_ad && nad>0 )
                 for (int c0=0; c0<S; c0+=CH)
                 {
@@ -262,6 +266,11 @@ __global__ void __launch_bounds__(BG_WARPS*32, BG_MINCTA) mcall_biallelic_groups
                     }
                     __syncwarp();
                     /* lane (g, a): the float32 running sum over the members of g inside the chunk, in group order (adding +0 is exact) */
+                    #pragma unroll
+                    for (int p=0; p<2; p++)
+                    {
+                    if ( p>=NP ) continue;
+                    int mi = mi2[p]; const int end = end2[p]; float q = q2[p];
                     for (;;)
                     {
                         /* four member indices per round: their loads are independent, the float32 additions stay in order */
@@ -277,8 +286,19 @@ __global__ void __launch_bounds__(BG_WARPS*32, BG_MINCTA) mcall_biallelic_groups
                         if ( i3 >= cend ) break;
                         q = __fadd_rn(q, bg_lds_f32(fo + 8u*(uint32_t)i3)); mi++;
                     }
+                    mi2[p] = mi; q2[p] = q;
+                    }
                     __syncwarp();
                 }
+        }
+        #pragma unroll
+        for (int p=0; p<2; p++)
+        {
+            if ( p>=NP ) continue;
+            const int g = p*16 + (lane>>1);
+            const bool gvalid = g < NG;
+            const int beg = gvalid ? (int)a.grp_off[g] : 0, end = end2[p];
+            const float q = q2[p];
             const float qo = __shfl_xor_sync(0xffffffffu, q, 1);
             float qf0 = al ? qo : q, qf1 = al ? q : qo;
             /* -F prior (mcall.c:1507-1527) with this group's sample count, then normalisation (1530-1535) */
