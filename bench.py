@@ -436,12 +436,14 @@ def main():
                                           h2d_bytes_per_step=int(sub16.pl.nbytes + h2d - sub.pl.nbytes), d2h_bytes_per_step=int(d2ht),
                                           types="in: PL int16 (BCF_BT_INT16 as stored in the record); out: GT int8, GQ int8, PL int16, narrowed on the device")
 
-    # ---- secondary workload (rank 0): BASELINE config 5 -- every 2nd sample haploid -- pooled and with 5 -G groups, device-resident
+    # ---- secondary workloads (rank 0), device-resident: BASELINE config 5 -- every 2nd sample haploid -- pooled and with 5 -G
+    # groups; BASELINE config 2 -- 1,000 diploid samples, two-allele sites only
     secondary = None
     if rank == 0 and not args.no_secondary:
         secondary = {}
-        for name, groups in (("C5_pooled", 0), ("C5_groups5", 5)):
-            p5, h5, t5 = synth.make_batch("C5", args.secondary_sites, with_groups=groups)
+        for name, cfg5, nsites5, groups in (("C5_pooled", "C5", args.secondary_sites, 0), ("C5_groups5", "C5", args.secondary_sites, 5),
+                                            ("C2", "C2", 4 * args.secondary_sites, 0)):
+            p5, h5, t5 = synth.make_batch(cfg5, nsites5, with_groups=groups)
             p5.device = local_rank
             with mcall.MCaller(p5, ploidy_tab=t5) as m5:
                 d5 = device.DeviceBatch(h5, device=f"cuda:{local_rank}", replicate=args.replicate)
@@ -457,7 +459,7 @@ def main():
                 torch.cuda.synchronize()
                 s5 = e0.elapsed_time(e1) * 1e-3 / 5
                 secondary[name] = dict(value=d5.nsites * p5.nsmpl / s5, unit=UNIT, ms_per_step=1e3 * s5, sites_per_step=d5.nsites, nsmpl=p5.nsmpl,
-                                       groups=groups, ploidy="every 2nd sample haploid")
+                                       groups=groups, ploidy="every 2nd sample haploid" if cfg5 == "C5" else "diploid")
             del d5, r5
 
     # ---- N > 1: ONE job over the N GPUs of the box (mcall_job.h): BASELINE config 4 shape (100,000 samples), contiguous site
