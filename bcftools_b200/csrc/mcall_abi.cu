@@ -67,6 +67,7 @@ struct mcb_ctx
     std::vector<uint8_t> h_ploidy;
     uint32_t *d_grp_off = nullptr, *d_grp_smpl = nullptr, *d_smpl2grp = nullptr;  int ngroups = 1;
     bool grp_sorted = false;             /* every group lists its members in ascending sample order (what mcall_biallelic_groups.cu walks) */
+    int64_t opt_gorder = 35421;          /* -G: launch order of the allele-count classes on their streams, one decimal digit per class (sweep: profiles/r02_groups_launch_order.log) */
     int64_t opt_bgroups = 1;             /* -G, two-allele class: the warp-per-site kernel of mcall_biallelic_groups.cu (0: mcall_groups.cu only) */
     KernelScratch scratch;              /* device path (mcb_call_device) */
     /* device-path scratch */
@@ -184,6 +185,13 @@ extern "C" int mcb_set_option(mcb_ctx *ctx, const char *key, int64_t value)
     else if ( !strcmp(key,"order") )         ctx->opt_order = value;
     else if ( !strcmp(key,"multi") )         ctx->opt_multi = value;
     else if ( !strcmp(key,"bgroups") )       ctx->opt_bgroups = value;
+    else if ( !strcmp(key,"gorder") )
+    {
+        int seen = 0; int64_t v = value;
+        for (int i=0; i<5; i++) { const int d = (int)(v % 10); v /= 10; if ( d<1 || d>5 ) return MCB_EINVAL; seen |= 1<<d; }
+        if ( v || seen != 0x3e ) return MCB_EINVAL;      /* a permutation of 1..5 */
+        ctx->opt_gorder = value;
+    }
     else if ( !strcmp(key,"exact_phase1") )  { if ( value<0 || value>1 ) return MCB_EINVAL; ctx->opt_exact = value; }
     else if ( !strcmp(key,"mm_nst") )        { if ( value<0 || value>4 ) return MCB_EINVAL; ctx->opt_mm_nst = value; }
     else if ( !strncmp(key,"mm_nst_",7) && key[7]>='3' && key[7]<='5' && !key[8] ) { if ( value<0 || value>4 ) return MCB_EINVAL; ctx->opt_mm_nst_c[key[7]-'0'] = value; }
@@ -524,7 +532,8 @@ static int enqueue(mcb_ctx *ctx, const mcb_batch *b, const mcb_result *r, int32_
         }
         for (int step=0; step<5; step++)
         {
-            const int nals = gtiming ? step+1 : 5-step;
+            int nals = step+1;
+            if ( !gtiming ) { int64_t v = ctx->opt_gorder; for (int i=0; i<4-step; i++) v /= 10; nals = (int)(v % 10); }
             a.site_list = lists + (size_t)nals*list_stride; a.site_count = counts + nals;
             a.work_counter = counts + NCLASS + nals;
             cudaStream_t cs = gfork ? ctx->cstream[nals] : st;
