@@ -463,12 +463,15 @@ static int rd_size(rd_t *r, int *type)
     *type = b & 0xf;
     int n = b >> 4;
     if ( n==15 ) { int t2; const int n2 = rd_size(r, &t2); if ( n2!=1 ) { r->bad = 1; return 0; } n = rd_int(r, t2); }
+    /* a length from a damaged file: every element takes at least one byte, so it cannot exceed what is left of the block */
+    if ( r->bad || n<0 || (size_t)n > (size_t)(r->end - r->p) ) { r->bad = 1; return 0; }
     return n;
 }
+static size_t bt_size(int t) { return t==BT_INT8 || t==BT_CHAR ? 1 : (t==BT_INT16 ? 2 : ((t==BT_INT32 || t==BT_FLOAT) ? 4 : 0)); }
 static char *rd_str(rd_t *r, b200_vrec_t *rec, void *(*own)(b200_vrec_t*, void*))
 {
     int t; const int n = rd_size(r, &t);
-    if ( r->bad || (n && t!=BT_CHAR) || r->p + n > r->end ) { r->bad = 1; return NULL; }
+    if ( r->bad || (n && t!=BT_CHAR) || (size_t)n > (size_t)(r->end - r->p) ) { r->bad = 1; return NULL; }
     char *s = dupn((const char*)r->p, (size_t)n);
     r->p += n;
     return (char*) own(rec, s);
@@ -488,6 +491,7 @@ static void *own_ptr(b200_vrec_t *r, void *p)
 }
 static void fmt_typed(b200_str_t *s, rd_t *r, int n, int t)      /* one typed vector as VCF text */
 {
+    if ( n<0 || !bt_size(t) || (size_t)n*bt_size(t) > (size_t)(r->end - r->p) ) { r->bad = 1; return; }        /* the whole vector lies inside the block */
     if ( t==BT_CHAR ) { size_t l = 0; while ( l<(size_t)n && r->p[l] ) l++; b200_str_putsn(s, (const char*)r->p, l); if ( !l ) b200_str_putc(s, '.'); r->p += n; return; }
     int k = 0;
     for (int i=0; i<n; i++)
@@ -587,10 +591,12 @@ b200_vrec_t *b200_bcf_decode_rec(const b200_vhdr_t *h, const b200_bcfdict_t *d, 
             const int nv = rd_size(&q, &t);
             if ( q.bad ) break;
             f->n = nv;
+            if ( !bt_size(t) ? nv!=0 : (size_t)nv*bt_size(t) > (size_t)(q.end - q.p)/(nsmpl ? (size_t)nsmpl : 1) ) { q.bad = 1; break; }     /* nsmpl vectors of nv values must fit */
             if ( t==BT_CHAR )
             {
                 f->kind = B200_FMT_TEXT;
-                f->txt = (char**) own_ptr(rec, malloc(sizeof(char*)*(nsmpl ? nsmpl : 1)));
+                f->txt = (char**) own_ptr(rec, calloc(nsmpl ? nsmpl : 1, sizeof(char*)));
+                if ( !f->txt ) { q.bad = 1; break; }
                 for (int i=0; i<nsmpl; i++)
                 {
                     if ( q.p + nv > q.end ) { q.bad = 1; break; }
@@ -603,12 +609,14 @@ b200_vrec_t *b200_bcf_decode_rec(const b200_vhdr_t *h, const b200_bcfdict_t *d, 
             {
                 f->kind = B200_FMT_REAL;
                 f->fv = (float*) own_ptr(rec, malloc(sizeof(float)*((size_t)nv*nsmpl + 1)));
+                if ( !f->fv ) { q.bad = 1; break; }
                 for (size_t i=0; i<(size_t)nv*nsmpl; i++) { if ( q.p+4 > q.end ) { q.bad = 1; break; } f->fv[i] = f32_from(get_u32(q.p)); q.p += 4; }
             }
             else
             {
                 f->kind = !strcmp(f->key, "GT") ? B200_FMT_GT : B200_FMT_INT;
                 f->iv = (int32_t*) own_ptr(rec, malloc(sizeof(int32_t)*((size_t)nv*nsmpl + 1)));
+                if ( !f->iv ) { q.bad = 1; break; }
                 for (size_t i=0; i<(size_t)nv*nsmpl && !q.bad; i++) f->iv[i] = rd_int(&q, t);
             }
             rec->n_fmt++;
