@@ -129,6 +129,17 @@ def test_sample_groups(S, maxA, mode, flag, oracle_built):
     assert st["compared"] > 0, st
 
 
+def test_grouped_launch_order_option_takes_permutations_only():
+    from bcftools_b200 import mcall
+    params = abi.CallParams(64, 5, output_tags=abi.CALL_FMT_GQ, groups=[list(range(0, 64, 2)), list(range(1, 64, 2))])
+    with mcall.MCaller(params) as mc:
+        mc.set_option("gorder", 12345)
+        mc.set_option("gorder", 35421)
+        for bad in (11111, 5432, 123456, 12340, -1):
+            with pytest.raises(Exception):
+                mc.set_option("gorder", bad)
+
+
 def test_grouped_call_reports_per_class_times():
     """time_kernels=1 in a grouped call: the classes run one after the other and every class with sites reports a duration
     (what scripts/quick_bench.py --classes and the sweeps under profiles/r02_groups_* read)."""
