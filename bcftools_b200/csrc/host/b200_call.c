@@ -38,7 +38,8 @@ struct b200_batcher
 {
     mcb_ctx *ctx;
     int nsmpl, max_nals, cap;
-    int64_t pl_cap, ad_cap;
+    int64_t pl_cap, ad_cap;     /* elements of the PL / AD slabs */
+    int64_t pl_rec, ad_rec;     /* ... of one worst-case record (max_nals alleles) */
     b200_slabs_t set[2];
     int fill;               /* set the driver is queuing records into */
     int inflight;           /* set the worker is running, -1 = none */
@@ -265,8 +266,15 @@ void b200_mcall_init(b200_call_t *call)
 
     const int S = b->nsmpl, M = b->max_nals, R = b->cap;
     const int64_t gmax = (int64_t)M*(M+1)/2;
-    b->pl_cap = (int64_t)R*(((int64_t)S*gmax + 7) & ~7ll);      /* sites start on 16-byte boundaries (8 int16 / 4 int32 elements) */
-    b->ad_cap = (int64_t)R*(((int64_t)S*M + 3) & ~3ll);
+    /*  The PL / AD slabs hold a VOLUME, not max_records worst-case records (1,024 records x 2,504 samples x 528 genotypes of a
+     *  32-allele site would be 5.4 GB per slab, four slabs, all pinned): a batch is also full when less than one worst-case record
+     *  is left (b200_mcall).  Sites start on 16-byte boundaries (8 int16 / 4 int32 elements).  */
+    b->pl_rec = ((int64_t)S*gmax + 7) & ~7ll;
+    b->ad_rec = ((int64_t)S*M + 3) & ~3ll;
+    b->pl_cap = (int64_t)R*b->pl_rec;
+    b->ad_cap = (int64_t)R*b->ad_rec;
+    { const int64_t budget = 32ll<<20; if ( b->pl_cap > budget ) b->pl_cap = budget > 2*b->pl_rec ? budget : 2*b->pl_rec; }     /* elements */
+    { const int64_t budget = 16ll<<20; if ( b->ad_cap > budget ) b->ad_cap = budget > 2*b->ad_rec ? budget : 2*b->ad_rec; }
     for (int k=0; k<2; k++) alloc_set(b, &b->set[k], p.output_tags);
     b->cap_ploidy = 8;
     b->ploidy_tab = (uint8_t*) xcalloc((size_t)b->cap_ploidy*S, 1);
@@ -418,7 +426,9 @@ int b200_mcall(b200_call_t *call, const b200_rec_t *rec)
     /* set_ploidy() rewrites call->ploidy between records (vcfcall.c:807-825): each DISTINCT vector is registered once */
     s->ploidy_id[i] = (uint16_t)(call->ploidy ? ploidy_id_of(b, call->ploidy) : 0);
     s->user_in[i] = rec->user;
-    if ( ++s->n == b->cap ) return b->async ? b200_mcall_flush_async(call) : b200_mcall_flush(call);
+    /* full: max_records records, or no room left for a worst-case record */
+    if ( ++s->n == b->cap || b->pl_cap - s->pl_used < b->pl_rec || (b->grouped && b->ad_cap - s->ad_used < b->ad_rec) )
+        return b->async ? b200_mcall_flush_async(call) : b200_mcall_flush(call);
     return 0;
 }
 

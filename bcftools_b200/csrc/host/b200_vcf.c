@@ -28,11 +28,23 @@ int b200_str_putsn(b200_str_t *s, const char *p, size_t n)
     return 0;
 }
 int b200_str_puts(b200_str_t *s, const char *p) { return b200_str_putsn(s, p, strlen(p)); }
-int b200_str_putc(b200_str_t *s, int c) { char ch = (char)c; return b200_str_putsn(s, &ch, 1); }
+int b200_str_putc(b200_str_t *s, int c)
+{
+    if ( s->l + 2 > s->m && str_reserve(s, 1) ) return -1;
+    s->s[s->l++] = (char)c; s->s[s->l] = 0;
+    return 0;
+}
+/*  decimal digits by hand ([htslib] kputw / kputl do the same): a 2,504-sample record prints ~30,000 integers  */
 int b200_str_putw(b200_str_t *s, long long v)
 {
-    char buf[32]; int n = snprintf(buf, sizeof buf, "%lld", v);
-    return b200_str_putsn(s, buf, (size_t)n);
+    char buf[24]; int n = 0;
+    unsigned long long x = v<0 ? 0ull - (unsigned long long)v : (unsigned long long)v;
+    do { buf[n++] = (char)('0' + x % 10); x /= 10; } while ( x );
+    if ( v<0 ) buf[n++] = '-';
+    if ( s->l + (size_t)n + 1 > s->m && str_reserve(s, (size_t)n) ) return -1;
+    while ( n ) s->s[s->l++] = buf[--n];
+    s->s[s->l] = 0;
+    return 0;
 }
 /*  [htslib] kputd: "%g" for |d| outside [1e-4, 999999]; otherwise the first six significant digits of trunc(d*1e10),
  *  rounded half up at the seventh, trailing zeros (and a bare '.') culled.  */
@@ -587,6 +599,14 @@ int b200_vrec_fmt_ints(const b200_vrec_t *r, const char *key, int32_t **dst, int
         while ( *v && k<n )
         {
             if ( *v=='.' && (v[1]==',' || !v[1]) ) { d[k++] = B200_I32_MISSING; v++; }
+            else if ( (unsigned)(*v - '0') < 10u && (unsigned)(v[1] - '0') >= 10u ) { d[k++] = *v - '0'; v++; }        /* one digit: most PL values of a confident call */
+            else if ( (unsigned)(*v - '0') < 10u )                  /* plain digits (what every PL / AD is): no locale, no errno */
+            {
+                long long x = 0; int nd = 0;
+                while ( (unsigned)(*v - '0') < 10u && nd < 18 ) { x = x*10 + (*v - '0'); v++; nd++; }
+                if ( (unsigned)(*v - '0') < 10u ) return -2;
+                d[k++] = x > INT32_MAX ? INT32_MAX : (int32_t)x;
+            }
             else { char *e; long x = strtol(v, &e, 10); if ( e==v ) return -2; d[k++] = (int32_t)x; v = e; }
             if ( *v==',' ) v++; else break;
         }
