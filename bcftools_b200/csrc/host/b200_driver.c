@@ -249,6 +249,37 @@ static int ped_add(lines_t *out, const char *name, char sex)
 }
 
 /*  parse_ped_samples (vcfcall.c:200-261): 1 = PED (out filled), 0 = not PED, <0 error  */
+/*  sample names -> header index without a scan per name (100,000 names would be 1e10 comparisons): an index sorted by name,
+ *  ties by position, and a lower-bound search, so that the FIRST header column of a name is the one found  */
+typedef struct { const char *s; int i; } name_ix_t;
+static int name_ix_cmp(const void *a, const void *b)
+{
+    const name_ix_t *x = (const name_ix_t*)a, *y = (const name_ix_t*)b;
+    const int c = strcmp(x->s, y->s);
+    return c ? c : (x->i > y->i) - (x->i < y->i);
+}
+static name_ix_t *name_index(const char *const *names, int n)
+{
+    name_ix_t *ix = (name_ix_t*) malloc(sizeof(name_ix_t)*(n ? n : 1));
+    if ( !ix ) return NULL;
+    for (int i=0; i<n; i++) { ix[i].s = names[i]; ix[i].i = i; }
+    qsort(ix, n, sizeof(name_ix_t), name_ix_cmp);
+    return ix;
+}
+static int name_find(const name_ix_t *ix, int n, const char *s, size_t len)
+{
+    int lo = 0, hi = n;         /* first entry >= (s,len) */
+    while ( lo < hi )
+    {
+        const int mid = lo + (hi - lo)/2;
+        int c = strncmp(ix[mid].s, s, len);
+        if ( !c && ix[mid].s[len] ) c = 1;
+        if ( c < 0 ) lo = mid + 1; else hi = mid;
+    }
+    if ( lo < n && !strncmp(ix[lo].s, s, len) && !ix[lo].s[len] ) return ix[lo].i;
+    return -1;
+}
+
 static int ped_parse(const lines_t *in, lines_t *out)
 {
     int i;
@@ -309,7 +340,8 @@ int b200_samples_parse(const char *text, const char *const *hdr_samples, int nhd
     const lines_t *L = rc ? &ped : &in;
     rc = 0;
     int *old2new = (int*) malloc(sizeof(int)*(nhdr ? nhdr : 1));
-    if ( !old2new ) { lines_free(&in); lines_free(&ped); return B200_DRV_ENOMEM; }
+    name_ix_t *hdr_ix = name_index(hdr_samples, nhdr);
+    if ( !old2new || !hdr_ix ) { free(old2new); free(hdr_ix); lines_free(&in); lines_free(&ped); return B200_DRV_ENOMEM; }
     const int dflt_sex = ploidy->nsex - 1;                  /* vcfcall.c:288-289 */
     for (i=0; i<nhdr; i++) { sample2sex[i] = dflt_sex; old2new[i] = -1; }
     int n = 0, warn = 0;
@@ -321,8 +353,7 @@ int b200_samples_parse(const char *text, const char *const *hdr_samples, int nhd
         if ( *s0=='#' ) continue;
         const char *e0 = s0;
         while ( *e0 && !isspace((unsigned char)*e0) ) e0++;
-        int ismpl = -1;
-        for (int k=0; k<nhdr; k++) if ( strlen(hdr_samples[k])==(size_t)(e0-s0) && !strncmp(hdr_samples[k], s0, (size_t)(e0-s0)) ) { ismpl = k; break; }
+        const int ismpl = name_find(hdr_ix, nhdr, s0, (size_t)(e0-s0));
         if ( ismpl < 0 ) { warn++; continue; }              /* "Warning: No such sample in the VCF" */
         if ( old2new[ismpl] != -1 ) { warn++; continue; }   /* "Warning: The sample is listed multiple times" */
         const char *s1 = e0;
@@ -347,7 +378,7 @@ int b200_samples_parse(const char *text, const char *const *hdr_samples, int nhd
         old2new[ismpl] = n;
         n++;
     }
-    free(old2new); lines_free(&in); lines_free(&ped);
+    free(old2new); free(hdr_ix); lines_free(&in); lines_free(&ped);
     if ( rc ) return rc;
     *nsel = n;
     if ( nwarn ) *nwarn = warn;
@@ -374,7 +405,8 @@ int b200_groups_parse(const char *text, const char *const *samples, int nsmpl, u
     int *smpl2grp = (int*) calloc(nsmpl ? nsmpl : 1, sizeof(int));        /* group + 1, 0 = not listed */
     char **gname = (char**) calloc(nsmpl ? nsmpl : 1, sizeof(char*));
     uint32_t *cnt = (uint32_t*) calloc(nsmpl ? nsmpl : 1, sizeof(uint32_t));
-    if ( !smpl2grp || !gname || !cnt ) { free(smpl2grp); free(gname); free(cnt); return B200_DRV_ENOMEM; }
+    name_ix_t *smpl_ix = name_index(samples, nsmpl);
+    if ( !smpl2grp || !gname || !cnt || !smpl_ix ) { free(smpl2grp); free(gname); free(cnt); free(smpl_ix); return B200_DRV_ENOMEM; }
     int ng = 0, rc = 0;
     const char *ss = text;
     while ( *ss && !rc )
@@ -398,8 +430,7 @@ int b200_groups_parse(const char *text, const char *const *samples, int nsmpl, u
             /* mcall.c:310-325 leaves ptr on the FIRST character of the population name and keys the hash with ptr+1: groups
                are told apart by the remainder of the line behind that character ("CEU" and "YEU" are one group).  Kept. */
             const char *g = p + 1; size_t gl = (size_t)(le - g);
-            int ismpl = -1;
-            for (i=0; i<nsmpl; i++) if ( strlen(samples[i])==(size_t)(name_end-ss) && !strncmp(samples[i], ss, (size_t)(name_end-ss)) ) { ismpl = i; break; }
+            const int ismpl = name_find(smpl_ix, nsmpl, ss, (size_t)(name_end-ss));
             if ( ismpl >= 0 )
             {
                 if ( smpl2grp[ismpl] )
@@ -431,7 +462,7 @@ int b200_groups_parse(const char *text, const char *const *samples, int nsmpl, u
         *ngroups = ng;
     }
     for (i=0; i<ng; i++) free(gname[i]);
-    free(smpl2grp); free(gname); free(cnt);
+    free(smpl2grp); free(gname); free(cnt); free(smpl_ix);
     return rc;
 }
 
