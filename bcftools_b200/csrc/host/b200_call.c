@@ -273,7 +273,12 @@ void b200_mcall_init(b200_call_t *call)
     b->ad_rec = ((int64_t)S*M + 3) & ~3ll;
     b->pl_cap = (int64_t)R*b->pl_rec;
     b->ad_cap = (int64_t)R*b->ad_rec;
-    { const int64_t budget = 64ll<<20; if ( b->pl_cap > budget ) b->pl_cap = budget > 2*b->pl_rec ? budget : 2*b->pl_rec; }     /* elements */
+    {
+        int64_t budget = 64ll<<20;                          /* elements */
+        const char *e = getenv("B200_PL_SLAB_ELEMS");       /* tests shrink the slab to reach the volume limit with small batches */
+        if ( e && atoll(e) > 0 ) budget = atoll(e);
+        if ( b->pl_cap > budget ) b->pl_cap = budget > 2*b->pl_rec ? budget : 2*b->pl_rec;
+    }
     { const int64_t budget = 16ll<<20; if ( b->ad_cap > budget ) b->ad_cap = budget > 2*b->ad_rec ? budget : 2*b->ad_rec; }
     for (int k=0; k<2; k++) alloc_set(b, &b->set[k], p.output_tags);
     b->cap_ploidy = 8;

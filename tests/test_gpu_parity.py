@@ -609,6 +609,22 @@ def test_async_host_batcher_replays_reference_goldens(name):
     assert golden_util.check_against_expect(case, params, batch, res) == len(case["expect"])
 
 
+@pytest.mark.parametrize("async_flush,groups", [(False, 0), (True, 0), (True, 3)])
+def test_host_batcher_flushes_when_the_slab_is_full(async_flush, groups, oracle_built, monkeypatch):
+    """The pinned PL / AD slabs hold a volume, not max_records worst-case records: a batch is handed over as soon as less than
+    one worst-case record fits.  With the slab shrunk to 40,000 elements (B200_PL_SLAB_ELEMS) 300 records of 200 samples go
+    out in many partial batches; every record must come back, in order, equal to the reference."""
+    from bcftools_b200 import host_call
+    monkeypatch.setenv("B200_PL_SLAB_ELEMS", "40000")
+    S = 200
+    rng = np.random.default_rng([5, int(async_flush), groups])
+    batch = parity.random_batch(rng, 300, S, 5)
+    params = abi.CallParams(S, 5, output_tags=abi.CALL_FMT_GQ, groups=[list(range(k, S, groups)) for k in range(groups)] if groups else None)
+    exp, _ = oracle_built.call(ORACLE(oracle_built), params, batch, None)
+    res = host_call.replay(params, batch, None, max_records=256, async_flush=async_flush)      # 256 x 200 x 15 = 768,000 elements worst case
+    assert parity.compare(res, exp, params)["compared"] > 0
+
+
 @pytest.mark.parametrize("async_flush", [False, True])
 def test_host_batcher_registers_each_distinct_ploidy_vector_once(async_flush, oracle_built):
     """chrX-style alternation (PAR / non-PAR): 1,000 records switch between two ploidy vectors; the batcher must end with
